@@ -1,0 +1,218 @@
+/*
+ * qsv.h — C ABI of the B200-native state-vector engine behind quantr's
+ * `Circuit::simulate` hot path.
+ *
+ * The reference (a-barlow/quantr v0.6.0, pure Rust) has no FFI of its own; the
+ * seam this library replaces is Rust-internal.  Each entry point below names the
+ * reference interface it stands in for (paths relative to the reference root):
+ *
+ *   qsv_create / qsv_destroy     SuperPosition storage owned by SimulatedCircuit
+ *                                (src/simulated_circuit.rs:20-27, src/circuit/states/super_positions.rs:22-25)
+ *   qsv_init_basis               SuperPosition::new_unchecked  (src/circuit/states/super_positions_unchecked.rs:39-46)
+ *                                and ProductState -> SuperPosition registers (src/circuit.rs:463-473)
+ *   qsv_upload                   Circuit::change_register       (src/circuit.rs:463-473)
+ *   qsv_download / qsv_gather    SimulatedCircuit::get_state / take_state (src/simulated_circuit.rs:158-160,185-187)
+ *   qsv_apply                    Circuit::simulate_with_register + Circuit::apply_gate
+ *                                (src/circuit/simulation.rs:21-57, 64-135) over the whole gate list
+ *   qsv_plan_* / qsv_run_plan    the same, split into "lower + schedule" and "launch" so a
+ *                                circuit can be re-run with its schedule resident on the device
+ *                                (SimulatedCircuit::measure_all_without_cache re-simulates per shot,
+ *                                src/simulated_circuit.rs:81-114)
+ *   qsv_sample                   SuperPosition::measure x shots  (src/circuit/states/super_positions.rs:332-342,
+ *                                src/simulated_circuit.rs:63-73,116-130)
+ *   qsv_norm_sqr                 the probability-conservation sums (src/circuit/states/super_positions.rs:236-248)
+ *
+ * Conventions
+ *   - wire q of an n-qubit circuit is bit (n-1-q) of the amplitude index
+ *     (src/circuit/states/product_states.rs:205-215): wire 0 is the MSB.
+ *   - amplitudes are complex f64, interleaved (re, im), 16 bytes each, canonical index order.
+ *   - every function returns 0 on success or a QSV_ERR_* code; the message is
+ *     available from qsv_last_error().  No C++ exception crosses this boundary.
+ *   - pointers passed in are borrowed for the duration of the call only.
+ *   - a handle is not internally synchronised: one call at a time per handle.
+ *   - there is NO CPU fallback: without a usable CUDA device qsv_create fails.
+ */
+#ifndef QSV_H_
+#define QSV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSV_VERSION 100
+
+/* error codes */
+enum {
+    QSV_OK = 0,
+    QSV_ERR_INVALID_ARG = 1,
+    QSV_ERR_OUT_OF_MEMORY = 2,
+    QSV_ERR_CUDA = 3,
+    QSV_ERR_NCCL = 4,
+    QSV_ERR_UNSUPPORTED = 5,
+    QSV_ERR_INTERNAL = 6
+};
+
+/* Gate kinds: the 24 non-Id variants of `enum Gate` (src/circuit/gate.rs:19-106),
+ * in declaration order.  QSV_GATE_ID is accepted and skipped, as in
+ * src/circuit/simulation.rs:38-41. */
+enum {
+    QSV_GATE_ID = 0,
+    QSV_GATE_H = 1,
+    QSV_GATE_X = 2,
+    QSV_GATE_Y = 3,
+    QSV_GATE_Z = 4,
+    QSV_GATE_S = 5,
+    QSV_GATE_SDAG = 6,
+    QSV_GATE_T = 7,
+    QSV_GATE_TDAG = 8,
+    QSV_GATE_RX = 9,      /* param = angle */
+    QSV_GATE_RY = 10,     /* param = angle */
+    QSV_GATE_RZ = 11,     /* param = angle */
+    QSV_GATE_X90 = 12,
+    QSV_GATE_Y90 = 13,
+    QSV_GATE_MX90 = 14,
+    QSV_GATE_MY90 = 15,
+    QSV_GATE_PHASE = 16,  /* param = angle; exp(i*angle/2) * Identity */
+    QSV_GATE_CR = 17,     /* param = angle, controls[0] */
+    QSV_GATE_CRK = 18,    /* iparam = k,    controls[0] */
+    QSV_GATE_CZ = 19,     /* controls[0] */
+    QSV_GATE_CY = 20,     /* controls[0] */
+    QSV_GATE_CNOT = 21,   /* controls[0] */
+    QSV_GATE_SWAP = 22,   /* controls[0] */
+    QSV_GATE_TOFFOLI = 23,/* controls[0], controls[1] */
+    QSV_GATE_CUSTOM = 24, /* controls[0..n_controls), matrix, none_mask */
+    QSV_GATE_KIND_COUNT = 25
+};
+
+/* One non-Id gate as it reaches Circuit::apply_gate: the POD image of
+ * `GateInfo { cat_gate: GateCategory, position }` (src/circuit/gate.rs:243-259).
+ *
+ * Custom gates: the host evaluates the user closure on the 2^k basis states of
+ * the sub-register [controls..., target] (k = n_controls + 1, first control =
+ * MSB of the sub-index; src/circuit/simulation.rs:137-156) and passes
+ *   matrix    : 2^k x 2^k complex f64, row-major, interleaved;
+ *               matrix[(t * 2^k + s) * 2 + {0,1}] = amplitude of output sub-state t
+ *               in the image of input sub-state s (one closure result per column).
+ *   none_mask : 2^k bytes; non-zero where the closure returned None
+ *               ("leave this basis state untouched", src/circuit/simulation.rs:120-133).
+ *               May be NULL (no None results).  Column s of `matrix` is ignored
+ *               where none_mask[s] != 0.
+ */
+typedef struct qsv_op {
+    uint32_t kind;            /* QSV_GATE_* */
+    uint32_t target;          /* wire the gate sits on (`position`) */
+    uint32_t n_controls;
+    uint32_t reserved;        /* must be 0 */
+    const uint32_t* controls; /* wires, reference order */
+    double param;
+    int32_t iparam;
+    int32_t reserved2;        /* must be 0 */
+    const double* matrix;
+    const uint8_t* none_mask;
+} qsv_op;
+
+/* Filled by qsv_apply / qsv_run_plan when non-NULL. */
+typedef struct qsv_stats {
+    uint64_t n_gates;          /* non-Id gates consumed */
+    uint64_t n_passes;         /* fused passes over the local state */
+    uint64_t n_rounds;         /* register rounds summed over passes */
+    uint64_t n_kernel_launches;/* kernels of this library launched by the call */
+    uint64_t bytes_per_pass;   /* algorithmic bytes of one pass: 32 * 2^n_local */
+    uint64_t n_exchanges;      /* global-qubit remaps (sharded handles only) */
+    uint64_t exchange_bytes;   /* bytes sent per rank over all remaps */
+    double device_ms;          /* CUDA-event time of all passes (0 unless timing enabled) */
+    double exchange_ms;        /* CUDA-event time of the remaps */
+} qsv_stats;
+
+typedef struct qsv_state qsv_state; /* opaque */
+typedef struct qsv_plan qsv_plan;   /* opaque */
+
+/* ---- lifetime ---------------------------------------------------------- */
+
+/* Allocates a 2^n_qubits complex-f64 state on CUDA device `device` (HBM) and
+ * sets it to |0...0>.  Fails (QSV_ERR_CUDA) if no device is usable. */
+int qsv_create(qsv_state** out, uint32_t n_qubits, int device);
+
+/* Sharded state: this process owns the 2^(n_qubits - log2(world)) amplitudes
+ * whose top log2(world) index bits equal `rank`.  `nccl_unique_id` is the
+ * 128-byte ncclUniqueId produced by qsv_nccl_unique_id() on rank 0 and
+ * distributed by the caller.  Collective: every rank must call it. */
+int qsv_create_sharded(qsv_state** out, uint32_t n_qubits, int device, int rank, int world,
+                       const void* nccl_unique_id, size_t nccl_unique_id_bytes);
+int qsv_nccl_unique_id(void* out, size_t out_bytes);
+
+int qsv_destroy(qsv_state* s);
+
+/* Thread-local message of the last failed call made with `s` (or with no
+ * handle, e.g. a failed qsv_create, when s == NULL). */
+const char* qsv_last_error(const qsv_state* s);
+
+/* ---- options ----------------------------------------------------------- */
+
+/* key: "tile_bits" (8..13), "low_bits" (contiguous low index bits kept in every
+ * tile, >= 2), "timing" (0/1: record CUDA-event times in qsv_stats),
+ * "fuse" (0: one pass per gate, 1: fused passes). */
+int qsv_set_option(qsv_state* s, const char* key, int64_t value);
+int qsv_get_info(const qsv_state* s, const char* key, int64_t* value);
+
+/* ---- register access --------------------------------------------------- */
+
+/* amp[index] = 1, everything else 0 (index is a canonical, i.e. global, index). */
+int qsv_init_basis(qsv_state* s, uint64_t index);
+
+/* Copies `count` amplitudes starting at canonical index `first` from / to host
+ * memory (interleaved f64).  On a sharded handle the range must lie inside the
+ * rank's shard. */
+int qsv_upload(qsv_state* s, const double* host_amps, uint64_t first, uint64_t count);
+int qsv_download(qsv_state* s, double* host_amps, uint64_t first, uint64_t count);
+
+/* host_amps[2*i..2*i+1] = amplitude at canonical index indices[i]. */
+int qsv_gather(qsv_state* s, const uint64_t* indices, uint64_t count, double* host_amps);
+
+/* ---- simulation -------------------------------------------------------- */
+
+/* Applies ops[0..n_ops) in order (Id entries skipped), exactly as
+ * Circuit::simulate_with_register walks the gate list. */
+int qsv_apply(qsv_state* s, const qsv_op* ops, size_t n_ops, qsv_stats* stats);
+
+/* Lowering + scheduling only (host work, needs no GPU).  `n_local_qubits` is
+ * the shard size (== n_qubits when unsharded). */
+int qsv_plan_create(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubits,
+                    const qsv_op* ops, size_t n_ops, uint32_t tile_bits, uint32_t low_bits,
+                    int fuse);
+int qsv_plan_destroy(qsv_plan* p);
+int qsv_plan_stats(const qsv_plan* p, qsv_stats* stats);
+/* Serialised schedule (for inspection and for the host-side schedule tests):
+ * writes up to `cap` bytes, returns the full size in *size. */
+int qsv_plan_serialize(const qsv_plan* p, void* out, size_t cap, size_t* size);
+const char* qsv_plan_last_error(void);
+
+/* Runs a plan made for this handle's (n_qubits, n_local_qubits).  The first
+ * run uploads the schedule to the device; later runs reuse it. */
+int qsv_run_plan(qsv_state* s, qsv_plan* p, qsv_stats* stats);
+
+/* ---- measurement ------------------------------------------------------- */
+
+/* For each uniform u in [0,1): the first canonical index i with
+ * u < sum_{j<=i} |amp_j|^2, or UINT64_MAX if u >= total ("failed to collapse",
+ * src/circuit/states/super_positions.rs:341).  The caller draws the uniforms
+ * (fastrand::f64() per shot in the reference, src/circuit/states/super_positions.rs:334). */
+int qsv_sample(qsv_state* s, const double* uniforms, uint64_t shots, uint64_t* out_indices);
+
+/* sum |amp|^2 over the local state (sharded: over all ranks). */
+int qsv_norm_sqr(qsv_state* s, double* out);
+
+/* Blocks until all work queued on the handle's stream has finished. */
+int qsv_synchronize(qsv_state* s);
+
+/* Raw device pointer / stream of the handle, for callers that time with their
+ * own CUDA events or wrap the memory (no ownership transfer). */
+int qsv_device_pointer(qsv_state* s, void** dev_ptr, void** cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSV_H_ */

@@ -1,0 +1,453 @@
+"""`Circuit` / `SimulatedCircuit`: host-side mirror of quantr's public API over the C ABI.
+
+The builder (column layout, validation) follows src/circuit.rs:48-473 and stays on the
+host; `simulate` encodes the gate list and hands it to libqsv.so (`qsv_apply`), which
+replaces src/circuit/simulation.rs.  `SimulatedCircuit` keeps the device handle and a
+lazily downloaded host mirror, replacing the `register: SuperPosition` field of
+src/simulated_circuit.rs:20-27.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+from . import _ffi as F
+from .error import QuantrError
+from .gate import Gate
+from .states import ProductState, SuperPosition, into_super_position
+
+_rng = np.random.default_rng()
+
+
+def seed(value: int):
+    """Seeds the host RNG that draws the per-shot uniforms (the reference's `fastrand::seed`)."""
+    global _rng
+    _rng = np.random.default_rng(value)
+
+
+class Measurement:
+    """measurement.rs:16-28"""
+
+    __slots__ = ("kind", "value")
+
+    def __init__(self, kind, value):
+        self.kind = kind
+        self.value = value
+
+    @staticmethod
+    def Observable(value):
+        return Measurement("Observable", value)
+
+    @staticmethod
+    def NonObservable(value):
+        return Measurement("NonObservable", value)
+
+    def take(self):
+        return self.value
+
+
+# ---- gate list -> qsv_op[] ---------------------------------------------------------------------
+
+class EncodedOps:
+    """qsv_op array plus the buffers it points into."""
+
+    def __init__(self, ops, keep, positions):
+        self.ops = ops
+        self.keep = keep
+        self.positions = positions  # (flat index, wire) of every non-Id gate
+        self.n_ops = len(ops)
+
+    @property
+    def nbytes(self) -> int:
+        return C.sizeof(self.ops) + sum(getattr(k, "nbytes", 0) for k in self.keep)
+
+
+def expand_custom(gate: Gate):
+    """Evaluates a Custom closure on the 2^k basis states of [controls..., target]
+    (src/circuit/simulation.rs:137-156) -> (matrix[2^k, 2^k] complex, none_mask[2^k])."""
+    k = len(gate.controls) + 1
+    dim = 1 << k
+    matrix = np.zeros((dim, dim), dtype=np.complex128)
+    none = np.zeros(dim, dtype=np.uint8)
+    for s in range(dim):
+        image = gate.func(ProductState.binary_basis(s, k))
+        if image is None:
+            none[s] = 1
+            continue
+        image = into_super_position(image)
+        if image.get_dimension() != dim:
+            raise QuantrError(
+                f"The custom gate {gate.name!r} returned a superposition of dimension {image.get_dimension()} "
+                f"for a {k}-qubit input; it must have dimension {dim}."
+            )
+        matrix[:, s] = image.get_amplitudes()
+    return matrix, none
+
+
+def encode_gates(circuit_gates, num_qubits) -> EncodedOps:
+    """Walks the flat gate vector exactly like src/circuit/simulation.rs:37-56."""
+    entries = []
+    for counter, gate in enumerate(circuit_gates):
+        if gate.kind == F.GATE_ID:
+            continue
+        entries.append((counter, counter % num_qubits, gate))
+    ops = (F.QsvOp * max(1, len(entries)))()
+    keep = []
+    positions = []
+    for i, (counter, wire, gate) in enumerate(entries):
+        op = ops[i]
+        op.kind = gate.kind
+        op.target = wire
+        op.n_controls = len(gate.controls)
+        op.param = gate.param
+        op.iparam = gate.iparam
+        if gate.controls:
+            ctrl = (C.c_uint32 * len(gate.controls))(*gate.controls)
+            keep.append(ctrl)
+            op.controls = ctrl
+        if gate.kind == F.GATE_CUSTOM:
+            matrix, none = expand_custom(gate)
+            matrix = np.ascontiguousarray(matrix)
+            keep.extend([matrix, none])
+            op.matrix = matrix.ctypes.data_as(C.POINTER(C.c_double))
+            op.none_mask = none.ctypes.data_as(C.POINTER(C.c_uint8))
+        positions.append((counter, wire))
+    enc = EncodedOps(ops, keep, positions)
+    enc.n_ops = len(entries)
+    return enc
+
+
+# ---- device handle -----------------------------------------------------------------------------
+
+def default_device() -> int:
+    return int(os.environ.get("QSV_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+class DeviceState:
+    """Owns a `qsv_state*` (freed on drop, like the Rust shim's `Drop`)."""
+
+    def __init__(self, n_qubits: int, device: int | None = None, *, rank: int = 0, world: int = 1, nccl_id: bytes | None = None):
+        self.lib = F.load_library()
+        self.n_qubits = n_qubits
+        self.handle = C.c_void_p()
+        dev = default_device() if device is None else device
+        if world > 1:
+            buf = C.create_string_buffer(nccl_id, len(nccl_id))
+            code = self.lib.qsv_create_sharded(C.byref(self.handle), n_qubits, dev, rank, world, buf, len(nccl_id))
+        else:
+            code = self.lib.qsv_create(C.byref(self.handle), n_qubits, dev)
+        F.check(code, None)
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.qsv_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    __del__ = close
+
+    def set_option(self, key: str, value: int):
+        F.check(self.lib.qsv_set_option(self.handle, key.encode(), value), self.handle)
+
+    def get_info(self, key: str) -> int:
+        out = C.c_int64()
+        F.check(self.lib.qsv_get_info(self.handle, key.encode(), C.byref(out)), self.handle)
+        return out.value
+
+    def init_basis(self, index: int = 0):
+        F.check(self.lib.qsv_init_basis(self.handle, index), self.handle)
+
+    def upload(self, amps: np.ndarray, first: int = 0):
+        a = np.ascontiguousarray(amps, dtype=np.complex128)
+        F.check(self.lib.qsv_upload(self.handle, a.ctypes.data_as(C.POINTER(C.c_double)), first, a.shape[0]), self.handle)
+
+    def download(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        if count is None:
+            count = (1 << self.n_qubits) - first
+        out = np.empty(count, dtype=np.complex128)
+        F.check(self.lib.qsv_download(self.handle, out.ctypes.data_as(C.POINTER(C.c_double)), first, count), self.handle)
+        return out
+
+    def gather(self, indices) -> np.ndarray:
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        out = np.empty(idx.shape[0], dtype=np.complex128)
+        F.check(self.lib.qsv_gather(self.handle, idx.ctypes.data_as(C.POINTER(C.c_uint64)), idx.shape[0],
+                                    out.ctypes.data_as(C.POINTER(C.c_double))), self.handle)
+        return out
+
+    def apply(self, enc: EncodedOps) -> dict:
+        stats = F.QsvStats()
+        F.check(self.lib.qsv_apply(self.handle, enc.ops, enc.n_ops, C.byref(stats)), self.handle)
+        return stats.as_dict()
+
+    def run_plan(self, plan: "Plan") -> dict:
+        stats = F.QsvStats()
+        F.check(self.lib.qsv_run_plan(self.handle, plan.handle, C.byref(stats)), self.handle)
+        return stats.as_dict()
+
+    def sample(self, uniforms: np.ndarray) -> np.ndarray:
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        out = np.empty(u.shape[0], dtype=np.uint64)
+        F.check(self.lib.qsv_sample(self.handle, u.ctypes.data_as(C.POINTER(C.c_double)), u.shape[0],
+                                    out.ctypes.data_as(C.POINTER(C.c_uint64))), self.handle)
+        return out
+
+    def norm_sqr(self) -> float:
+        out = C.c_double()
+        F.check(self.lib.qsv_norm_sqr(self.handle, C.byref(out)), self.handle)
+        return out.value
+
+    def synchronize(self):
+        F.check(self.lib.qsv_synchronize(self.handle), self.handle)
+
+
+class Plan:
+    """A lowered + scheduled circuit (`qsv_plan*`).  Host-only to build."""
+
+    def __init__(self, n_qubits: int, enc: EncodedOps, *, n_local: int | None = None, tile_bits: int = 0, low_bits: int = 0, fuse: bool = True):
+        self.lib = F.load_library()
+        self.handle = C.c_void_p()
+        self.enc = enc
+        F.check_plan(self.lib.qsv_plan_create(C.byref(self.handle), n_qubits, n_qubits if n_local is None else n_local,
+                                              enc.ops, enc.n_ops, tile_bits, low_bits, 1 if fuse else 0))
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.qsv_plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    __del__ = close
+
+    def stats(self) -> dict:
+        s = F.QsvStats()
+        F.check_plan(self.lib.qsv_plan_stats(self.handle, C.byref(s)))
+        return s.as_dict()
+
+    def describe(self) -> dict:
+        import json
+        size = C.c_size_t()
+        F.check_plan(self.lib.qsv_plan_serialize(self.handle, None, 0, C.byref(size)))
+        buf = C.create_string_buffer(size.value)
+        F.check_plan(self.lib.qsv_plan_serialize(self.handle, buf, size.value, C.byref(size)))
+        return json.loads(buf.raw[: size.value].decode())
+
+
+# ---- Circuit -----------------------------------------------------------------------------------
+
+class Circuit:
+    """src/circuit.rs:27-474"""
+
+    def __init__(self, num_qubits: int):
+        if num_qubits == 0:  # circuit.rs:48-54
+            raise QuantrError("The initialised circuit must have at least one wire.")
+        self.circuit_gates: list[Gate] = []
+        self.num_qubits = num_qubits
+        self.register: SuperPosition | None = None
+        self.config_progress = False
+
+    @staticmethod
+    def new(num_qubits: int) -> "Circuit":
+        return Circuit(num_qubits)
+
+    def get_num_qubits(self) -> int:
+        return self.num_qubits
+
+    def set_print_progress(self, progress: bool):
+        self.config_progress = progress
+
+    def get_gates(self):
+        return self.circuit_gates
+
+    def add_gate(self, gate: Gate, position: int) -> "Circuit":  # circuit.rs:124
+        return self.add_gates_with_positions({position: gate})
+
+    def add_gates_with_positions(self, gates_with_positions: dict) -> "Circuit":  # circuit.rs:152-188
+        for key in gates_with_positions:
+            if key >= self.num_qubits:
+                raise QuantrError(f"The position, {key}, is out of bounds for the circuit with {self.num_qubits} qubits.")
+        gates_to_add = [gates_with_positions.get(row, Gate.Id) for row in range(self.num_qubits)]
+        self._has_overlapping_controls_and_target(gates_to_add, self.num_qubits)
+        self.circuit_gates.extend(self._push_multi_gates(gates_to_add))
+        return self
+
+    def add_gates(self, gates) -> "Circuit":  # circuit.rs:210-226
+        gates = list(gates)
+        if len(gates) != self.num_qubits:
+            raise QuantrError(
+                f"The number of gates, {len(gates)}, does not match the number of wires, {self.num_qubits}. All wires must have gates added."
+            )
+        self._has_overlapping_controls_and_target(gates, self.num_qubits)
+        self.circuit_gates.extend(self._push_multi_gates(gates))
+        return self
+
+    @staticmethod
+    def _push_multi_gates(gates):  # circuit.rs:230-270
+        for gate in gates:
+            if gate.kind == F.GATE_CUSTOM and not gate.name.isascii():
+                raise QuantrError(
+                    f"The custom function name, {gate.name}, does not only use ASCII chars. This could lead to problems in "
+                    "printing the circuit diagram. This warning will be promoted to an Error in the next major release."
+                )
+        non_id = sum(1 for g in gates if g.kind != F.GATE_ID)
+        if non_id < 2:
+            return list(gates)
+        gates = list(gates)
+        extended = []
+        for pos, gate in enumerate(gates):
+            if not gate.is_single_gate():
+                column = [Gate.Id] * len(gates)
+                column[pos] = gate
+                extended.extend(column)
+                gates[pos] = Gate.Id
+        return gates + extended
+
+    @staticmethod
+    def _contains_repeating_values(num_qubits, array) -> bool:  # circuit.rs:296-305
+        seen = [False] * num_qubits
+        for j in array:
+            if seen[j]:
+                return True
+            seen[j] = True
+        return False
+
+    @classmethod
+    def _has_overlapping_controls_and_target(cls, gates, circuit_size):  # circuit.rs:272-293
+        for pos, gate in enumerate(gates):
+            nodes = gate.get_nodes()
+            if nodes is None:
+                continue
+            for node in nodes:  # (the reference indexes a counter first and would panic; same outcome: an error)
+                if node >= circuit_size:
+                    raise QuantrError(f"The control node at position {node}, is greater than the umnber of qubits {circuit_size}.")
+            if cls._contains_repeating_values(circuit_size, nodes):
+                raise QuantrError(f"The gate, {gate!r}, has overlapping control nodes.")
+            if pos in nodes:
+                raise QuantrError(f"The gate, {gate!r}, has a control node that equals the gate's position {pos}.")
+
+    def add_repeating_gate(self, gate: Gate, positions) -> "Circuit":  # circuit.rs:324-341
+        for p in positions:
+            if p >= self.num_qubits:
+                raise QuantrError(f"The position, {p}, is out of bounds for the circuit with {self.num_qubits} qubits.")
+        if self._contains_repeating_values(self.num_qubits, positions):
+            raise QuantrError(
+                f"Attempted to add more than one gate onto a single wire. The positions in {list(positions)} must all differ."
+            )
+        gates = [Gate.Id] * self.num_qubits
+        for pos in positions:
+            gates[pos] = gate
+        return self.add_gates(gates)
+
+    def change_register(self, super_pos) -> "Circuit":  # circuit.rs:463-473
+        super_pos = into_super_position(super_pos)
+        if super_pos.product_dim != self.num_qubits:
+            raise QuantrError(
+                f"The custom register has a product state dimension of {super_pos.product_dim}, while the number of qubits is "
+                f"{self.num_qubits}. These must equal each other."
+            )
+        self.register = super_pos
+        return self
+
+    # -- the hot path ------------------------------------------------------------------------
+    def _simulate(self, gates, register) -> "SimulatedCircuit":
+        enc = encode_gates(gates, self.num_qubits)
+        if self.config_progress:  # simulation.rs:32-34,45-47,183-200
+            print("Starting circuit simulation...")
+            for counter, wire in enc.positions:
+                print(f"Applying {gates[counter]!r} on wire {wire} # {counter + 1}/{len(gates)} ")
+                if counter + 1 == len(gates):
+                    print("Finished circuit simulation.")
+        state = DeviceState(self.num_qubits)
+        if register is None:
+            state.init_basis(0)  # SuperPosition::new_unchecked, super_positions_unchecked.rs:39-46
+        else:
+            state.upload(register.get_amplitudes())
+        stats = state.apply(enc)
+        return SimulatedCircuit(gates, self.num_qubits, state, self.config_progress, stats)
+
+    def simulate(self) -> "SimulatedCircuit":  # circuit.rs:364-388 (consumes the circuit)
+        register, self.register = self.register, None
+        gates, self.circuit_gates = self.circuit_gates, []
+        return self._simulate(gates, register)
+
+    def clone_and_simulate(self) -> "SimulatedCircuit":  # circuit.rs:411-435
+        return self._simulate(list(self.circuit_gates), self.register)
+
+
+class SimulatedCircuit:
+    """src/simulated_circuit.rs:20-188 with the register held in HBM."""
+
+    def __init__(self, circuit_gates, num_qubits, state: DeviceState, config_progress: bool, stats: dict | None = None):
+        self.circuit_gates = circuit_gates
+        self.num_qubits = num_qubits
+        self.config_progress = config_progress
+        self.disable_warnings = False
+        self.stats = stats or {}
+        self._state = state
+        self._host: SuperPosition | None = None
+
+    def _bin_samples(self, indices, bin_count):
+        for idx in indices:
+            idx = int(idx)
+            if idx == F.UINT64_MAX:  # add_to_bin, simulated_circuit.rs:116-130
+                if not self.disable_warnings:
+                    print("\x1b[93m[Quantr Warning] The superposition failed to collapse to a state during repeat measurements. "
+                          "This is likely due to the use of Gate::Custom where the mapping is not unitary.\x1b[0m", file=sys.stderr)
+                continue
+            key = ProductState.binary_basis(idx, self.num_qubits)
+            bin_count[key] = bin_count.get(key, 0) + 1
+
+    def measure_all(self, shots: int) -> Measurement:  # simulated_circuit.rs:63-73
+        if any(g.is_custom_gate() for g in self.circuit_gates) and not self.disable_warnings:
+            print("\x1b[93m[Quantr Warning] Custom gates were detected in the circuit. Measurements will be taken from a cached "
+                  "register in memory, and so if the Custom gate does NOT implement a unitary mapping, the measure_all method will "
+                  "most likely lead to wrong results. To simulate a circuit without cache, see "
+                  "SimulatedCircuit::measure_all_without_cache.\x1b[0m", file=sys.stderr)
+        bin_count: dict = {}
+        uniforms = _rng.random(shots)  # one f64 in [0,1) per shot, in shot order (super_positions.rs:334)
+        self._bin_samples(self._state.sample(uniforms), bin_count)
+        return Measurement.Observable(bin_count)
+
+    def measure_all_without_cache(self, shots: int) -> Measurement:  # simulated_circuit.rs:81-114
+        bin_count: dict = {}
+        self._bin_samples(self._state.sample(_rng.random(1)), bin_count)
+        if self.config_progress:
+            print(f"Measured state # 1/{shots}")
+        for i in range(shots - 1):
+            if self.config_progress:
+                print("Register reset to zero state")
+            enc = encode_gates(self.circuit_gates, self.num_qubits)  # Custom closures are evaluated again per shot
+            self._state.init_basis(0)
+            self._state.apply(enc)
+            self._host = None
+            self._bin_samples(self._state.sample(_rng.random(1)), bin_count)
+            if self.config_progress:
+                print(f"Measured state # {i + 2}/{shots}")
+        return Measurement.Observable(bin_count)
+
+    def get_state(self) -> Measurement:  # simulated_circuit.rs:158-160
+        if self._host is None:
+            self._host = SuperPosition._raw(self._state.download(), self.num_qubits)
+        return Measurement.NonObservable(self._host)
+
+    def take_state(self) -> Measurement:  # simulated_circuit.rs:185-187
+        m = self.get_state()
+        self._state.close()
+        return m
+
+    def print_warnings(self, printing: bool):  # simulated_circuit.rs:163-165 (sets disable_warnings = printing, as upstream)
+        self.disable_warnings = printing
+
+    def get_circuit_gates(self):
+        return self.circuit_gates
+
+    def get_num_qubits(self) -> int:
+        return self.num_qubits
+
+    def set_print_progress(self, printing: bool):
+        self.config_progress = printing
+
+    def device_state(self) -> DeviceState:
+        """Escape hatch for large states: range downloads, gathers and sampling without a host copy."""
+        return self._state

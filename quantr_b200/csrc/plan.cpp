@@ -1,0 +1,508 @@
+// plan.cpp — gate lowering, diagonal merging and the fusion scheduler (host, no CUDA).
+//
+// Reference behaviour being encoded:
+//   gate walk / order             src/circuit/simulation.rs:37-56
+//   gate -> positions dispatch    src/circuit/gate.rs:140-168, src/circuit/simulation.rs:75-112
+//   gate columns (the matrices)   src/circuit/standard_gate_ops.rs:37-267
+//   Custom None rule              src/circuit/simulation.rs:120-133
+#include "plan.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <sstream>
+#include <stdexcept>
+
+#include "pass_core.h"
+
+namespace qsv {
+
+void host_sincospi(double x, double* s, double* c) { sincospi_hd(x, s, c); }
+
+uint64_t LOp::support() const {
+    uint64_t m = 0;
+    if (kind == MAT) m = cmask | (1ull << target);
+    else if (kind == DIAG) { m = cmask; for (auto& t : lin) m |= 1ull << t.first; }
+    else for (int b : bits) m |= 1ull << b;
+    return m;
+}
+uint64_t LOp::targets() const {
+    uint64_t m = 0;
+    if (kind == MAT) m = 1ull << target;
+    else if (kind == DENSE) for (int b : bits) m |= 1ull << b;
+    return m;
+}
+
+namespace {
+
+[[noreturn]] void fail(const std::string& msg) { throw std::runtime_error(msg); }
+
+LOp make_mat(uint32_t src, OpType t, int target, uint64_t cmask, double m00r, double m00i, double m01r, double m01i,
+             double m10r, double m10i, double m11r, double m11i) {
+    LOp o;
+    o.kind = LOp::MAT; o.src_gate = src; o.mtype = t; o.target = target; o.cmask = cmask;
+    const double mm[8] = {m00r, m00i, m01r, m01i, m10r, m10i, m11r, m11i};
+    memcpy(o.m, mm, sizeof(mm));
+    return o;
+}
+LOp make_xswap(uint32_t src, int target, uint64_t cmask) { return make_mat(src, OP_MAT_XSWAP, target, cmask, 0, 0, 1, 0, 1, 0, 0, 0); }
+LOp make_diag(uint32_t src, uint64_t cmask, double theta0, std::vector<std::pair<int, double>> lin) {
+    LOp o;
+    o.kind = LOp::DIAG; o.src_gate = src; o.cmask = cmask; o.theta0 = theta0; o.lin = std::move(lin);
+    return o;
+}
+
+int expected_controls(uint32_t kind) {
+    if (kind == QSV_GATE_TOFFOLI) return 2;
+    if (kind >= QSV_GATE_CR && kind <= QSV_GATE_SWAP) return 1;
+    if (kind == QSV_GATE_CUSTOM) return -1;
+    return 0;
+}
+
+}  // namespace
+
+void lower_gates(uint32_t n, const qsv_op* ops, size_t n_ops, std::vector<LOp>& out, uint64_t* n_gates) {
+    if (n == 0 || n > 62) fail("n_qubits must be in 1..62");
+    if (n_ops && !ops) fail("ops is NULL");
+    uint64_t gates = 0;
+    const double S2 = 0.70710678118654752440;  // FRAC_1_SQRT_2
+    for (size_t g = 0; g < n_ops; ++g) {
+        const qsv_op& op = ops[g];
+        if (op.kind == QSV_GATE_ID) continue;  // simulation.rs:38-41
+        std::ostringstream where;
+        where << "op " << g << ": ";
+        if (op.kind >= QSV_GATE_KIND_COUNT) fail(where.str() + "unknown gate kind");
+        if (op.target >= n) fail(where.str() + "target wire out of range");
+        const int want = expected_controls(op.kind);
+        if (want >= 0 && (int)op.n_controls != want) fail(where.str() + "wrong number of control wires for this gate kind");
+        if (op.n_controls && !op.controls) fail(where.str() + "controls is NULL");
+        if (op.n_controls > 20) fail(where.str() + "too many control wires");
+        for (uint32_t i = 0; i < op.n_controls; ++i) {
+            if (op.controls[i] >= n) fail(where.str() + "control wire out of range");
+            if (op.controls[i] == op.target) fail(where.str() + "control wire equals the gate's position");  // circuit.rs:272-293
+            for (uint32_t j = 0; j < i; ++j)
+                if (op.controls[i] == op.controls[j]) fail(where.str() + "overlapping control wires");
+        }
+        ++gates;
+        const uint32_t src = (uint32_t)g;
+        const int t = (int)(n - 1 - op.target);
+        const int c0 = op.n_controls > 0 ? (int)(n - 1 - op.controls[0]) : -1;
+        const int c1 = op.n_controls > 1 ? (int)(n - 1 - op.controls[1]) : -1;
+        const uint64_t cm0 = c0 >= 0 ? (1ull << c0) : 0, cm1 = c1 >= 0 ? (1ull << c1) : 0;
+        switch (op.kind) {
+            case QSV_GATE_H: out.push_back(make_mat(src, OP_MAT_REAL, t, 0, S2, 0, S2, 0, S2, 0, -S2, 0)); break;
+            case QSV_GATE_X: out.push_back(make_xswap(src, t, 0)); break;
+            case QSV_GATE_Y: out.push_back(make_mat(src, OP_MAT_ANTIDIAG, t, 0, 0, 0, 0, -1, 0, 1, 0, 0)); break;
+            case QSV_GATE_Z: out.push_back(make_diag(src, 0, 0, {{t, 1.0}})); break;
+            case QSV_GATE_S: out.push_back(make_diag(src, 0, 0, {{t, 0.5}})); break;
+            case QSV_GATE_SDAG: out.push_back(make_diag(src, 0, 0, {{t, -0.5}})); break;
+            case QSV_GATE_T: out.push_back(make_diag(src, 0, 0, {{t, 0.25}})); break;
+            case QSV_GATE_TDAG: out.push_back(make_diag(src, 0, 0, {{t, -0.25}})); break;
+            case QSV_GATE_RX: {
+                const double c = cos(0.5 * op.param), s = sin(0.5 * op.param);
+                out.push_back(make_mat(src, OP_MAT_GENERAL, t, 0, c, 0, 0, -s, 0, -s, c, 0));
+                break;
+            }
+            case QSV_GATE_RY: {
+                const double c = cos(0.5 * op.param), s = sin(0.5 * op.param);
+                out.push_back(make_mat(src, OP_MAT_REAL, t, 0, c, 0, -s, 0, s, 0, c, 0));
+                break;
+            }
+            case QSV_GATE_RZ: out.push_back(make_diag(src, 0, -0.5 * op.param / M_PI, {{t, op.param / M_PI}})); break;
+            case QSV_GATE_PHASE: out.push_back(make_diag(src, 0, 0.5 * op.param / M_PI, {})); break;
+            case QSV_GATE_X90: out.push_back(make_mat(src, OP_MAT_ANTIDIAG, t, 0, 0, 0, 0, -1, 0, -1, 0, 0)); break;
+            case QSV_GATE_MX90: out.push_back(make_mat(src, OP_MAT_ANTIDIAG, t, 0, 0, 0, 0, 1, 0, 1, 0, 0)); break;
+            case QSV_GATE_Y90: out.push_back(make_mat(src, OP_MAT_ANTIDIAG, t, 0, 0, 0, 1, 0, -1, 0, 0, 0)); break;
+            case QSV_GATE_MY90: out.push_back(make_mat(src, OP_MAT_ANTIDIAG, t, 0, 0, 0, -1, 0, 1, 0, 0, 0)); break;
+            case QSV_GATE_CR: out.push_back(make_diag(src, 1ull << t, 0, {{c0, op.param / M_PI}})); break;
+            case QSV_GATE_CRK: out.push_back(make_diag(src, 1ull << t, 0, {{c0, ldexp(1.0, 1 - op.iparam)}})); break;
+            case QSV_GATE_CZ: out.push_back(make_diag(src, 1ull << t, 0, {{c0, 1.0}})); break;
+            case QSV_GATE_CY: out.push_back(make_mat(src, OP_MAT_ANTIDIAG, t, cm0, 0, 0, 0, -1, 0, 1, 0, 0)); break;
+            case QSV_GATE_CNOT: out.push_back(make_xswap(src, t, cm0)); break;
+            case QSV_GATE_SWAP:
+                out.push_back(make_xswap(src, t, cm0));
+                out.push_back(make_xswap(src, c0, 1ull << t));
+                out.push_back(make_xswap(src, t, cm0));
+                break;
+            case QSV_GATE_TOFFOLI: out.push_back(make_xswap(src, t, cm0 | cm1)); break;
+            case QSV_GATE_CUSTOM: {
+                if (!op.matrix) fail(where.str() + "Custom gate without a matrix");
+                const uint32_t k = op.n_controls + 1;
+                if (k > (uint32_t)kMaxTileBits) fail(where.str() + "Custom gates on more than 13 wires are not supported");
+                const uint64_t dim = 1ull << k;
+                LOp o;
+                o.kind = LOp::DENSE; o.src_gate = src;
+                for (uint32_t i = 0; i < op.n_controls; ++i) o.bits.push_back((int)(n - 1 - op.controls[i]));
+                o.bits.push_back(t);
+                o.rowptr.assign(dim + 1, 0);
+                for (uint64_t r = 0; r < dim; ++r) {
+                    const bool none_r = op.none_mask && op.none_mask[r];
+                    for (uint64_t s = 0; s < dim; ++s) {
+                        cplx v;
+                        if (none_r) v = cplx{r == s ? 1.0 : 0.0, 0.0};  // untouched state keeps its own amplitude (overwrite)
+                        else if (op.none_mask && op.none_mask[s]) v = cplx{0.0, 0.0};
+                        else v = cplx{op.matrix[(r * dim + s) * 2], op.matrix[(r * dim + s) * 2 + 1]};
+                        if (v.x == 0.0 && v.y == 0.0) continue;
+                        o.cols.push_back((uint32_t)s);
+                        o.vals.push_back(v);
+                    }
+                    o.rowptr[r + 1] = (uint32_t)o.cols.size();
+                }
+                out.push_back(std::move(o));
+                break;
+            }
+            default: fail(where.str() + "unhandled gate kind");
+        }
+    }
+    if (n_gates) *n_gates = gates;
+}
+
+// A diagonal op commutes with every other diagonal op and with any op that has no *target*
+// in its support; pull it back to the nearest earlier diagonal with the same control mask.
+void merge_diagonals(std::vector<LOp>& lops) {
+    std::vector<char> dead(lops.size(), 0);
+    for (size_t i = 0; i < lops.size(); ++i) {
+        if (lops[i].kind != LOp::DIAG) continue;
+        const uint64_t sup = lops[i].support();
+        const size_t lo = i > 512 ? i - 512 : 0;
+        for (size_t j = i; j-- > lo;) {
+            if (dead[j]) continue;
+            LOp& p = lops[j];
+            if (p.kind == LOp::DIAG) {
+                if (p.cmask != lops[i].cmask) continue;
+                p.theta0 += lops[i].theta0;
+                for (auto& t : lops[i].lin) {
+                    bool found = false;
+                    for (auto& q : p.lin) if (q.first == t.first) { q.second += t.second; found = true; break; }
+                    if (!found) p.lin.push_back(t);
+                }
+                dead[i] = 1;
+                break;
+            }
+            if (p.targets() & sup) break;
+        }
+    }
+    std::vector<LOp> kept;
+    kept.reserve(lops.size());
+    for (size_t i = 0; i < lops.size(); ++i)
+        if (!dead[i]) kept.push_back(std::move(lops[i]));
+    lops.swap(kept);
+}
+
+namespace {
+
+struct RoundB {
+    bool dense = false;
+    std::vector<int> reg;      // physical bits held in registers (targets first, then filler)
+    std::vector<size_t> ops;   // indices into lops
+};
+struct PassB {
+    uint64_t req = 0;          // physical bits that must be tile bits
+    bool relaxed_low = false;  // a wide Custom gate took the low passenger bits
+    std::vector<RoundB> rounds;
+    size_t n_ops = 0;
+    bool empty() const { return rounds.empty(); }
+};
+
+int popcnt(uint64_t v) { return __builtin_popcountll(v); }
+
+std::vector<Seg> runs_to_segs(const std::vector<int>& phys_sorted) {
+    std::vector<Seg> segs;
+    size_t i = 0;
+    while (i < phys_sorted.size()) {
+        size_t j = i + 1;
+        while (j < phys_sorted.size() && phys_sorted[j] == phys_sorted[j - 1] + 1) ++j;
+        segs.push_back(Seg{(uint8_t)i, (uint8_t)(j - i), (uint8_t)phys_sorted[i], 0});
+        i = j;
+    }
+    return segs;
+}
+
+template <class T>
+size_t append(std::vector<uint8_t>& blob, const T* data, size_t count) {
+    while (blob.size() % 16) blob.push_back(0);
+    const size_t off = blob.size();
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(data);
+    blob.insert(blob.end(), p, p + sizeof(T) * count);
+    return off;
+}
+
+cplx unit_phase(double half_turns) {
+    cplx r;
+    sincospi_hd(half_turns, &r.y, &r.x);
+    return r;
+}
+
+void emit_pass(Plan& plan, const PassB& pb) {
+    const int T = std::min<int>(plan.opt.tile_bits, (int)plan.n_alloc);
+    const int nloc = (int)plan.n_alloc;
+    // tile bits = required bits + lowest free bits
+    uint64_t tile_mask = pb.req;
+    for (int b = 0; b < nloc && popcnt(tile_mask) < T; ++b) tile_mask |= 1ull << b;
+    if (popcnt(tile_mask) != T) fail("internal: tile bit count");
+    std::vector<int> tile_phys, ext_phys;
+    for (int b = 0; b < nloc; ++b) ((tile_mask >> b) & 1 ? tile_phys : ext_phys).push_back(b);
+    std::vector<int> local_of(64, -1);
+    for (size_t i = 0; i < tile_phys.size(); ++i) local_of[tile_phys[i]] = (int)i;
+
+    DevPass hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    hdr.magic = kPassMagic;
+    hdr.tile_bits = (uint32_t)T;
+    hdr.n_tiles = 1ull << (nloc - T);
+    auto tsegs = runs_to_segs(tile_phys), esegs = runs_to_segs(ext_phys);
+    if (tsegs.size() > (size_t)kMaxSegs || esegs.size() > (size_t)kMaxSegs) fail("internal: too many tile segments");
+    hdr.n_tile_segs = (uint32_t)tsegs.size();
+    hdr.n_ext_segs = (uint32_t)esegs.size();
+    for (size_t i = 0; i < tsegs.size(); ++i) hdr.tile_segs[i] = tsegs[i];
+    for (size_t i = 0; i < esegs.size(); ++i) hdr.ext_segs[i] = esegs[i];
+
+    std::vector<DevRound> rounds;
+    std::vector<DevOp> ops;
+    std::vector<uint8_t> aux;  // appended after header/rounds/ops; offsets fixed up below
+    struct Fix { size_t op; int field; };  // field: 0 ext_off, 1 tbl_off, 2 dense_off
+    std::vector<Fix> fixes;
+    std::vector<std::pair<size_t, std::vector<size_t>>> dense_fix;  // aux offset of DevDense -> needs internal fix
+    uint32_t n_diag = 0;
+
+    for (const RoundB& rb : pb.rounds) {
+        DevRound dr;
+        memset(&dr, 0, sizeof(dr));
+        dr.first_op = (uint32_t)ops.size();
+        if (rb.dense) {
+            dr.type = ROUND_DENSE;
+            dr.n_ops = 1;
+            const LOp& lop = plan.lops[rb.ops[0]];
+            DevOp dop;
+            memset(&dop, 0, sizeof(dop));
+            dop.type = OP_DENSE;
+            DevDense dd;
+            memset(&dd, 0, sizeof(dd));
+            dd.k = (uint32_t)lop.bits.size();
+            for (size_t e = 0; e < lop.bits.size(); ++e) {
+                const int lp = local_of[lop.bits[e]];
+                if (lp < 0) fail("internal: dense bit outside tile");
+                dd.gpos[e] = (uint8_t)lp;
+                dd.gate_mask |= 1u << lp;
+            }
+            dd.nnz = (uint32_t)lop.cols.size();
+            std::vector<uint32_t> coloff(lop.cols.size());
+            for (size_t p = 0; p < lop.cols.size(); ++p) {
+                uint32_t off = 0;
+                for (uint32_t e = 0; e < dd.k; ++e)
+                    if ((lop.cols[p] >> (dd.k - 1 - e)) & 1u) off |= 1u << dd.gpos[e];
+                coloff[p] = off;
+            }
+            dd.rowptr_off = (uint32_t)append(aux, lop.rowptr.data(), lop.rowptr.size());
+            dd.coloff_off = (uint32_t)append(aux, coloff.data(), coloff.size());
+            dd.val_off = (uint32_t)append(aux, lop.vals.data(), lop.vals.size());
+            const size_t dd_off = append(aux, &dd, 1);
+            dense_fix.push_back({dd_off, {}});
+            dop.dense_off = (uint32_t)dd_off;
+            fixes.push_back({ops.size(), 2});
+            ops.push_back(dop);
+            rounds.push_back(dr);
+            continue;
+        }
+        dr.type = ROUND_REG;
+        // register bits: the round's targets, padded with the highest free tile bits
+        std::vector<int> reg_local;
+        for (int b : rb.reg) reg_local.push_back(local_of[b]);
+        for (int lp = T - 1; lp >= 0 && (int)reg_local.size() < kRegBits; --lp)
+            if (std::find(reg_local.begin(), reg_local.end(), lp) == reg_local.end()) reg_local.push_back(lp);
+        std::sort(reg_local.begin(), reg_local.end());
+        std::vector<int> slot_of(16, -1), thr_local, thr_index(16, -1);
+        for (int j = 0; j < kRegBits; ++j) { dr.reg_pos[j] = (uint8_t)reg_local[j]; slot_of[reg_local[j]] = j; }
+        for (int lp = 0; lp < T; ++lp)
+            if (slot_of[lp] < 0) { thr_index[lp] = (int)thr_local.size(); thr_local.push_back(lp); }
+        auto thsegs = runs_to_segs(thr_local);
+        if (thsegs.size() > (size_t)kMaxThrSegs) fail("internal: too many thread segments");
+        dr.n_thr_segs = (uint32_t)thsegs.size();
+        for (size_t i = 0; i < thsegs.size(); ++i) dr.thr_segs[i] = thsegs[i];
+
+        auto split_cmask = [&](uint64_t cmask, DevOp& d) {
+            for (int b = 0; b < 64; ++b) {
+                if (!((cmask >> b) & 1)) continue;
+                const int lp = b < nloc ? local_of[b] : -1;
+                if (lp < 0) d.cmask_ext |= 1ull << b;
+                else if (slot_of[lp] >= 0) d.cmask_reg |= 1u << slot_of[lp];
+                else d.cmask_thr |= 1u << lp;
+            }
+        };
+        for (size_t oi : rb.ops) {
+            const LOp& lop = plan.lops[oi];
+            DevOp d;
+            memset(&d, 0, sizeof(d));
+            split_cmask(lop.cmask, d);
+            if (lop.kind == LOp::MAT) {
+                d.type = lop.mtype;
+                const int lp = local_of[lop.target];
+                if (lp < 0 || slot_of[lp] < 0) fail("internal: MAT target not a register bit");
+                d.slot = (uint32_t)slot_of[lp];
+                memcpy(d.m, lop.m, sizeof(d.m));
+            } else {
+                d.type = OP_DIAG;
+                d.diag_index = n_diag++;
+                d.m[0] = lop.theta0;
+                double thr_coef[16] = {0}, reg_coef[4] = {0};
+                std::vector<DiagExtTerm> ext;
+                for (auto& t : lop.lin) {
+                    if (t.second == 0.0) continue;
+                    const int lp = t.first < nloc ? local_of[t.first] : -1;
+                    if (lp < 0) ext.push_back(DiagExtTerm{(uint32_t)t.first, 0, t.second});
+                    else if (slot_of[lp] >= 0) reg_coef[slot_of[lp]] += t.second;
+                    else thr_coef[thr_index[lp]] += t.second;
+                }
+                std::vector<cplx> tbl(80);
+                bool has_lo = false, has_hi = false, has_reg = false;
+                for (int i = 0; i < 32; ++i) {
+                    double alo = 0, ahi = 0;
+                    for (int b = 0; b < 5; ++b) {
+                        if ((i >> b) & 1) { alo += thr_coef[b]; if (5 + b < 16) ahi += thr_coef[5 + b]; }
+                    }
+                    tbl[i] = unit_phase(alo);
+                    tbl[32 + i] = unit_phase(ahi);
+                }
+                for (int b = 0; b < 5; ++b) { has_lo |= thr_coef[b] != 0.0; has_hi |= thr_coef[5 + b] != 0.0; }
+                for (int s = 0; s < 16; ++s) {
+                    double a = 0;
+                    for (int j = 0; j < 4; ++j) if ((s >> j) & 1) a += reg_coef[j];
+                    tbl[64 + s] = unit_phase(a);
+                }
+                for (int j = 0; j < 4; ++j) has_reg |= reg_coef[j] != 0.0;
+                d.flags = (has_lo ? (uint32_t)DIAG_HAS_THR_LO : 0u) | (has_hi ? (uint32_t)DIAG_HAS_THR_HI : 0u) | (has_reg ? (uint32_t)DIAG_HAS_REG : 0u);
+                d.n_ext = (uint32_t)ext.size();
+                if (!ext.empty()) { d.ext_off = (uint32_t)append(aux, ext.data(), ext.size()); fixes.push_back({ops.size(), 0}); }
+                if (d.flags) { d.tbl_off = (uint32_t)append(aux, tbl.data(), tbl.size()); fixes.push_back({ops.size(), 1}); }
+            }
+            ops.push_back(d);
+        }
+        dr.n_ops = (uint32_t)ops.size() - dr.first_op;
+        rounds.push_back(dr);
+    }
+    if (rounds.size() > (size_t)kMaxRounds || ops.size() > (size_t)kMaxOps) fail("internal: pass exceeds round/op caps");
+
+    hdr.n_rounds = (uint32_t)rounds.size();
+    hdr.n_ops = (uint32_t)ops.size();
+    hdr.n_diag = n_diag;
+    hdr.rounds_off = (uint32_t)sizeof(DevPass);
+    hdr.ops_off = hdr.rounds_off + (uint32_t)(rounds.size() * sizeof(DevRound));
+    const uint32_t aux_base = hdr.ops_off + (uint32_t)(ops.size() * sizeof(DevOp));
+    for (auto& f : fixes) {
+        DevOp& d = ops[f.op];
+        if (f.field == 0) d.ext_off += aux_base;
+        else if (f.field == 1) d.tbl_off += aux_base;
+        else d.dense_off += aux_base;
+    }
+    for (auto& df : dense_fix) {
+        DevDense* dd = reinterpret_cast<DevDense*>(aux.data() + df.first);
+        dd->rowptr_off += aux_base;
+        dd->coloff_off += aux_base;
+        dd->val_off += aux_base;
+    }
+    while (aux.size() % 16) aux.push_back(0);
+    hdr.blob_bytes = aux_base + (uint32_t)aux.size();
+
+    std::vector<uint8_t> blob(hdr.blob_bytes);
+    memcpy(blob.data(), &hdr, sizeof(hdr));
+    if (!rounds.empty()) memcpy(blob.data() + hdr.rounds_off, rounds.data(), rounds.size() * sizeof(DevRound));
+    if (!ops.empty()) memcpy(blob.data() + hdr.ops_off, ops.data(), ops.size() * sizeof(DevOp));
+    if (!aux.empty()) memcpy(blob.data() + aux_base, aux.data(), aux.size());
+    plan.passes.push_back(std::move(blob));
+    plan.n_rounds += rounds.size();
+}
+
+}  // namespace
+
+void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* ops, size_t n_ops, const PlanOptions& opt_in) {
+    if (n_local == 0 || n_local > n_qubits) fail("n_local_qubits must be in 1..n_qubits");
+    plan.n_qubits = n_qubits;
+    plan.n_local = n_local;
+    plan.n_alloc = std::max<uint32_t>(n_local, kMinQubits);
+    plan.opt = opt_in;
+    plan.opt.tile_bits = std::max<int>(kRegBits, std::min<int>(opt_in.tile_bits, kMaxTileBits));
+    plan.passes.clear();
+    plan.lops.clear();
+    plan.n_rounds = 0;
+    lower_gates(n_qubits, ops, n_ops, plan.lops, &plan.n_gates);
+    if (plan.opt.fuse) merge_diagonals(plan.lops);
+
+    const int nloc = (int)plan.n_alloc;
+    const int T = std::min<int>(plan.opt.tile_bits, nloc);
+    const int L = std::max(0, std::min<int>(plan.opt.low_bits, T - 1));
+    const uint64_t low_mask = (T == nloc) ? 0 : ((1ull << L) - 1);  // single-tile states: every bit is a tile bit
+    const uint64_t local_mask = (nloc >= 64) ? ~0ull : ((1ull << n_local) - 1);
+
+    PassB cur;
+    auto close_pass = [&]() {
+        if (!cur.empty()) emit_pass(plan, cur);
+        cur = PassB();
+    };
+    for (size_t i = 0; i < plan.lops.size(); ++i) {
+        const LOp& lop = plan.lops[i];
+        const uint64_t tg = lop.targets();
+        if (tg & ~local_mask) fail("gate " + std::to_string(lop.src_gate) + " targets a qubit held across ranks; global-qubit remap is required");
+        if (lop.kind == LOp::DENSE && popcnt(tg) > T) fail("Custom gate is wider than the tile (" + std::to_string(T) + " bits)");
+        if (!plan.opt.fuse) close_pass();
+        // Can the op join the open pass?  Its targets must fit next to the pass's tile bits and the
+        // low passenger bits, and the pass must stay within the kernel's round/op caps.
+        const bool can_join = !cur.relaxed_low && popcnt(cur.req | tg | low_mask) <= T &&
+                              cur.n_ops + 1 <= (size_t)kMaxOps && cur.rounds.size() + 1 <= (size_t)kMaxRounds;
+        if (!can_join) close_pass();
+        // A Custom gate wider than T - low_bits gets a pass of its own without passenger bits.
+        const bool relaxed = popcnt(cur.req | tg | low_mask) > T;
+        cur.req |= tg;
+        cur.relaxed_low |= relaxed;
+        if (lop.kind == LOp::DENSE) {
+            RoundB r;
+            r.dense = true;
+            r.ops.push_back(i);
+            cur.rounds.push_back(std::move(r));
+        } else {
+            if (cur.rounds.empty() || cur.rounds.back().dense) cur.rounds.push_back(RoundB());
+            if (lop.kind == LOp::MAT) {
+                RoundB* r = &cur.rounds.back();
+                if (std::find(r->reg.begin(), r->reg.end(), lop.target) == r->reg.end()) {
+                    if ((int)r->reg.size() == kRegBits) { cur.rounds.push_back(RoundB()); r = &cur.rounds.back(); }
+                    r->reg.push_back(lop.target);
+                }
+                r->ops.push_back(i);
+            } else {
+                cur.rounds.back().ops.push_back(i);
+            }
+        }
+        cur.n_ops++;
+        if (relaxed) close_pass();
+    }
+    close_pass();
+}
+
+std::string describe_plan(const Plan& plan) {
+    std::ostringstream os;
+    os << "{\"n_qubits\":" << plan.n_qubits << ",\"n_local\":" << plan.n_local << ",\"n_alloc\":" << plan.n_alloc
+       << ",\"tile_bits\":" << std::min<int>(plan.opt.tile_bits, (int)plan.n_alloc) << ",\"low_bits\":" << plan.opt.low_bits
+       << ",\"n_gates\":" << plan.n_gates << ",\"n_lowered_ops\":" << plan.lops.size() << ",\"passes\":[";
+    for (size_t p = 0; p < plan.passes.size(); ++p) {
+        const uint8_t* blob = plan.passes[p].data();
+        const DevPass* h = reinterpret_cast<const DevPass*>(blob);
+        const DevRound* rounds = reinterpret_cast<const DevRound*>(blob + h->rounds_off);
+        const DevOp* ops = reinterpret_cast<const DevOp*>(blob + h->ops_off);
+        os << (p ? "," : "") << "{\"tile\":[";
+        bool first = true;
+        for (uint32_t s = 0; s < h->n_tile_segs; ++s)
+            for (uint32_t b = 0; b < h->tile_segs[s].width; ++b) { os << (first ? "" : ",") << (int)h->tile_segs[s].dst_lo + (int)b; first = false; }
+        os << "],\"n_tiles\":" << h->n_tiles << ",\"bytes\":" << h->blob_bytes << ",\"rounds\":[";
+        for (uint32_t r = 0; r < h->n_rounds; ++r) {
+            os << (r ? "," : "") << "{\"type\":" << rounds[r].type << ",\"reg\":[" << (int)rounds[r].reg_pos[0] << "," << (int)rounds[r].reg_pos[1]
+               << "," << (int)rounds[r].reg_pos[2] << "," << (int)rounds[r].reg_pos[3] << "],\"ops\":[";
+            for (uint32_t o = 0; o < rounds[r].n_ops; ++o) os << (o ? "," : "") << ops[rounds[r].first_op + o].type;
+            os << "]}";
+        }
+        os << "]}";
+    }
+    os << "]}";
+    return os.str();
+}
+
+}  // namespace qsv

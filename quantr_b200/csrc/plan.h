@@ -1,0 +1,66 @@
+// plan.h — host-side lowering and fusion scheduler (no CUDA here).
+//
+// Takes the gate list exactly as Circuit::simulate_with_register walks it
+// (src/circuit/simulation.rs:37-56) and produces pass blobs (qsv_types.h) for the kernels.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/qsv.h"
+#include "qsv_types.h"
+
+namespace qsv {
+
+// A gate lowered to physical-bit space (bit = n-1-wire).
+struct LOp {
+    enum Kind { MAT, DIAG, DENSE } kind = MAT;
+    uint32_t src_gate = 0;
+    // MAT: 2x2 matrix on `target`, applied where all bits of cmask are 1
+    int target = -1;
+    uint64_t cmask = 0;
+    OpType mtype = OP_MAT_GENERAL;
+    double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // DIAG: amp *= exp(i*pi*(theta0 + sum coef*bit)) where all bits of cmask are 1 (half-turns)
+    double theta0 = 0;
+    std::vector<std::pair<int, double>> lin;
+    // DENSE: CSR over sub-index (bits[0] is the MSB of the sub-index)
+    std::vector<int> bits;
+    std::vector<uint32_t> rowptr, cols;
+    std::vector<cplx> vals;
+
+    uint64_t support() const;  // bits the op's action depends on or changes
+    uint64_t targets() const;  // bits that must be tile bits
+};
+
+struct PlanOptions {
+    int tile_bits = 12;
+    int low_bits = 3;
+    int fuse = 1;
+};
+
+struct Plan {
+    uint32_t n_qubits = 0;        // logical qubits of the circuit
+    uint32_t n_local = 0;         // logical index bits held by this rank
+    uint32_t n_alloc = 0;         // allocated local bits (>= kMinQubits)
+    PlanOptions opt;
+    std::vector<LOp> lops;                        // after lowering + diagonal merging
+    std::vector<std::vector<uint8_t>> passes;     // device blobs
+    uint64_t n_gates = 0, n_rounds = 0;
+    // device residency (owned by the state API)
+    void* dev_blob = nullptr;
+    std::vector<size_t> dev_offsets;
+    int dev_device = -1;
+};
+
+// Throws std::runtime_error with a message on invalid input / unsupported circuits.
+void lower_gates(uint32_t n_qubits, const qsv_op* ops, size_t n_ops, std::vector<LOp>& out, uint64_t* n_gates);
+void merge_diagonals(std::vector<LOp>& lops);
+void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* ops, size_t n_ops, const PlanOptions& opt);
+std::string describe_plan(const Plan& plan);
+
+void host_sincospi(double x, double* s, double* c);
+
+}  // namespace qsv

@@ -1,0 +1,83 @@
+// plan_api.cpp — C ABI for the host-only part of the library (lowering + scheduling).
+// Needs no GPU; see include/qsv.h.
+#include <string.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "plan.h"
+#include "plan_handle.h"
+
+namespace {
+thread_local std::string g_plan_error;
+}
+
+extern "C" {
+
+const char* qsv_plan_last_error(void) { return g_plan_error.c_str(); }
+
+int qsv_plan_create(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubits, const qsv_op* ops, size_t n_ops,
+                    uint32_t tile_bits, uint32_t low_bits, int fuse) {
+    if (!out) { g_plan_error = "out is NULL"; return QSV_ERR_INVALID_ARG; }
+    *out = nullptr;
+    try {
+        qsv_plan* p = new qsv_plan();
+        qsv::PlanOptions opt;
+        if (tile_bits) opt.tile_bits = (int)tile_bits;
+        if (low_bits) opt.low_bits = (int)low_bits;
+        opt.fuse = fuse;
+        try {
+            qsv::build_plan(p->plan, n_qubits, n_local_qubits, ops, n_ops, opt);
+        } catch (...) {
+            delete p;
+            throw;
+        }
+        *out = p;
+        return QSV_OK;
+    } catch (const std::bad_alloc&) {
+        g_plan_error = "out of host memory while building the plan";
+        return QSV_ERR_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        g_plan_error = e.what();
+        const bool unsupported = g_plan_error.find("not supported") != std::string::npos ||
+                                 g_plan_error.find("remap is required") != std::string::npos ||
+                                 g_plan_error.find("wider than the tile") != std::string::npos;
+        return unsupported ? QSV_ERR_UNSUPPORTED : QSV_ERR_INVALID_ARG;
+    } catch (...) {
+        g_plan_error = "unknown error";
+        return QSV_ERR_INTERNAL;
+    }
+}
+
+int qsv_plan_destroy(qsv_plan* p) {
+    if (!p) return QSV_OK;
+    if (p->release_device) p->release_device(p);
+    delete p;
+    return QSV_OK;
+}
+
+int qsv_plan_stats(const qsv_plan* p, qsv_stats* stats) {
+    if (!p || !stats) { g_plan_error = "NULL argument"; return QSV_ERR_INVALID_ARG; }
+    memset(stats, 0, sizeof(*stats));
+    stats->n_gates = p->plan.n_gates;
+    stats->n_passes = p->plan.passes.size();
+    stats->n_rounds = p->plan.n_rounds;
+    stats->n_kernel_launches = p->plan.passes.size();
+    stats->bytes_per_pass = 32ull << p->plan.n_alloc;
+    return QSV_OK;
+}
+
+int qsv_plan_serialize(const qsv_plan* p, void* out, size_t cap, size_t* size) {
+    if (!p || !size) { g_plan_error = "NULL argument"; return QSV_ERR_INVALID_ARG; }
+    try {
+        const std::string s = qsv::describe_plan(p->plan);
+        *size = s.size();
+        if (out && cap) memcpy(out, s.data(), s.size() < cap ? s.size() : cap);
+        return QSV_OK;
+    } catch (const std::exception& e) {
+        g_plan_error = e.what();
+        return QSV_ERR_INTERNAL;
+    }
+}
+
+}  // extern "C"

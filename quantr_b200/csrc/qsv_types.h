@@ -1,0 +1,137 @@
+// qsv_types.h — POD layouts shared by the host scheduler and the sm_100a kernels.
+//
+// A *plan* is a list of *passes*.  One pass streams the whole local state once:
+// every CTA pulls a tile of 2^T amplitudes (T "tile bits" of the amplitude index,
+// always including the lowest `low_bits` so global accesses stay coalesced) into
+// shared memory, runs the pass's *rounds* on it and writes it back in place.
+// A register round keeps 16 amplitudes (4 "register bits") per thread in registers
+// and applies a list of lowered ops to them; a dense round applies one k-qubit
+// Custom matrix (CSR) to the tile.
+//
+// Index convention (reference: src/circuit/states/product_states.rs:205-215):
+// wire q of an n-qubit circuit is physical index bit n-1-q.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define QSV_HD __host__ __device__ __forceinline__
+#else
+#define QSV_HD inline
+#endif
+
+namespace qsv {
+
+constexpr int kRegBits = 4;
+constexpr int kSlots = 1 << kRegBits;
+constexpr int kMinQubits = 4;      // states smaller than one register group are padded with idle top bits
+constexpr int kMaxTileBits = 13;
+constexpr int kMaxSegs = 16;
+constexpr int kMaxThrSegs = 8;
+constexpr int kMaxRounds = 32;
+constexpr int kMaxOps = 96;
+constexpr int kThreads = 256;
+constexpr uint32_t kPassMagic = 0x51535631u;  // "QSV1"
+
+struct alignas(16) cplx {
+    double x, y;
+};
+
+// deposit: result |= ((v >> src_lo) & mask(width)) << dst_lo
+struct Seg {
+    uint8_t src_lo, width, dst_lo, pad;
+};
+
+enum OpType : uint32_t {
+    OP_MAT_GENERAL = 0,   // complex 2x2 on one register bit
+    OP_MAT_REAL = 1,      // real 2x2 (H, Ry)
+    OP_MAT_ANTIDIAG = 2,  // a0' = m01*a1, a1' = m10*a0 (Y, X90, CY, ...)
+    OP_MAT_XSWAP = 3,     // a0 <-> a1 (X, CNot, Toffoli)
+    OP_DIAG = 4,          // amp *= exp(i*pi*(theta0 + sum_b coef_b*bit_b)) where control mask holds
+    OP_DENSE = 5          // k-qubit Custom matrix (dense round)
+};
+
+enum DiagFlags : uint32_t { DIAG_HAS_THR_LO = 1, DIAG_HAS_THR_HI = 2, DIAG_HAS_REG = 4 };
+enum RoundType : uint32_t { ROUND_REG = 0, ROUND_DENSE = 1 };
+
+struct DiagExtTerm {
+    uint32_t bit;  // physical bit (outside the tile, may be a rank bit)
+    uint32_t pad;
+    double coef;   // half-turns
+};
+
+// 128 bytes
+struct DevOp {
+    uint32_t type;
+    uint32_t slot;        // MAT: register slot 0..3 of the target bit
+    uint32_t cmask_reg;   // controls among the register slots (4 bits)
+    uint32_t cmask_thr;   // controls among the tile-local, non-register bits (tile-local positions)
+    uint64_t cmask_ext;   // controls outside the tile (physical bit positions, rank bits included)
+    uint32_t flags;       // DIAG: DiagFlags
+    uint32_t diag_index;  // DIAG: slot in the per-tile external-phase array
+    double m[8];          // MAT: m00 m01 m10 m11 (re, im);  DIAG: m[0] = theta0 (half-turns)
+    uint32_t ext_off;     // DIAG: byte offset in the pass blob of DiagExtTerm[n_ext]
+    uint32_t n_ext;
+    uint32_t tbl_off;     // DIAG: byte offset of cplx lo[32], hi[32], reg[16]
+    uint32_t dense_off;   // DENSE: byte offset of DevDense
+    uint32_t pad[4];
+};
+static_assert(sizeof(DevOp) == 128, "DevOp layout");
+
+// 64 bytes
+struct DevRound {
+    uint32_t type;
+    uint32_t first_op;
+    uint32_t n_ops;
+    uint32_t n_thr_segs;
+    uint8_t reg_pos[4];  // tile-local positions of the 4 register bits, ascending
+    uint32_t pad[3];
+    Seg thr_segs[kMaxThrSegs];  // thread index e -> tile-local index with register bits zero
+};
+static_assert(sizeof(DevRound) == 64, "DevRound layout");
+
+struct DevDense {
+    uint32_t k;
+    uint32_t gate_mask;   // tile-local mask of the gate bits
+    uint32_t rowptr_off;  // byte offsets in the pass blob
+    uint32_t coloff_off;  // uint32 tile-local offset of each non-zero's input sub-state
+    uint32_t val_off;     // cplx value of each non-zero
+    uint32_t nnz;
+    uint8_t gpos[16];     // tile-local position of sub-index bit e (e = 0 is the MSB = first control)
+};
+
+struct DevPass {
+    uint32_t magic;
+    uint32_t tile_bits;
+    uint32_t n_rounds;
+    uint32_t n_ops;
+    uint32_t n_diag;
+    uint32_t n_tile_segs;
+    uint32_t n_ext_segs;
+    uint32_t flags;
+    uint64_t n_tiles;
+    uint32_t rounds_off;  // byte offsets in the pass blob
+    uint32_t ops_off;
+    uint32_t blob_bytes;
+    uint32_t pad[3];
+    Seg tile_segs[kMaxSegs];  // tile-local index -> physical (local) offset
+    Seg ext_segs[kMaxSegs];   // tile id -> physical (local) base
+};
+static_assert(sizeof(DevPass) == 192, "DevPass layout");
+
+QSV_HD uint64_t deposit(uint64_t v, const Seg* segs, uint32_t n) {
+    uint64_t r = 0;
+    for (uint32_t i = 0; i < n; ++i) r |= ((v >> segs[i].src_lo) & ((1ull << segs[i].width) - 1ull)) << segs[i].dst_lo;
+    return r;
+}
+
+// Shared-memory swizzle of a tile-local index: XOR-folds every higher 3-bit group into the
+// 16-byte-unit bits so that any three index bits with distinct (position mod 3) spread a
+// quarter-warp's 128-bit accesses over all 32 banks.
+QSV_HD uint32_t swz(uint32_t l) {
+    const uint32_t x = l >> 3;
+    return l ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7u);
+}
+
+QSV_HD cplx cmul(cplx a, cplx b) { return cplx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+
+}  // namespace qsv

@@ -1,0 +1,63 @@
+// qsv_emu.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Walks a plan's pass blobs on the CPU by calling the very same __host__ __device__
+// per-thread functions (quantr_b200/csrc/pass_core.h) the sm_100a kernel runs, one
+// "thread" after another with the barriers where the kernel has them.  This lets the
+// `-m "not gpu"` suite check the host scheduler, the blob encoding and the per-thread
+// arithmetic against the oracle without a GPU.  It is compiled only into
+// tests/emu/libqsv_emu.so and never linked or loaded by the product library.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../quantr_b200/csrc/pass_core.h"
+#include "../../quantr_b200/csrc/plan_handle.h"
+
+using namespace qsv;
+
+static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
+    const DevPass* P = reinterpret_cast<const DevPass*>(blob);
+    const DevRound* rounds = reinterpret_cast<const DevRound*>(blob + P->rounds_off);
+    const DevOp* ops = reinterpret_cast<const DevOp*>(blob + P->ops_off);
+    const uint32_t T = P->tile_bits;
+    const uint32_t tile_len = 1u << T, groups = 1u << (T - kRegBits);
+    std::vector<cplx> tile(tile_len);
+    std::vector<cplx> ext_phase(kMaxOps);
+    std::vector<cplx> dense_out((size_t)groups * kSlots);
+    for (uint64_t t = 0; t < P->n_tiles; ++t) {
+        const uint64_t base = deposit(t, P->ext_segs, P->n_ext_segs);
+        const uint64_t base_full = base | rank_hi;
+        for (uint32_t l = 0; l < tile_len; ++l) tile[swz(l)] = state[base + deposit(l, P->tile_segs, P->n_tile_segs)];
+        for (uint32_t o = 0; o < P->n_ops; ++o)
+            if (ops[o].type == OP_DIAG) ext_phase[ops[o].diag_index] = diag_ext_phase(ops[o], blob, base_full);
+        for (uint32_t r = 0; r < P->n_rounds; ++r) {
+            const DevRound& R = rounds[r];
+            if (R.type == ROUND_REG) {
+                for (uint32_t e = 0; e < groups; ++e) reg_round(R, ops, blob, ext_phase.data(), base_full, e, tile.data());
+            } else {
+                const DevDense* D = reinterpret_cast<const DevDense*>(blob + ops[R.first_op].dense_off);
+                for (uint32_t e = 0; e < groups; ++e) {
+                    cplx out[kSlots];
+                    dense_compute(*D, blob, e, tile.data(), out);
+                    memcpy(&dense_out[(size_t)e * kSlots], out, sizeof(out));
+                }
+                for (uint32_t e = 0; e < groups; ++e) {
+                    cplx out[kSlots];
+                    memcpy(out, &dense_out[(size_t)e * kSlots], sizeof(out));
+                    dense_store(e, tile.data(), out);
+                }
+            }
+        }
+        for (uint32_t l = 0; l < tile_len; ++l) state[base + deposit(l, P->tile_segs, P->n_tile_segs)] = tile[swz(l)];
+    }
+}
+
+extern "C" int qsv_emu_run_plan(const qsv_plan* p, double* amps, uint64_t rank) {
+    if (!p || !amps) return 1;
+    const uint64_t rank_hi = rank << p->plan.n_local;
+    for (const auto& blob : p->plan.passes) run_pass(blob.data(), reinterpret_cast<cplx*>(amps), rank_hi);
+    return 0;
+}
+
+extern "C" uint32_t qsv_emu_alloc_qubits(const qsv_plan* p) { return p ? p->plan.n_alloc : 0; }

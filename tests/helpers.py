@@ -1,0 +1,237 @@
+"""Shared test plumbing: oracle- and emulator-backed variants of the host `Circuit`.
+
+`OracleCircuit` keeps the product's builder (column layout, validation, encoding are host
+logic under test) but runs the gate list through the CPU oracle instead of the device, so the
+reference's tests can be replayed on a CPU-only box and used as the checker on the GPU box.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import quantr_b200 as qb  # noqa: E402
+from quantr_b200 import _ffi as F  # noqa: E402
+from quantr_b200 import states as st  # noqa: E402
+from quantr_b200.circuit import Measurement, encode_gates  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+class _HostSimulated:
+    """SimulatedCircuit look-alike over a host amplitude vector (oracle / emulator results)."""
+
+    def __init__(self, gates, n, amps):
+        self.circuit_gates, self.num_qubits, self.amps = gates, n, amps
+
+    def get_state(self):
+        return Measurement.NonObservable(st.SuperPosition._raw(self.amps, self.num_qubits))
+
+    take_state = get_state
+
+    def measure_all(self, shots, rng=None):
+        rng = rng or np.random.default_rng(0)
+        idx = orc.measure_all(self.num_qubits, self.amps, rng.random(shots))
+        bins = {}
+        for i in idx:
+            if int(i) == F.UINT64_MAX:
+                continue
+            key = st.ProductState.binary_basis(int(i), self.num_qubits)
+            bins[key] = bins.get(key, 0) + 1
+        return Measurement.Observable(bins)
+
+
+class OracleCircuit(qb.Circuit):
+    mode = "dense"
+
+    @staticmethod
+    def new(n):
+        return OracleCircuit(n)
+
+    def _simulate(self, gates, register):
+        enc = encode_gates(gates, self.num_qubits)
+        reg = None if register is None else register.get_amplitudes()
+        amps = orc.simulate(self.num_qubits, enc.ops, enc.n_ops, reg, mode=self.mode)
+        return _HostSimulated(gates, self.num_qubits, amps)
+
+
+class FaithfulOracleCircuit(OracleCircuit):
+    mode = "faithful"
+
+    @staticmethod
+    def new(n):
+        return FaithfulOracleCircuit(n)
+
+
+_emu = None
+
+
+def emu_lib():
+    global _emu
+    if _emu is None:
+        lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "libqsv_emu.so"))
+        lib.qsv_emu_run_plan.restype = C.c_int
+        lib.qsv_emu_run_plan.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint64]
+        lib.qsv_emu_alloc_qubits.restype = C.c_uint32
+        lib.qsv_emu_alloc_qubits.argtypes = [C.c_void_p]
+        lib.qsv_plan_create.restype = C.c_int
+        lib.qsv_plan_create.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.POINTER(F.QsvOp), C.c_size_t,
+                                        C.c_uint32, C.c_uint32, C.c_int]
+        lib.qsv_plan_destroy.argtypes = [C.c_void_p]
+        lib.qsv_plan_last_error.restype = C.c_char_p
+        lib.qsv_plan_serialize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        _emu = lib
+    return _emu
+
+
+def emu_simulate(n, enc, register=None, *, tile_bits=0, low_bits=0, fuse=True, n_local=None, rank=0, describe=False):
+    """Schedules `enc` with the product's scheduler and executes the pass blobs with the host
+    emulation of the kernel's per-thread code (tests/emu/qsv_emu.cpp)."""
+    import json
+    lib = emu_lib()
+    plan = C.c_void_p()
+    nl = n if n_local is None else n_local
+    rc = lib.qsv_plan_create(C.byref(plan), n, nl, enc.ops, enc.n_ops, tile_bits, low_bits, 1 if fuse else 0)
+    if rc != 0:
+        raise F.QsvError(rc, lib.qsv_plan_last_error().decode())
+    try:
+        n_alloc = lib.qsv_emu_alloc_qubits(plan)
+        amps = np.zeros(1 << n_alloc, dtype=np.complex128)
+        if register is None:
+            if rank == 0:
+                amps[0] = 1.0
+        else:
+            reg = np.asarray(register, dtype=np.complex128)
+            amps[: reg.shape[0]] = reg
+        assert lib.qsv_emu_run_plan(plan, amps.ctypes.data_as(C.POINTER(C.c_double)), rank) == 0
+        out = amps[: 1 << nl].copy()
+        if describe:
+            size = C.c_size_t()
+            lib.qsv_plan_serialize(plan, None, 0, C.byref(size))
+            buf = C.create_string_buffer(size.value)
+            lib.qsv_plan_serialize(plan, buf, size.value, C.byref(size))
+            return out, json.loads(buf.raw[: size.value].decode())
+        return out
+    finally:
+        lib.qsv_plan_destroy(plan)
+
+
+class EmuCircuit(qb.Circuit):
+    tile_bits = 0
+    low_bits = 0
+
+    @staticmethod
+    def new(n):
+        return EmuCircuit(n)
+
+    def _simulate(self, gates, register):
+        enc = encode_gates(gates, self.num_qubits)
+        reg = None if register is None else register.get_amplitudes()
+        amps = emu_simulate(self.num_qubits, enc, reg, tile_bits=self.tile_bits, low_bits=self.low_bits)
+        return _HostSimulated(gates, self.num_qubits, amps)
+
+
+# ---- workload generators ---------------------------------------------------
+
+def qft_circuit(C, G, n, x=None):
+    """QFT as the reference writes it (tests/qft.rs:55-62): H(pos) then CRk(k, pos+k-1), no final swaps."""
+    c = C.new(n)
+    for pos in range(n):
+        c.add_gate(G.H, pos)
+        for k in range(2, n - pos + 1):
+            c.add_gate(G.CRk(k, pos + k - 1), pos)
+    if x is not None:
+        c.change_register(st.ProductState.binary_basis(x, n))
+    return c
+
+
+def qft_expected(n, x):
+    """Closed form: amp[y] = 2^{-n/2} exp(2 pi i x bitrev_n(y) / 2^n)."""
+    y = np.arange(1 << n, dtype=np.uint64)
+    rev = np.zeros_like(y)
+    for b in range(n):
+        rev |= ((y >> np.uint64(b)) & np.uint64(1)) << np.uint64(n - 1 - b)
+    phase = (rev.astype(object) * x) % (1 << n)
+    ang = np.array([float(p) for p in phase]) * (2.0 * np.pi / (1 << n))
+    return (np.cos(ang) + 1j * np.sin(ang)) / np.sqrt(float(1 << n))
+
+
+class SplitMix64:
+    def __init__(self, seed):
+        self.s = seed & 0xFFFFFFFFFFFFFFFF
+
+    def next(self):
+        self.s = (self.s + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return z ^ (z >> 31)
+
+
+def random_layered_circuit(C, G, n, depth, seed=None):
+    """BASELINE config 3 generator: per layer one column of random H/Rx/Ry/Rz, then
+    n//3 CNot/Toffoli on a shuffled wire order."""
+    rng = SplitMix64(n if seed is None else seed)
+    c = C.new(n)
+    for _ in range(depth):
+        col = []
+        for _q in range(n):
+            kind = rng.next() % 4
+            theta = 2.0 * np.pi * (rng.next() >> 11) / float(1 << 53)
+            col.append([G.H, G.Rx(theta), G.Ry(theta), G.Rz(theta)][kind])
+        c.add_gates(col)
+        perm = list(range(n))
+        for i in range(n - 1, 0, -1):
+            j = rng.next() % (i + 1)
+            perm[i], perm[j] = perm[j], perm[i]
+        for j in range(n // 3):
+            a, b, t = perm[3 * j], perm[3 * j + 1], perm[3 * j + 2]
+            if rng.next() % 4 == 0:
+                c.add_gate(G.Toffoli(a, b), t)
+            else:
+                c.add_gate(G.CNot(a), b)
+    return c
+
+
+ALL_SINGLE = ["H", "X", "Y", "Z", "S", "Sdag", "T", "Tdag", "X90", "Y90", "MX90", "MY90"]
+
+
+def random_any_gate_circuit(C, G, n, n_gates, rng, custom=None):
+    """Random circuit over every standard gate kind (for differential tests)."""
+    c = C.new(n)
+    for _ in range(n_gates):
+        r = rng.integers(0, 24 if n >= 3 else (22 if n >= 2 else 16))
+        wires = rng.permutation(n)
+        t = int(wires[0])
+        theta = float(rng.uniform(-2 * np.pi, 2 * np.pi))
+        if r < 12:
+            g = getattr(G, ALL_SINGLE[r])
+        elif r == 12:
+            g = G.Rx(theta)
+        elif r == 13:
+            g = G.Ry(theta)
+        elif r == 14:
+            g = G.Rz(theta)
+        elif r == 15:
+            g = G.Phase(theta)
+        elif r == 16:
+            g = G.CR(theta, int(wires[1]))
+        elif r == 17:
+            g = G.CRk(int(rng.integers(1, 8)), int(wires[1]))
+        elif r == 18:
+            g = G.CZ(int(wires[1]))
+        elif r == 19:
+            g = G.CY(int(wires[1]))
+        elif r == 20:
+            g = G.CNot(int(wires[1]))
+        elif r == 21:
+            g = G.Swap(int(wires[1]))
+        else:
+            g = G.Toffoli(int(wires[1]), int(wires[2]))
+        c.add_gate(g, t)
+    return c
