@@ -5,11 +5,11 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 HOSTCXX := $(shell command -v /usr/bin/g++ || echo g++)
 CSRC := quantr_b200/csrc
-NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall -ccbin $(HOSTCXX)
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas -ccbin $(HOSTCXX)
 HOSTFLAGS := -O2 -std=c++17 -fPIC -Wall -Wextra -Wno-unknown-pragmas -pthread
 
 HOST_SRCS := $(CSRC)/plan.cpp $(CSRC)/plan_api.cpp
-CUDA_SRCS := $(CSRC)/kernels.cu $(CSRC)/state_api.cu
+CUDA_SRCS := $(CSRC)/kernels.cu $(CSRC)/state_api.cu $(CSRC)/shard.cpp
 HDRS := include/qsv.h $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh)
 
 all: lib oracle emu

@@ -1,0 +1,305 @@
+// kernels.cu — hand-written sm_100a kernels of the state-vector engine.
+//
+//   pass_kernel<T>        K1/K2/K3: one fused pass (tile of 2^T amplitudes per CTA in shared memory,
+//                         16 amplitudes per thread in registers per round); replaces
+//                         Circuit::apply_gate (src/circuit/simulation.rs:64-135) for a list of gates
+//   set_amp / gather      K4: SuperPosition::new_unchecked (super_positions_unchecked.rs:39-46), get_state
+//   prob_block_sums,      K6: the cumulative |amp|^2 loop of SuperPosition::measure
+//   scan_block_sums           (src/circuit/states/super_positions.rs:335-336), hierarchically
+//   sample_shots          K7: the inverse-CDF search of measure (:333-341), one warp per shot
+//
+// All kernels are HBM-bound streaming kernels: 128-bit coalesced accesses, grids sized to the SM count
+// (persistent CTAs), no tensor-core work.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "pass_core.h"
+
+namespace qsv {
+
+__device__ __forceinline__ cplx ld_stream(const cplx* p) {
+    const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+    return cplx{v.x, v.y};
+}
+__device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
+
+// ---------------------------------------------------------------------------------------------
+// Fused pass.  Shared memory: [tile: 2^T cplx][header + rounds + ops copied from the blob][ext phases]
+// ---------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(kThreads, (T >= 13) ? 1 : 2)
+pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t rank_hi) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr uint32_t kTileLen = 1u << T;
+    constexpr uint32_t kGroups = kTileLen >> kRegBits;
+    constexpr uint32_t kLoadsPerThread = (kTileLen + kThreads - 1) / kThreads;
+    cplx* tile = reinterpret_cast<cplx*>(smem);
+    uint8_t* meta = smem + sizeof(cplx) * kTileLen;
+    const uint32_t tid = threadIdx.x;
+
+    const DevPass* gP = reinterpret_cast<const DevPass*>(blob);
+    const uint32_t meta_bytes = gP->ops_off + gP->n_ops * (uint32_t)sizeof(DevOp);
+    for (uint32_t i = tid * 16u; i < meta_bytes; i += kThreads * 16u)
+        *reinterpret_cast<uint4*>(meta + i) = *reinterpret_cast<const uint4*>(blob + i);
+    __syncthreads();
+    const DevPass& P = *reinterpret_cast<const DevPass*>(meta);
+    const DevRound* rounds = reinterpret_cast<const DevRound*>(meta + P.rounds_off);
+    const DevOp* ops = reinterpret_cast<const DevOp*>(meta + P.ops_off);
+    cplx* ext_phase = reinterpret_cast<cplx*>(meta + meta_bytes);
+    const uint32_t n_tile_segs = P.n_tile_segs, n_ext_segs = P.n_ext_segs;
+
+    for (uint64_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
+        const uint64_t base = deposit(t, P.ext_segs, n_ext_segs);
+        const uint64_t base_full = base | rank_hi;
+        cplx* gtile = state + base;
+        {
+            cplx v[kLoadsPerThread];
+#pragma unroll
+            for (uint32_t i = 0; i < kLoadsPerThread; ++i) {
+                const uint32_t l = i * kThreads + tid;
+                if (l < kTileLen) v[i] = ld_stream(gtile + deposit(l, P.tile_segs, n_tile_segs));
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < kLoadsPerThread; ++i) {
+                const uint32_t l = i * kThreads + tid;
+                if (l < kTileLen) tile[swz(l)] = v[i];
+            }
+        }
+        for (uint32_t o = tid; o < P.n_ops; o += kThreads)
+            if (ops[o].type == OP_DIAG) ext_phase[ops[o].diag_index] = diag_ext_phase(ops[o], blob, base_full);
+        __syncthreads();
+
+        for (uint32_t r = 0; r < P.n_rounds; ++r) {
+            const DevRound& R = rounds[r];
+            if (R.type == ROUND_REG) {
+                for (uint32_t e = tid; e < kGroups; e += kThreads) reg_round(R, ops, blob, ext_phase, base_full, e, tile);
+            } else {
+                const DevDense& D = *reinterpret_cast<const DevDense*>(blob + ops[R.first_op].dense_off);
+                constexpr uint32_t kIter = (kGroups + kThreads - 1) / kThreads;
+                cplx out[kIter][kSlots];
+#pragma unroll
+                for (uint32_t it = 0; it < kIter; ++it) {
+                    const uint32_t e = it * kThreads + tid;
+                    if (e < kGroups) dense_compute(D, blob, e, tile, out[it]);
+                }
+                __syncthreads();
+#pragma unroll
+                for (uint32_t it = 0; it < kIter; ++it) {
+                    const uint32_t e = it * kThreads + tid;
+                    if (e < kGroups) dense_store(e, tile, out[it]);
+                }
+            }
+            __syncthreads();
+        }
+
+#pragma unroll
+        for (uint32_t i = 0; i < kLoadsPerThread; ++i) {
+            const uint32_t l = i * kThreads + tid;
+            if (l < kTileLen) st_stream(gtile + deposit(l, P.tile_segs, n_tile_segs), tile[swz(l)]);
+        }
+        __syncthreads();
+    }
+}
+
+template <int T>
+static cudaError_t launch_pass_t(cplx* state, const uint8_t* blob, const DevPass& hdr, uint64_t rank_hi, int sm_count, cudaStream_t stream) {
+    const size_t smem = sizeof(cplx) * (size_t(1) << T) + hdr.ops_off + hdr.n_ops * sizeof(DevOp) + sizeof(cplx) * (hdr.n_diag + 1);
+    static int blocks_per_sm[2] = {0, 0};  // cached for the largest smem seen (conservative)
+    static size_t smem_cfg = 0;
+    cudaError_t err;
+    if (smem > smem_cfg) {
+        const size_t want = sizeof(cplx) * (size_t(1) << T) + sizeof(DevPass) + kMaxRounds * sizeof(DevRound) + kMaxOps * sizeof(DevOp) + sizeof(cplx) * (kMaxOps + 1);
+        err = cudaFuncSetAttribute(pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+        if (err != cudaSuccess) return err;
+        smem_cfg = want;
+        int nb = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pass_kernel<T>, kThreads, want);
+        if (err != cudaSuccess) return err;
+        blocks_per_sm[0] = nb > 0 ? nb : 1;
+    }
+    uint64_t grid = (uint64_t)sm_count * (uint64_t)blocks_per_sm[0];
+    if (grid > hdr.n_tiles) grid = hdr.n_tiles;
+    pass_kernel<T><<<(unsigned)grid, kThreads, smem, stream>>>(state, blob, rank_hi);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const DevPass& hdr, uint64_t rank_hi, int sm_count, cudaStream_t stream) {
+    switch (hdr.tile_bits) {
+        case 4: return launch_pass_t<4>(state, dev_blob, hdr, rank_hi, sm_count, stream);
+        case 5: return launch_pass_t<5>(state, dev_blob, hdr, rank_hi, sm_count, stream);
+        case 6: return launch_pass_t<6>(state, dev_blob, hdr, rank_hi, sm_count, stream);
+        case 7: return launch_pass_t<7>(state, dev_blob, hdr, rank_hi, sm_count, stream);
+        case 8: return launch_pass_t<8>(state, dev_blob, hdr, rank_hi, sm_count, stream);
+        case 9: return launch_pass_t<9>(state, dev_blob, hdr, rank_hi, sm_count, stream);
+        case 10: return launch_pass_t<10>(state, dev_blob, hdr, rank_hi, sm_count, stream);
+        case 11: return launch_pass_t<11>(state, dev_blob, hdr, rank_hi, sm_count, stream);
+        case 12: return launch_pass_t<12>(state, dev_blob, hdr, rank_hi, sm_count, stream);
+        case 13: return launch_pass_t<13>(state, dev_blob, hdr, rank_hi, sm_count, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: register access
+// ---------------------------------------------------------------------------------------------
+__global__ void set_amp_kernel(cplx* state, uint64_t index, cplx v) { state[index] = v; }
+
+__global__ void gather_kernel(const cplx* __restrict__ state, const uint64_t* __restrict__ idx, cplx* __restrict__ out, uint64_t count) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) out[i] = state[idx[i]];
+}
+
+cudaError_t launch_set_amp(cplx* state, uint64_t index, double re, double im, cudaStream_t stream) {
+    set_amp_kernel<<<1, 1, 0, stream>>>(state, index, cplx{re, im});
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather(const cplx* state, const uint64_t* idx, cplx* out, uint64_t count, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((count + 255) / 256 > 1184 ? 1184 : (count + 255) / 256);
+    gather_kernel<<<grid ? grid : 1, 256, 0, stream>>>(state, idx, out, count);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: per-block probability sums and their exclusive scan.  Fixed summation tree -> deterministic.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One CTA per block of 2^block_bits amplitudes (grid-stride).  256 threads.
+__global__ void __launch_bounds__(256) prob_block_sums_kernel(const cplx* __restrict__ state, double* __restrict__ sums, uint64_t n_blocks, uint32_t block_bits) {
+    __shared__ double warp_part[8];
+    const uint32_t len = 1u << block_bits;
+    for (uint64_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const cplx* p = state + (b << block_bits);
+        double acc = 0.0;
+        for (uint32_t l = threadIdx.x; l < len; l += 256) {
+            const cplx a = ld_stream(p + l);
+            acc += a.x * a.x + a.y * a.y;
+        }
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 8; ++w) s += warp_part[w];
+            sums[b] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// Single CTA, 1024 threads: exclusive scan of `n` doubles with a running carry; prefix[n] = total.
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(const double* __restrict__ sums, double* __restrict__ prefix, uint64_t n) {
+    __shared__ double warp_tot[32];
+    __shared__ double carry_s;
+    if (threadIdx.x == 0) carry_s = 0.0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < n; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const double v = i < n ? sums[i] : 0.0;
+        double inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += y;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            double w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= (uint32_t)o) w += y;
+            }
+            warp_tot[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const double carry = carry_s;
+        const double before = carry + (warp ? warp_tot[warp - 1] : 0.0) + (inc - v);
+        if (i < n) prefix[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) prefix[n] = carry_s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: one warp per shot.  prefix[b] = sum of the blocks before b (b = 0..n_blocks), prefix[n_blocks] = total.
+// Returns the first canonical index i with u < cumulative(i), UINT64_MAX if u >= total
+// (super_positions.rs:341 "None").
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_shots_kernel(const cplx* __restrict__ state, const double* __restrict__ prefix, uint64_t n_blocks,
+                                                         uint32_t block_bits, const double* __restrict__ uniforms, uint64_t shots,
+                                                         uint64_t index_or, uint64_t* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp_global = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t len = 1u << block_bits;
+    for (uint64_t s = warp_global; s < shots; s += n_warps) {
+        const double u = uniforms[s];
+        uint64_t result = UINT64_MAX;
+        if (u < prefix[n_blocks]) {
+            // largest b with prefix[b] <= u  (prefix is non-decreasing, prefix[0] = 0 <= u)
+            uint64_t lo = 0, hi = n_blocks;  // invariant: prefix[lo] <= u, (hi == n_blocks or prefix[hi] > u)
+            while (hi - lo > 1) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (prefix[mid] <= u) lo = mid; else hi = mid;
+            }
+            for (uint64_t b = lo; b < n_blocks && result == UINT64_MAX; ++b) {
+                double carry = prefix[b];
+                const cplx* p = state + (b << block_bits);
+                for (uint32_t l0 = 0; l0 < len; l0 += 32) {
+                    double inc = 0.0;
+                    if (l0 + lane < len) {
+                        const cplx a = p[l0 + lane];
+                        inc = a.x * a.x + a.y * a.y;
+                    }
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double y = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= (uint32_t)o) inc += y;
+                    }
+                    const double cum = carry + inc;
+                    const uint32_t hit = __ballot_sync(0xffffffffu, u < cum);
+                    if (hit) {
+                        result = (b << block_bits) + l0 + (uint32_t)(__ffs(hit) - 1);
+                        break;
+                    }
+                    carry = __shfl_sync(0xffffffffu, cum, 31);
+                }
+            }
+        }
+        if (lane == 0) out[s] = (result == UINT64_MAX) ? result : (result | index_or);
+    }
+}
+
+cudaError_t launch_prob_block_sums(const cplx* state, double* sums, uint64_t n_blocks, uint32_t block_bits, int sm_count, cudaStream_t stream) {
+    uint64_t grid = (uint64_t)sm_count * 8;
+    if (grid > n_blocks) grid = n_blocks;
+    prob_block_sums_kernel<<<(unsigned)grid, 256, 0, stream>>>(state, sums, n_blocks, block_bits);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_block_sums(const double* sums, double* prefix, uint64_t n, cudaStream_t stream) {
+    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(sums, prefix, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sample_shots(const cplx* state, const double* prefix, uint64_t n_blocks, uint32_t block_bits, const double* uniforms,
+                                uint64_t shots, uint64_t index_or, uint64_t* out, int sm_count, cudaStream_t stream) {
+    uint64_t grid = (shots + 7) / 8;
+    const uint64_t cap = (uint64_t)sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid == 0) grid = 1;
+    sample_shots_kernel<<<(unsigned)grid, 256, 0, stream>>>(state, prefix, n_blocks, block_bits, uniforms, shots, index_or, out);
+    return cudaGetLastError();
+}
+
+}  // namespace qsv

@@ -1,0 +1,18 @@
+// kernels.h — launchers of the sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "qsv_types.h"
+
+namespace qsv {
+
+cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const DevPass& hdr, uint64_t rank_hi, int sm_count, cudaStream_t stream);
+cudaError_t launch_set_amp(cplx* state, uint64_t index, double re, double im, cudaStream_t stream);
+cudaError_t launch_gather(const cplx* state, const uint64_t* idx, cplx* out, uint64_t count, cudaStream_t stream);
+cudaError_t launch_prob_block_sums(const cplx* state, double* sums, uint64_t n_blocks, uint32_t block_bits, int sm_count, cudaStream_t stream);
+cudaError_t launch_scan_block_sums(const double* sums, double* prefix, uint64_t n, cudaStream_t stream);
+cudaError_t launch_sample_shots(const cplx* state, const double* prefix, uint64_t n_blocks, uint32_t block_bits, const double* uniforms,
+                                uint64_t shots, uint64_t index_or, uint64_t* out, int sm_count, cudaStream_t stream);
+
+}  // namespace qsv

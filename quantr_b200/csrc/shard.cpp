@@ -1,0 +1,134 @@
+// shard.cpp — dlopen'ed NCCL: communicator set-up, scalar all-reduce and the global-qubit slot exchange.
+#include "shard.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+namespace qsv {
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi g_nccl;
+
+bool load_nccl(std::string& err) {
+    if (g_nccl.handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {  // prefer a copy the process already holds (torch bundles its own)
+        h = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h)
+        for (const char* n : names) {
+            h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+    if (!h) {
+        err = std::string("cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : "not found");
+        return false;
+    }
+#define QSV_SYM(field, name)                                                   \
+    *reinterpret_cast<void**>(&g_nccl.field) = dlsym(h, name);                 \
+    if (!g_nccl.field) { err = std::string("NCCL symbol missing: ") + name; return false; }
+    QSV_SYM(GetUniqueId, "ncclGetUniqueId");
+    QSV_SYM(CommInitRank, "ncclCommInitRank");
+    QSV_SYM(CommDestroy, "ncclCommDestroy");
+    QSV_SYM(AllReduce, "ncclAllReduce");
+    QSV_SYM(Send, "ncclSend");
+    QSV_SYM(Recv, "ncclRecv");
+    QSV_SYM(GroupStart, "ncclGroupStart");
+    QSV_SYM(GroupEnd, "ncclGroupEnd");
+    QSV_SYM(GetErrorString, "ncclGetErrorString");
+#undef QSV_SYM
+    g_nccl.handle = h;
+    return true;
+}
+
+bool nccl_ok(ncclResult_t r, const char* what, std::string& err) {
+    if (r == ncclSuccess) return true;
+    err = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "NCCL error");
+    return false;
+}
+
+}  // namespace
+
+struct ShardComm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    double* d_scalar = nullptr;
+};
+
+bool shard_unique_id(void* out, size_t out_bytes, std::string& err) {
+    if (!out || out_bytes < sizeof(ncclUniqueId)) { err = "unique-id buffer must hold 128 bytes"; return false; }
+    if (!load_nccl(err)) return false;
+    ncclUniqueId id;
+    if (!nccl_ok(g_nccl.GetUniqueId(&id), "ncclGetUniqueId", err)) return false;
+    memcpy(out, &id, sizeof(id));
+    return true;
+}
+
+ShardComm* shard_comm_create(int rank, int world, const void* unique_id, size_t unique_id_bytes, cudaStream_t stream, std::string& err) {
+    if (!unique_id || unique_id_bytes < sizeof(ncclUniqueId)) { err = "nccl_unique_id must be the 128 bytes from qsv_nccl_unique_id"; return nullptr; }
+    if (!load_nccl(err)) return nullptr;
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    ShardComm* c = new ShardComm();
+    c->rank = rank;
+    c->world = world;
+    c->stream = stream;
+    if (!nccl_ok(g_nccl.CommInitRank(&c->comm, world, id, rank), "ncclCommInitRank", err)) { delete c; return nullptr; }
+    if (cudaMalloc(&c->d_scalar, sizeof(double)) != cudaSuccess) { err = "cudaMalloc failed"; g_nccl.CommDestroy(c->comm); delete c; return nullptr; }
+    return c;
+}
+
+void shard_comm_destroy(ShardComm* c) {
+    if (!c) return;
+    if (c->d_scalar) cudaFree(c->d_scalar);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    delete c;
+}
+
+bool shard_allreduce_sum(ShardComm* c, double* value, std::string& err) {
+    if (cudaMemcpyAsync(c->d_scalar, value, sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { err = "cudaMemcpyAsync failed"; return false; }
+    if (!nccl_ok(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclFloat64, ncclSum, c->comm, c->stream), "ncclAllReduce", err)) return false;
+    if (cudaMemcpyAsync(value, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        err = "all-reduce of a scalar failed";
+        return false;
+    }
+    return true;
+}
+
+bool shard_exchange_slots(ShardComm* c, void* base, size_t slot_bytes, void* staging, size_t chunk_bytes, std::string& err) {
+    char* b = static_cast<char*>(base);
+    // Round-robin pairing (peer = rank ^ step) so every step is a perfect matching over NVSwitch.
+    for (int step = 1; step < c->world; ++step) {
+        const int peer = c->rank ^ step;
+        char* slot = b + (size_t)peer * slot_bytes;
+        for (size_t off = 0; off < slot_bytes; off += chunk_bytes) {
+            const size_t len = slot_bytes - off < chunk_bytes ? slot_bytes - off : chunk_bytes;
+            if (!nccl_ok(g_nccl.GroupStart(), "ncclGroupStart", err)) return false;
+            if (!nccl_ok(g_nccl.Send(slot + off, len, ncclUint8, peer, c->comm, c->stream), "ncclSend", err)) return false;
+            if (!nccl_ok(g_nccl.Recv(staging, len, ncclUint8, peer, c->comm, c->stream), "ncclRecv", err)) return false;
+            if (!nccl_ok(g_nccl.GroupEnd(), "ncclGroupEnd", err)) return false;
+            if (cudaMemcpyAsync(slot + off, staging, len, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { err = "staging copy failed"; return false; }
+        }
+    }
+    return true;
+}
+
+}  // namespace qsv

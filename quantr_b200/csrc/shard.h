@@ -1,0 +1,25 @@
+// shard.h — NCCL plumbing for sharded registers (one process per GPU).
+//
+// The reference has no distributed code (README.md:96 "No parallelisation option"); this is new.
+// NCCL is loaded with dlopen at first use so that single-GPU users need no NCCL at all and so that
+// a process that already carries torch's bundled libnccl.so.2 shares that copy.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace qsv {
+
+struct ShardComm;
+
+bool shard_unique_id(void* out, size_t out_bytes, std::string& err);
+ShardComm* shard_comm_create(int rank, int world, const void* unique_id, size_t unique_id_bytes, cudaStream_t stream, std::string& err);
+void shard_comm_destroy(ShardComm* c);
+bool shard_allreduce_sum(ShardComm* c, double* value, std::string& err);
+// In-place pairwise exchange: for every peer p != rank, the `slot_bytes` at `base + p*slot_bytes` are swapped with
+// the peer's slot `rank`.  Staged through `staging` (>= chunk_bytes) in chunks.  Enqueued on the comm's stream.
+bool shard_exchange_slots(ShardComm* c, void* base, size_t slot_bytes, void* staging, size_t chunk_bytes, std::string& err);
+
+}  // namespace qsv

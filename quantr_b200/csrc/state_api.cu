@@ -1,0 +1,432 @@
+// state_api.cu — the device-resident register (`qsv_state`) and the C ABI around it.
+//
+// Replaces the `register: SuperPosition` owned by SimulatedCircuit (src/simulated_circuit.rs:20-27)
+// with a handle to 2^n complex-f64 amplitudes in HBM.  See include/qsv.h for the reference
+// interface each export stands in for.  No exception crosses the boundary.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "plan.h"
+#include "plan_handle.h"
+#include "shard.h"
+
+using namespace qsv;
+
+struct qsv_state {
+    uint32_t n_qubits = 0;  // logical qubits of the circuit
+    uint32_t n_local = 0;   // index bits held by this rank
+    uint32_t n_alloc = 0;   // allocated local bits (>= kMinQubits)
+    int device = 0;
+    int rank = 0, world = 1;
+    int sm_count = 148;
+    cplx* d_state = nullptr;
+    cudaStream_t stream = nullptr;
+    PlanOptions opt;
+    int timing = 0;
+    // measurement cache (K6): per-block sums + exclusive scan, valid until the register changes
+    double* d_sums = nullptr;
+    double* d_prefix = nullptr;
+    uint64_t n_blocks = 0;
+    uint32_t block_bits = 0;
+    bool prefix_valid = false;
+    double total_prob = 0.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ShardComm* comm = nullptr;
+    std::string error;
+};
+
+namespace {
+
+thread_local std::string g_global_error;
+
+int set_error(qsv_state* s, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (s) s->error = buf;
+    g_global_error = buf;
+    return code;
+}
+
+#define QSV_CUDA(s, call)                                                                                            \
+    do {                                                                                                             \
+        cudaError_t e__ = (call);                                                                                    \
+        if (e__ != cudaSuccess) {                                                                                    \
+            cudaGetLastError();                                                                                      \
+            return set_error(s, e__ == cudaErrorMemoryAllocation ? QSV_ERR_OUT_OF_MEMORY : QSV_ERR_CUDA, "%s: %s", #call, \
+                             cudaGetErrorString(e__));                                                               \
+        }                                                                                                            \
+    } while (0)
+
+uint64_t local_len(const qsv_state* s) { return 1ull << s->n_local; }
+uint64_t rank_base(const qsv_state* s) { return (uint64_t)s->rank << s->n_local; }
+
+int create_common(qsv_state** out, uint32_t n_qubits, int device, int rank, int world) {
+    if (!out) return set_error(nullptr, QSV_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (n_qubits == 0 || n_qubits > 62) return set_error(nullptr, QSV_ERR_INVALID_ARG, "n_qubits must be in 1..62");
+    uint32_t g = 0;
+    while ((1 << g) < world) ++g;
+    if (world < 1 || (1 << g) != world || rank < 0 || rank >= world) return set_error(nullptr, QSV_ERR_INVALID_ARG, "world must be a power of two and 0 <= rank < world");
+    if (g >= n_qubits) return set_error(nullptr, QSV_ERR_INVALID_ARG, "more ranks than amplitudes");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return set_error(nullptr, QSV_ERR_CUDA, "no usable CUDA device (%s); quantr_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return set_error(nullptr, QSV_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, count);
+    qsv_state* s = new (std::nothrow) qsv_state();
+    if (!s) return set_error(nullptr, QSV_ERR_OUT_OF_MEMORY, "host allocation failed");
+    s->n_qubits = n_qubits;
+    s->n_local = n_qubits - g;
+    s->n_alloc = s->n_local < (uint32_t)kMinQubits ? (uint32_t)kMinQubits : s->n_local;
+    s->device = device;
+    s->rank = rank;
+    s->world = world;
+    auto fail = [&](int code) { qsv_destroy(s); return code; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(set_error(nullptr, QSV_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e)));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(set_error(nullptr, QSV_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)));
+    s->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(set_error(nullptr, QSV_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)));
+    const size_t bytes = sizeof(cplx) << s->n_alloc;
+    if ((e = cudaMalloc(&s->d_state, bytes)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(set_error(nullptr, e == cudaErrorMemoryAllocation ? QSV_ERR_OUT_OF_MEMORY : QSV_ERR_CUDA, "cudaMalloc of %zu bytes for a %u-qubit register: %s", bytes, s->n_local, cudaGetErrorString(e)));
+    }
+    s->block_bits = s->n_alloc < 12 ? s->n_alloc : 12;
+    s->n_blocks = 1ull << (s->n_alloc - s->block_bits);
+    if ((e = cudaMalloc(&s->d_sums, sizeof(double) * s->n_blocks)) != cudaSuccess || (e = cudaMalloc(&s->d_prefix, sizeof(double) * (s->n_blocks + 1))) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(set_error(nullptr, QSV_ERR_OUT_OF_MEMORY, "cudaMalloc of the measurement scratch: %s", cudaGetErrorString(e)));
+    }
+    cudaEventCreate(&s->ev0);
+    cudaEventCreate(&s->ev1);
+    *out = s;
+    return QSV_OK;
+}
+
+int upload_plan(qsv_state* s, qsv_plan* p);
+
+void release_plan_device(qsv_plan* p) {
+    if (p->plan.dev_blob) {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(p->plan.dev_device);
+        cudaFree(p->plan.dev_blob);
+        if (prev >= 0) cudaSetDevice(prev);
+        p->plan.dev_blob = nullptr;
+    }
+}
+
+int upload_plan(qsv_state* s, qsv_plan* p) {
+    Plan& plan = p->plan;
+    if (plan.dev_blob && plan.dev_device == s->device) return QSV_OK;
+    if (plan.dev_blob) release_plan_device(p);
+    size_t total = 0;
+    plan.dev_offsets.clear();
+    for (auto& b : plan.passes) {
+        plan.dev_offsets.push_back(total);
+        total += (b.size() + 255) & ~size_t(255);
+    }
+    if (total == 0) return QSV_OK;
+    std::vector<uint8_t> host(total, 0);
+    for (size_t i = 0; i < plan.passes.size(); ++i) memcpy(host.data() + plan.dev_offsets[i], plan.passes[i].data(), plan.passes[i].size());
+    QSV_CUDA(s, cudaMalloc(&plan.dev_blob, total));
+    plan.dev_device = s->device;
+    p->release_device = release_plan_device;
+    QSV_CUDA(s, cudaMemcpyAsync(plan.dev_blob, host.data(), total, cudaMemcpyHostToDevice, s->stream));
+    QSV_CUDA(s, cudaStreamSynchronize(s->stream));  // `host` goes out of scope
+    return QSV_OK;
+}
+
+int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
+    Plan& plan = p->plan;
+    if (plan.n_qubits != s->n_qubits || plan.n_local != s->n_local)
+        return set_error(s, QSV_ERR_INVALID_ARG, "plan was made for %u/%u qubits, the handle holds %u/%u", plan.n_qubits, plan.n_local, s->n_qubits, s->n_local);
+    int rc = upload_plan(s, p);
+    if (rc != QSV_OK) return rc;
+    s->prefix_valid = false;
+    if (s->timing) QSV_CUDA(s, cudaEventRecord(s->ev0, s->stream));
+    for (size_t i = 0; i < plan.passes.size(); ++i) {
+        const DevPass& hdr = *reinterpret_cast<const DevPass*>(plan.passes[i].data());
+        QSV_CUDA(s, launch_pass(s->d_state, static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[i], hdr, rank_base(s), s->sm_count, s->stream));
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->n_gates = plan.n_gates;
+        stats->n_passes = plan.passes.size();
+        stats->n_rounds = plan.n_rounds;
+        stats->n_kernel_launches = plan.passes.size();
+        stats->bytes_per_pass = 32ull << s->n_alloc;
+    }
+    if (s->timing) {
+        QSV_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+        QSV_CUDA(s, cudaEventSynchronize(s->ev1));
+        float ms = 0.f;
+        QSV_CUDA(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        if (stats) stats->device_ms = ms;
+    }
+    return QSV_OK;
+}
+
+int ensure_prefix(qsv_state* s) {
+    if (s->prefix_valid) return QSV_OK;
+    QSV_CUDA(s, launch_prob_block_sums(s->d_state, s->d_sums, s->n_blocks, s->block_bits, s->sm_count, s->stream));
+    QSV_CUDA(s, launch_scan_block_sums(s->d_sums, s->d_prefix, s->n_blocks, s->stream));
+    QSV_CUDA(s, cudaMemcpyAsync(&s->total_prob, s->d_prefix + s->n_blocks, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    QSV_CUDA(s, cudaStreamSynchronize(s->stream));
+    s->prefix_valid = true;
+    return QSV_OK;
+}
+
+}  // namespace
+
+#define QSV_ENTER(s)                                                          \
+    if (!(s)) return set_error(nullptr, QSV_ERR_INVALID_ARG, "handle is NULL"); \
+    {                                                                         \
+        cudaError_t e0__ = cudaSetDevice((s)->device);                        \
+        if (e0__ != cudaSuccess) return set_error(s, QSV_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e0__)); \
+    }
+
+extern "C" {
+
+int qsv_create(qsv_state** out, uint32_t n_qubits, int device) {
+    try {
+        int rc = create_common(out, n_qubits, device, 0, 1);
+        if (rc != QSV_OK) return rc;
+        return qsv_init_basis(*out, 0);
+    } catch (...) {
+        return set_error(nullptr, QSV_ERR_INTERNAL, "unexpected exception in qsv_create");
+    }
+}
+
+int qsv_create_sharded(qsv_state** out, uint32_t n_qubits, int device, int rank, int world, const void* nccl_unique_id, size_t nccl_unique_id_bytes) {
+    try {
+        if (world == 1) return qsv_create(out, n_qubits, device);
+        int rc = create_common(out, n_qubits, device, rank, world);
+        if (rc != QSV_OK) return rc;
+        qsv_state* s = *out;
+        std::string err;
+        s->comm = shard_comm_create(rank, world, nccl_unique_id, nccl_unique_id_bytes, s->stream, err);
+        if (!s->comm) {
+            set_error(nullptr, QSV_ERR_NCCL, "%s", err.c_str());
+            qsv_destroy(s);
+            *out = nullptr;
+            return QSV_ERR_NCCL;
+        }
+        return qsv_init_basis(s, 0);
+    } catch (...) {
+        return set_error(nullptr, QSV_ERR_INTERNAL, "unexpected exception in qsv_create_sharded");
+    }
+}
+
+int qsv_nccl_unique_id(void* out, size_t out_bytes) {
+    std::string err;
+    if (!shard_unique_id(out, out_bytes, err)) return set_error(nullptr, QSV_ERR_NCCL, "%s", err.c_str());
+    return QSV_OK;
+}
+
+int qsv_destroy(qsv_state* s) {
+    if (!s) return QSV_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->comm) shard_comm_destroy(s->comm);
+    if (s->d_state) cudaFree(s->d_state);
+    if (s->d_sums) cudaFree(s->d_sums);
+    if (s->d_prefix) cudaFree(s->d_prefix);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return QSV_OK;
+}
+
+const char* qsv_last_error(const qsv_state* s) { return s ? s->error.c_str() : g_global_error.c_str(); }
+
+int qsv_set_option(qsv_state* s, const char* key, int64_t value) {
+    if (!s || !key) return set_error(s, QSV_ERR_INVALID_ARG, "NULL argument");
+    const std::string k(key);
+    if (k == "tile_bits") {
+        if (value < kRegBits || value > kMaxTileBits) return set_error(s, QSV_ERR_INVALID_ARG, "tile_bits must be in %d..%d", kRegBits, kMaxTileBits);
+        s->opt.tile_bits = (int)value;
+    } else if (k == "low_bits") {
+        if (value < 0 || value > 8) return set_error(s, QSV_ERR_INVALID_ARG, "low_bits must be in 0..8");
+        s->opt.low_bits = (int)value;
+    } else if (k == "fuse") {
+        s->opt.fuse = value ? 1 : 0;
+    } else if (k == "timing") {
+        s->timing = value ? 1 : 0;
+    } else {
+        return set_error(s, QSV_ERR_INVALID_ARG, "unknown option '%s'", key);
+    }
+    return QSV_OK;
+}
+
+int qsv_get_info(const qsv_state* s, const char* key, int64_t* value) {
+    if (!s || !key || !value) return set_error(nullptr, QSV_ERR_INVALID_ARG, "NULL argument");
+    const std::string k(key);
+    if (k == "n_qubits") *value = s->n_qubits;
+    else if (k == "n_local_qubits") *value = s->n_local;
+    else if (k == "n_alloc_qubits") *value = s->n_alloc;
+    else if (k == "sm_count") *value = s->sm_count;
+    else if (k == "tile_bits") *value = s->opt.tile_bits;
+    else if (k == "low_bits") *value = s->opt.low_bits;
+    else if (k == "device") *value = s->device;
+    else if (k == "rank") *value = s->rank;
+    else if (k == "world") *value = s->world;
+    else return QSV_ERR_INVALID_ARG;
+    return QSV_OK;
+}
+
+int qsv_init_basis(qsv_state* s, uint64_t index) {
+    QSV_ENTER(s);
+    if (index >> s->n_qubits) return set_error(s, QSV_ERR_INVALID_ARG, "basis index out of range");
+    QSV_CUDA(s, cudaMemsetAsync(s->d_state, 0, sizeof(cplx) << s->n_alloc, s->stream));
+    if ((index >> s->n_local) == (uint64_t)s->rank)
+        QSV_CUDA(s, launch_set_amp(s->d_state, index & (local_len(s) - 1), 1.0, 0.0, s->stream));
+    s->prefix_valid = false;
+    return QSV_OK;
+}
+
+int qsv_upload(qsv_state* s, const double* host_amps, uint64_t first, uint64_t count) {
+    QSV_ENTER(s);
+    if (!host_amps && count) return set_error(s, QSV_ERR_INVALID_ARG, "host_amps is NULL");
+    if (first < rank_base(s) || first - rank_base(s) + count > local_len(s)) return set_error(s, QSV_ERR_INVALID_ARG, "range is outside this rank's shard");
+    QSV_CUDA(s, cudaMemcpyAsync(s->d_state + (first - rank_base(s)), host_amps, sizeof(cplx) * count, cudaMemcpyHostToDevice, s->stream));
+    QSV_CUDA(s, cudaStreamSynchronize(s->stream));
+    s->prefix_valid = false;
+    return QSV_OK;
+}
+
+int qsv_download(qsv_state* s, double* host_amps, uint64_t first, uint64_t count) {
+    QSV_ENTER(s);
+    if (!host_amps && count) return set_error(s, QSV_ERR_INVALID_ARG, "host_amps is NULL");
+    if (first < rank_base(s) || first - rank_base(s) + count > local_len(s)) return set_error(s, QSV_ERR_INVALID_ARG, "range is outside this rank's shard");
+    QSV_CUDA(s, cudaMemcpyAsync(host_amps, s->d_state + (first - rank_base(s)), sizeof(cplx) * count, cudaMemcpyDeviceToHost, s->stream));
+    QSV_CUDA(s, cudaStreamSynchronize(s->stream));
+    return QSV_OK;
+}
+
+int qsv_gather(qsv_state* s, const uint64_t* indices, uint64_t count, double* host_amps) {
+    QSV_ENTER(s);
+    if (count == 0) return QSV_OK;
+    if (!indices || !host_amps) return set_error(s, QSV_ERR_INVALID_ARG, "NULL argument");
+    try {
+        std::vector<uint64_t> local(count);
+        for (uint64_t i = 0; i < count; ++i) {
+            if (indices[i] < rank_base(s) || indices[i] - rank_base(s) >= local_len(s)) return set_error(s, QSV_ERR_INVALID_ARG, "index %llu is outside this rank's shard", (unsigned long long)indices[i]);
+            local[i] = indices[i] - rank_base(s);
+        }
+        uint64_t* d_idx = nullptr;
+        cplx* d_out = nullptr;
+        QSV_CUDA(s, cudaMalloc(&d_idx, sizeof(uint64_t) * count));
+        cudaError_t e = cudaMalloc(&d_out, sizeof(cplx) * count);
+        if (e != cudaSuccess) { cudaFree(d_idx); return set_error(s, QSV_ERR_OUT_OF_MEMORY, "cudaMalloc: %s", cudaGetErrorString(e)); }
+        int rc = QSV_OK;
+        if ((e = cudaMemcpyAsync(d_idx, local.data(), sizeof(uint64_t) * count, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess ||
+            (e = launch_gather(s->d_state, d_idx, d_out, count, s->stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(host_amps, d_out, sizeof(cplx) * count, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(s->stream)) != cudaSuccess)
+            rc = set_error(s, QSV_ERR_CUDA, "gather: %s", cudaGetErrorString(e));
+        cudaFree(d_idx);
+        cudaFree(d_out);
+        return rc;
+    } catch (const std::bad_alloc&) {
+        return set_error(s, QSV_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+}
+
+int qsv_apply(qsv_state* s, const qsv_op* ops, size_t n_ops, qsv_stats* stats) {
+    QSV_ENTER(s);
+    qsv_plan* p = nullptr;
+    int rc = qsv_plan_create(&p, s->n_qubits, s->n_local, ops, n_ops, (uint32_t)s->opt.tile_bits, (uint32_t)s->opt.low_bits, s->opt.fuse);
+    if (rc != QSV_OK) return set_error(s, rc, "%s", qsv_plan_last_error());
+    try {
+        rc = run_plan_impl(s, p, stats);
+        if (rc == QSV_OK) {
+            cudaError_t e = cudaStreamSynchronize(s->stream);  // the plan's device copy is freed below
+            if (e != cudaSuccess) rc = set_error(s, QSV_ERR_CUDA, "fused pass failed: %s", cudaGetErrorString(e));
+        }
+    } catch (const std::exception& e) {
+        rc = set_error(s, QSV_ERR_INTERNAL, "%s", e.what());
+    } catch (...) {
+        rc = set_error(s, QSV_ERR_INTERNAL, "unexpected exception in qsv_apply");
+    }
+    qsv_plan_destroy(p);
+    return rc;
+}
+
+int qsv_run_plan(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
+    QSV_ENTER(s);
+    if (!p) return set_error(s, QSV_ERR_INVALID_ARG, "plan is NULL");
+    try {
+        return run_plan_impl(s, p, stats);
+    } catch (const std::exception& e) {
+        return set_error(s, QSV_ERR_INTERNAL, "%s", e.what());
+    } catch (...) {
+        return set_error(s, QSV_ERR_INTERNAL, "unexpected exception in qsv_run_plan");
+    }
+}
+
+int qsv_sample(qsv_state* s, const double* uniforms, uint64_t shots, uint64_t* out_indices) {
+    QSV_ENTER(s);
+    if (shots == 0) return QSV_OK;
+    if (!uniforms || !out_indices) return set_error(s, QSV_ERR_INVALID_ARG, "NULL argument");
+    if (s->world > 1) return set_error(s, QSV_ERR_UNSUPPORTED, "sampling on a sharded handle is not supported yet");
+    int rc = ensure_prefix(s);
+    if (rc != QSV_OK) return rc;
+    double* d_u = nullptr;
+    uint64_t* d_out = nullptr;
+    QSV_CUDA(s, cudaMalloc(&d_u, sizeof(double) * shots));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(uint64_t) * shots);
+    if (e != cudaSuccess) { cudaFree(d_u); return set_error(s, QSV_ERR_OUT_OF_MEMORY, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    if ((e = cudaMemcpyAsync(d_u, uniforms, sizeof(double) * shots, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess ||
+        (e = launch_sample_shots(s->d_state, s->d_prefix, s->n_blocks, s->block_bits, d_u, shots, rank_base(s), d_out, s->sm_count, s->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(out_indices, d_out, sizeof(uint64_t) * shots, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(s->stream)) != cudaSuccess)
+        rc = set_error(s, QSV_ERR_CUDA, "sample: %s", cudaGetErrorString(e));
+    cudaFree(d_u);
+    cudaFree(d_out);
+    return rc;
+}
+
+int qsv_norm_sqr(qsv_state* s, double* out) {
+    QSV_ENTER(s);
+    if (!out) return set_error(s, QSV_ERR_INVALID_ARG, "out is NULL");
+    int rc = ensure_prefix(s);
+    if (rc != QSV_OK) return rc;
+    double total = s->total_prob;
+    if (s->comm) {
+        std::string err;
+        if (!shard_allreduce_sum(s->comm, &total, err)) return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
+    }
+    *out = total;
+    return QSV_OK;
+}
+
+int qsv_synchronize(qsv_state* s) {
+    QSV_ENTER(s);
+    QSV_CUDA(s, cudaStreamSynchronize(s->stream));
+    return QSV_OK;
+}
+
+int qsv_device_pointer(qsv_state* s, void** dev_ptr, void** cuda_stream) {
+    if (!s) return set_error(nullptr, QSV_ERR_INVALID_ARG, "handle is NULL");
+    if (dev_ptr) *dev_ptr = s->d_state;
+    if (cuda_stream) *cuda_stream = s->stream;
+    return QSV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+"""The C-ABI library loads and exports every symbol include/qsv.h declares (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from helpers import ROOT
+from quantr_b200 import _ffi as F
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "qsv.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qsv_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert declared_functions() == sorted(F.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = F.load_library()
+    for name in declared_functions():
+        assert hasattr(lib, name), name
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(F.QsvOp) == 56
+    assert C.sizeof(F.QsvStats) == 72
+    assert F.QsvOp.controls.offset == 16 and F.QsvOp.param.offset == 24 and F.QsvOp.matrix.offset == 40
+
+
+def test_create_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a box without a CUDA device qsv_create must fail with a message."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    lib = F.load_library()
+    h = C.c_void_p()
+    rc = lib.qsv_create(C.byref(h), 3, 0)
+    assert rc == 3 and not h.value
+    assert b"no CPU fallback" in lib.qsv_last_error(None)
+    import quantr_b200 as qb
+    with pytest.raises(F.QsvError):
+        qb.Circuit.new(2).add_gate(qb.Gate.H, 0).simulate()
+
+
+def test_null_handles_are_rejected():
+    lib = F.load_library()
+    assert lib.qsv_init_basis(None, 0) == 1
+    assert lib.qsv_destroy(None) == 0
+    assert lib.qsv_plan_destroy(None) == 0

@@ -1,0 +1,235 @@
+"""Parity tests proper: the sm_100a path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): amplitudes within 1e-12 max-abs of the oracle on identical circuits;
+measure_all bin counts pass a chi-square test against the oracle's probabilities.
+"""
+import numpy as np
+import pytest
+
+from golden import reference_vectors as rv
+from helpers import (OracleCircuit, encode_gates, orc, qb, qft_circuit, qft_expected, random_any_gate_circuit,
+                     random_layered_circuit, st)
+from quantr_b200 import _ffi as F
+
+pytestmark = pytest.mark.gpu
+G, Circuit = qb.Gate, qb.Circuit
+TOL = 1e-12
+
+
+def device_run(n, enc, reg=None, **opts):
+    s = qb.DeviceState(n)
+    for k, v in opts.items():
+        s.set_option(k, v)
+    if reg is not None:
+        s.upload(reg)
+    stats = s.apply(enc)
+    out = s.download()
+    s.close()
+    return out, stats
+
+
+@pytest.mark.parametrize("vec", rv.VECTORS, ids=[v["name"] for v in rv.VECTORS])
+def test_reference_golden_vectors_on_device(vec):
+    """The reference's own tests, replayed through Circuit::simulate -> libqsv.so."""
+    amps = vec["build"](Circuit, G, st).simulate().get_state().take().get_amplitudes()
+    assert np.max(np.abs(amps - np.array(vec["expect"]))) < TOL
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_circuits_match_oracle(seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1, 19))
+    c = random_any_gate_circuit(OracleCircuit, G, n, int(rng.integers(1, 200)), rng)
+    enc = encode_gates(c.circuit_gates, n)
+    reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    reg /= np.linalg.norm(reg)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense", threads=4)
+    for opts in ({}, {"tile_bits": 8, "low_bits": 2}, {"tile_bits": 13}, {"fuse": 0, "tile_bits": 10}):
+        out, _ = device_run(n, enc, reg, **opts)
+        assert np.max(np.abs(out - ref)) < TOL, (n, opts)
+
+
+@pytest.mark.parametrize("n", [20, 22, 24])
+def test_layered_circuit_matches_oracle_at_scale(n):
+    """BASELINE config 3's generator (H/Rx/Ry/Rz/CNot/Toffoli) at sizes the dense oracle finishes in seconds."""
+    c = random_layered_circuit(OracleCircuit, G, n, 8, seed=30)
+    enc = encode_gates(c.circuit_gates, n)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, None, mode="dense", threads=8)
+    out, stats = device_run(n, enc)
+    assert np.max(np.abs(out - ref)) < TOL
+    assert stats["n_passes"] < stats["n_gates"]
+
+
+def test_qft16_config2_matches_oracle_and_closed_form():
+    """BASELINE config 2: QFT on 16 qubits from |0xACE1>, plus the variant with a 3-wire Custom QFT."""
+    n, x = 16, 0xACE1
+    c = qft_circuit(Circuit, G, n, x)
+    enc = encode_gates(c.circuit_gates, n)
+    reg = np.zeros(1 << n, dtype=np.complex128)
+    reg[x] = 1
+    ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense", threads=4)
+    amps = c.simulate().get_state().take().get_amplitudes()
+    assert np.max(np.abs(amps - ref)) < TOL
+    assert np.max(np.abs(amps - qft_expected(n, x))) < TOL
+    # variant: the last three wires' sub-QFT as one Gate::Custom exactly as tests/qft.rs:27-28,51-67
+    c2 = Circuit.new(n)
+    for pos in range(n - 3):
+        c2.add_gate(G.H, pos)
+        for k in range(2, n - pos + 1):
+            c2.add_gate(G.CRk(k, pos + k - 1), pos)
+    c2.add_gate(G.Custom(rv.make_qft_closure(Circuit, G), [13, 14], "QFT"), 15)
+    c2.change_register(st.ProductState.binary_basis(x, n))
+    amps2 = c2.simulate().get_state().take().get_amplitudes()
+    assert np.max(np.abs(amps2 - ref)) < TOL
+
+
+@pytest.mark.parametrize("n", [26, 28])
+def test_qft_closed_form_large(n):
+    """Sizes beyond the oracle's reach in test time: closed-form QFT amplitudes on random indices + norm."""
+    x = 0x123456789 & ((1 << n) - 1)
+    c = qft_circuit(OracleCircuit, G, n)
+    enc = encode_gates(c.circuit_gates, n)
+    s = qb.DeviceState(n)
+    s.init_basis(x)
+    stats = s.apply(enc)
+    rng = np.random.default_rng(n)
+    idx = rng.integers(0, 1 << n, size=4096, dtype=np.uint64)
+    got = s.gather(idx)
+    rev = np.zeros_like(idx)
+    for b in range(n):
+        rev |= ((idx >> np.uint64(b)) & np.uint64(1)) << np.uint64(n - 1 - b)
+    phase = np.array([(int(r) * x) % (1 << n) for r in rev], dtype=np.float64) * (2 * np.pi / (1 << n))
+    expect = (np.cos(phase) + 1j * np.sin(phase)) / np.sqrt(float(1 << n))
+    assert np.max(np.abs(got - expect)) < TOL
+    assert abs(s.norm_sqr() - 1.0) < 1e-12
+    assert stats["n_passes"] <= 4
+    s.close()
+
+
+def test_x3sudoko_on_device():
+    """tests/grovers.rs:75-155 through the device path, incl. the reference's own assertions."""
+    qb.seed(0)
+    sim = rv.build_x3sudoko(Circuit, G, st).simulate()
+    sim.print_warnings(True)
+    amps = sim.get_state().take().get_amplitudes()
+    ref = rv.build_x3sudoko(OracleCircuit, G, st).simulate().get_state().take().get_amplitudes()
+    assert np.max(np.abs(amps - ref)) < TOL
+    bins = sim.measure_all(5000).take()
+    assert sum(bins.values()) == 5000
+    for state, count in bins.items():
+        if state.to_string()[:6] in rv.SUDOKU_SOLUTIONS:
+            assert count > 150
+        else:
+            assert count < 150
+
+
+def test_grovers_config1_measure_all():
+    """BASELINE config 1 (examples/grovers.rs) + the assertions of tests/grovers.rs:62-69."""
+    qb.seed(0)
+    sim = rv.build_grovers_3qubit(Circuit, G, st).simulate()
+    bins = sim.measure_all(500).take()
+    for state, count in bins.items():
+        assert state.to_string() in ("011", "111") and count > 200
+    sim1 = rv.build_example_grovers(Circuit, G, st).simulate()
+    p = np.abs(sim1.get_state().take().get_amplitudes()) ** 2
+    assert abs(p[6] - 0.5) < TOL and abs(p[7] - 0.5) < TOL
+
+
+def chi_square_p(counts, probs, shots):
+    """Pearson chi-square with bins of expected count < 5 merged (SURVEY.md 8d protocol)."""
+    from scipy import stats as sps
+    expected = probs * shots
+    order = np.argsort(expected)
+    obs_m, exp_m, acc_o, acc_e = [], [], 0.0, 0.0
+    for i in order:
+        acc_o += counts[i]
+        acc_e += expected[i]
+        if acc_e >= 5:
+            obs_m.append(acc_o)
+            exp_m.append(acc_e)
+            acc_o = acc_e = 0.0
+    if acc_e > 0 and exp_m:
+        obs_m[-1] += acc_o
+        exp_m[-1] += acc_e
+    obs_m, exp_m = np.array(obs_m), np.array(exp_m)
+    chi2 = np.sum((obs_m - exp_m) ** 2 / exp_m)
+    return float(sps.chi2.sf(chi2, len(obs_m) - 1))
+
+
+@pytest.mark.parametrize("n", [5, 12, 14])
+def test_measure_all_chi_square_and_exact_inverse_cdf(n):
+    rng = np.random.default_rng(7 + n)
+    c = random_any_gate_circuit(OracleCircuit, G, n, 60, rng)
+    enc = encode_gates(c.circuit_gates, n)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, None, mode="dense")
+    s = qb.DeviceState(n)
+    s.apply(enc)
+    shots = 200000
+    u = rng.random(shots)
+    got = s.sample(u)
+    assert not np.any(got == np.uint64(F.UINT64_MAX))
+    counts = np.bincount(got.astype(np.int64), minlength=1 << n).astype(np.float64)
+    probs = np.abs(ref) ** 2
+    assert chi_square_p(counts, probs / probs.sum(), shots) > 1e-3
+    # the same uniforms through the reference's sequential rule: identical except within rounding of a boundary
+    want = orc.measure_all(n, s.download(), u)
+    assert np.mean(got != want) < 1e-4
+    s.close()
+
+
+def test_failed_collapse_and_strictness_on_device():
+    """Non-unitary register (total probability 0.25): shots with u >= total return UINT64_MAX."""
+    s = qb.DeviceState(2)
+    s.upload(np.array([0.5, 0, 0, 0], dtype=np.complex128))
+    got = s.sample(np.array([0.1, 0.2499, 0.25, 0.9]))
+    assert [int(g) for g in got] == [0, 0, F.UINT64_MAX, F.UINT64_MAX]
+    assert abs(s.norm_sqr() - 0.25) < 1e-15
+    s.upload(np.array([0.5, 0.5, 0.5, 0.5], dtype=np.complex128))
+    got = s.sample(np.array([0.0, 0.2499999, 0.25, 0.5, 0.74, 0.75, 0.999999]))
+    assert [int(g) for g in got] == [0, 0, 1, 2, 2, 3, 3]
+    s.close()
+
+
+def test_post_select_example_and_measure_all_without_cache():
+    """examples/post_select.rs:39-49 (non-unitary Custom) and simulated_circuit.rs:81-114."""
+    def post_select(prod):
+        if prod.get_qubits()[0] == st.Qubit.Zero:
+            return st.SuperPosition.new_with_amplitudes_unchecked([np.sqrt(2.0), 0.0])
+        return st.SuperPosition.new_with_amplitudes_unchecked([0.0, 0.0])
+
+    c = Circuit.new(2)
+    c.add_gate(G.H, 0).add_gate(G.H, 1).add_gate(G.Custom(post_select, [], "P"), 1)
+    sim = c.simulate()
+    sim.print_warnings(True)
+    assert np.allclose(sim.get_state().take().get_amplitudes(), [np.sqrt(0.5), 0, np.sqrt(0.5), 0], atol=1e-15)
+    qb.seed(1)
+    bins = sim.measure_all_without_cache(40).take()
+    assert set(k.to_string() for k in bins) <= {"00", "10"} and sum(bins.values()) == 40
+
+
+def test_plan_rerun_and_range_access():
+    n = 18
+    c = qft_circuit(OracleCircuit, G, n)
+    enc = encode_gates(c.circuit_gates, n)
+    plan = qb.Plan(n, enc)
+    s = qb.DeviceState(n)
+    outs = []
+    for x in (1, 77777):
+        s.init_basis(x)
+        s.run_plan(plan)
+        outs.append(s.download(1000, 5000))
+        assert np.max(np.abs(outs[-1] - qft_expected(n, x)[1000:6000])) < TOL
+    s.close()
+
+
+def test_error_paths_on_device():
+    s = qb.DeviceState(3)
+    with pytest.raises(F.QsvError):
+        s.init_basis(8)
+    with pytest.raises(F.QsvError):
+        s.download(4, 8)
+    with pytest.raises(F.QsvError):
+        s.set_option("tile_bits", 99)
+    with pytest.raises(F.QsvError):
+        s.gather([9])
+    s.close()

@@ -1,0 +1,115 @@
+"""Host-side logic that stays on the host in the reference too: builder layout, validation,
+state types, gate-list encoding.  Reference: src/circuit.rs:124-341 and its tests :516-597."""
+import numpy as np
+import pytest
+
+from golden import reference_vectors as rv
+from helpers import encode_gates, qb, st
+from quantr_b200 import _ffi as F
+
+G, Circuit, QuantrError = qb.Gate, qb.Circuit, qb.QuantrError
+
+
+def test_pushes_multi_gates():  # src/circuit.rs:535-551
+    c = Circuit.new(3)
+    c.add_gates([G.CNot(2), G.CNot(0), G.H]).add_gates([G.Toffoli(1, 2), G.H, G.CNot(0)])
+    assert [repr(g) for g in c.get_gates()] == rv.LAYOUT_EXPECT
+
+
+def test_pushes_multi_gates_using_vec():  # src/circuit.rs:554-575
+    c = Circuit.new(3)
+    c.add_gates_with_positions({2: G.H, 0: G.CNot(2), 1: G.CNot(0)})
+    c.add_gates_with_positions({2: G.CNot(0), 0: G.Toffoli(1, 2), 1: G.H})
+    assert [repr(g) for g in c.get_gates()] == rv.LAYOUT_EXPECT
+
+
+def test_single_multi_gate_column_is_left_alone():
+    c = Circuit.new(3)
+    c.add_gate(G.CNot(0), 2)
+    assert [repr(g) for g in c.get_gates()] == ["Id", "Id", "CNot(0)"]
+
+
+@pytest.mark.parametrize("bad", [
+    lambda c: c.add_gates([G.Id, G.Custom(rv.example_cnot(st), [1], "X"), G.Id]),  # circuit.rs:516-523
+    lambda c: c.add_gates([G.CNot(0), G.Id, G.Id]),  # :525-532
+    lambda c: c.add_gates_with_positions({2: G.H, 0: G.CNot(0), 1: G.CNot(0)}),  # :577-585
+    lambda c: c.add_gates_with_positions({2: G.H, 0: G.CNot(2), 1: G.CNot(3)}),  # :587-597
+    lambda c: c.add_gate(G.Custom(rv.example_cnot(st), [0], "NonAscii†"), 1),  # :839-845
+    lambda c: c.add_gates([G.H, G.H]),
+    lambda c: c.add_gate(G.H, 3),
+    lambda c: c.add_gate(G.Toffoli(1, 1), 0),
+])
+def test_builder_rejects(bad):
+    with pytest.raises(QuantrError):
+        bad(Circuit.new(3))
+
+
+def test_catches_repeating_positions():  # circuit.rs:715-720
+    with pytest.raises(QuantrError):
+        Circuit.new(4).add_repeating_gate(G.X, [0, 1, 1, 3])
+
+
+def test_custom_register_wrong_dimension():  # circuit.rs:984-991
+    c = Circuit.new(3)
+    with pytest.raises(QuantrError):
+        c.add_gate(G.X, 1).change_register(st.ProductState.new_unchecked([st.Qubit.One, st.Qubit.Zero]))
+
+
+def test_zero_qubit_circuit_rejected():
+    with pytest.raises(QuantrError):
+        Circuit.new(0)
+
+
+def test_product_state_bit_conventions():  # product_states.rs:275-320
+    p = st.ProductState.binary_basis(5, 4)
+    assert p.to_string() == "0101" and p.comp_basis() == 5
+    assert st.ProductState.new([st.Qubit.One, st.Qubit.Zero]).comp_basis() == 2
+    p.insert_qubits([st.Qubit.One, st.Qubit.Zero], [0, 3])
+    assert p.to_string() == "1100"
+    assert st.Qubit.One.kronecker_prod(st.Qubit.Zero).kronecker_prod(st.Qubit.One).to_string() == "101"
+    with pytest.raises(QuantrError):
+        st.ProductState.new([])
+    with pytest.raises(QuantrError):
+        p.invert_digit(4)
+    assert p.invert_digit(1).to_string() == "1000"
+
+
+def test_super_position_validation():  # super_positions.rs:403-544
+    with pytest.raises(QuantrError):
+        st.SuperPosition.new_with_amplitudes([1, 0, 0])
+    with pytest.raises(QuantrError):
+        st.SuperPosition.new_with_amplitudes([0.5, 0.5])
+    sp = st.SuperPosition.new_with_amplitudes([0, 1j, 0, 0])
+    assert sp.get_num_qubits() == 2 and sp.get_dimension() == 4
+    assert sp.get_amplitude(1) == 1j and sp.get_amplitude(4) is None
+    assert sp.get_amplitude_from_state(st.ProductState.binary_basis(1, 2)) == 1j
+    assert sp.to_hash_map() == {st.ProductState.binary_basis(1, 2): 1j}
+    items = list(sp)
+    assert len(items) == 4 and items[1][0].to_string() == "01"  # zeros included, super_position_iter.rs:23-37
+    hp = st.SuperPosition.new_with_hash_amplitudes({st.ProductState.binary_basis(2, 2): 1.0})
+    assert hp.get_amplitudes()[2] == 1.0
+    assert st.SuperPosition.new(2).get_amplitudes()[0] == 1.0
+
+
+def test_encoding_walks_gate_vector_like_simulation_rs():
+    """simulation.rs:37-56: flat position -> wire = position mod n, Id skipped, order kept."""
+    c = Circuit.new(3)
+    c.add_gates([G.CNot(2), G.CNot(0), G.H]).add_gate(G.Rx(0.25), 1).add_gate(G.CRk(3, 0), 2)
+    enc = encode_gates(c.get_gates(), 3)
+    got = [(enc.ops[i].kind, enc.ops[i].target, [enc.ops[i].controls[j] for j in range(enc.ops[i].n_controls)])
+           for i in range(enc.n_ops)]
+    assert got == [(F.GATE_H, 2, []), (F.GATE_CNOT, 0, [2]), (F.GATE_CNOT, 1, [0]), (F.GATE_RX, 1, []), (F.GATE_CRK, 2, [0])]
+    assert enc.ops[3].param == 0.25 and enc.ops[4].iparam == 3
+
+
+def test_custom_expansion_matrix_and_none_mask():
+    """Host expansion of a Custom closure: column s = closure(binary_basis(s))."""
+    from quantr_b200.circuit import expand_custom
+    m, none = expand_custom(G.Custom(rv.example_cnot(st), [2], "cNot"))
+    assert list(none) == [1, 1, 0, 0]
+    assert m[3, 2] == 1 and m[2, 3] == 1 and np.count_nonzero(m) == 2
+
+    def bad(prod):
+        return st.SuperPosition.new_with_amplitudes_unchecked([1, 0, 0, 0])
+    with pytest.raises(QuantrError):
+        expand_custom(G.Custom(bad, [], "bad"))

@@ -1,0 +1,133 @@
+"""Host scheduler + blob encoding + per-thread arithmetic, checked without a GPU.
+
+The plan is produced by the product's scheduler (quantr_b200/csrc/plan.cpp) and executed by
+tests/emu/qsv_emu.cpp, which drives the kernel's own __host__ __device__ per-thread functions
+sequentially.  The checker is the CPU oracle.
+"""
+import numpy as np
+import pytest
+
+from golden import reference_vectors as rv
+from helpers import (EmuCircuit, OracleCircuit, emu_simulate, encode_gates, orc, qb, qft_circuit, qft_expected,
+                     random_any_gate_circuit, random_layered_circuit, st)
+from quantr_b200 import _ffi as F
+
+G = qb.Gate
+
+
+@pytest.mark.parametrize("vec", rv.VECTORS, ids=[v["name"] for v in rv.VECTORS])
+def test_emulated_plan_reproduces_golden_vector(vec):
+    amps = vec["build"](EmuCircuit, G, st).simulate().get_state().take().get_amplitudes()
+    assert np.max(np.abs(amps - np.array(vec["expect"]))) < 1e-12
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_circuits_match_oracle_over_tile_configs(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 14))
+    c = random_any_gate_circuit(OracleCircuit, G, n, int(rng.integers(1, 120)), rng)
+    enc = encode_gates(c.circuit_gates, n)
+    reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    reg /= np.linalg.norm(reg)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense")
+    for tile_bits, low_bits, fuse in [(0, 0, True), (6, 2, True), (8, 3, True), (13, 3, True), (5, 1, False), (12, 3, False)]:
+        out = emu_simulate(n, enc, reg, tile_bits=tile_bits, low_bits=low_bits, fuse=fuse)
+        assert np.max(np.abs(out - ref)) < 1e-12, (n, tile_bits, low_bits, fuse)
+
+
+def test_layered_config3_generator_small():
+    """BASELINE config 3's generator at a CPU-checkable size."""
+    c = random_layered_circuit(OracleCircuit, G, 12, 6, seed=30)
+    enc = encode_gates(c.circuit_gates, 12)
+    ref = orc.simulate(12, enc.ops, enc.n_ops, None, mode="dense")
+    out, desc = emu_simulate(12, enc, None, tile_bits=8, low_bits=3, describe=True)
+    assert np.max(np.abs(out - ref)) < 1e-12
+    assert abs(np.sum(np.abs(out) ** 2) - 1.0) < 1e-12
+    assert len(desc["passes"]) < desc["n_gates"]  # fused
+
+
+def test_x3sudoko_with_custom_gates():
+    c = rv.build_x3sudoko(OracleCircuit, G, st)
+    enc = encode_gates(c.circuit_gates, 10)
+    ref = orc.simulate(10, enc.ops, enc.n_ops, None, mode="dense")
+    for tile_bits in (0, 7, 8):
+        out = emu_simulate(10, enc, None, tile_bits=tile_bits, low_bits=2)
+        assert np.max(np.abs(out - ref)) < 1e-12
+
+
+def test_none_overwrite_and_non_unitary_custom():
+    def closure(prod):
+        if prod.get_qubits()[0] == st.Qubit.Zero:
+            return None
+        return st.SuperPosition.new_with_amplitudes_unchecked([np.sqrt(0.5), np.sqrt(0.5)])
+
+    c = EmuCircuit.new(1)
+    c.add_gate(G.H, 0).add_gate(G.Custom(closure, [], "N"), 0)
+    assert np.allclose(c.simulate().get_state().take().get_amplitudes(), [np.sqrt(0.5), 0.5], atol=1e-15)
+
+
+@pytest.mark.parametrize("n,tile_bits,low_bits,expect_passes", [(13, 8, 3, 2), (16, 12, 3, 2), (33, 12, 3, 4), (33, 13, 3, 3), (36, 12, 3, 4)])
+def test_qft_pass_counts(n, tile_bits, low_bits, expect_passes):
+    """QFT-n: n H + n(n-1)/2 CRk fuse into ceil-ish(n / (T - L)) passes (SURVEY.md 7.2 hard part 1)."""
+    c = qft_circuit(OracleCircuit, G, n)
+    enc = encode_gates(c.circuit_gates, n)
+    plan = qb.Plan(n, enc, tile_bits=tile_bits, low_bits=low_bits)
+    stats = plan.stats()
+    assert stats["n_gates"] == n + n * (n - 1) // 2
+    assert stats["n_passes"] == expect_passes
+    assert stats["bytes_per_pass"] == 32 << n
+    desc = plan.describe()
+    assert desc["n_lowered_ops"] <= 2 * n  # all CRk of one target merged into one diagonal
+
+
+@pytest.mark.parametrize("n", [5, 9, 13])
+def test_qft_closed_form_through_plan(n):
+    x = 0x12345 & ((1 << n) - 1)
+    amps = qft_circuit(EmuCircuit, G, n, x).simulate().get_state().take().get_amplitudes()
+    assert np.max(np.abs(amps - qft_expected(n, x))) < 1e-13
+
+
+def test_sharded_plan_rank_bits_feed_controls_and_phases():
+    """Top log2(P) index bits live in the rank id: controls and diagonal phases on them must still act."""
+    n, g = 10, 2
+    rng = np.random.default_rng(5)
+    c = OracleCircuit.new(n)
+    for _ in range(60):
+        wires = rng.permutation(n)
+        t = int(wires[0]) if wires[0] >= g else int(wires[1] if wires[1] >= g else wires[2])
+        ctrl = [int(w) for w in wires if w != t][:2]
+        r = rng.integers(0, 6)
+        gate = [G.H, G.Rx(0.3), G.CNot(ctrl[0]), G.Toffoli(ctrl[0], ctrl[1]), G.CRk(3, ctrl[0]), G.CZ(ctrl[0])][r]
+        if r in (4, 5) and ctrl[0] < g:
+            # diagonal gates may sit on global wires as long as nothing non-diagonal targets them
+            pass
+        c.add_gate(gate, t)
+    c.add_gate(G.Rz(0.7), 0).add_gate(G.Z, 1).add_gate(G.CRk(2, 5), 1)  # diagonals targeting global wires
+    enc = encode_gates(c.circuit_gates, n)
+    reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    reg /= np.linalg.norm(reg)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense")
+    nl = n - g
+    for rank in range(1 << g):
+        shard = reg[rank << nl:(rank + 1) << nl]
+        out = emu_simulate(n, enc, shard, tile_bits=6, low_bits=2, n_local=nl, rank=rank)
+        assert np.max(np.abs(out - ref[rank << nl:(rank + 1) << nl])) < 1e-12
+
+
+def test_plan_errors():
+    enc = encode_gates(qft_circuit(OracleCircuit, G, 6).circuit_gates, 6)
+    with pytest.raises(F.QsvError) as e:
+        qb.Plan(6, enc, n_local=4)  # H on a rank bit needs a remap
+    assert e.value.code == 5
+    bad = (F.QsvOp * 1)()
+    bad[0].kind = F.GATE_CNOT
+    bad[0].target = 1
+    bad[0].n_controls = 0
+    fake = qb.EncodedOps(bad, [], [])
+    fake.n_ops = 1
+    with pytest.raises(F.QsvError) as e:
+        qb.Plan(3, fake)
+    assert e.value.code == 1
+    bad[0].kind = 99
+    with pytest.raises(F.QsvError):
+        qb.Plan(3, fake)
