@@ -5,28 +5,44 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 HOSTCXX := $(shell command -v /usr/bin/g++ || echo g++)
 CSRC := quantr_b200/csrc
+OBJ := build/obj
 NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas -ccbin $(HOSTCXX)
 HOSTFLAGS := -O2 -std=c++17 -fPIC -Wall -Wextra -Wno-unknown-pragmas -pthread
 
 HOST_SRCS := $(CSRC)/plan.cpp $(CSRC)/plan_api.cpp
-CUDA_SRCS := $(CSRC)/kernels.cu $(CSRC)/state_api.cu $(CSRC)/shard.cpp
-HDRS := include/qsv.h $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh)
+HDRS := include/qsv.h $(wildcard $(CSRC)/*.h)
+TILE_BITS := 0 10 11 12 13
+PASS_OBJS := $(foreach t,$(TILE_BITS),$(OBJ)/pass_kernel_t$(t).o)
+LIB_OBJS := $(OBJ)/plan.o $(OBJ)/plan_api.o $(OBJ)/kernels.o $(OBJ)/state_api.o $(OBJ)/shard.o $(PASS_OBJS)
 
-all: lib oracle emu
+all:
+	$(MAKE) -j8 lib oracle emu
 
 lib: quantr_b200/libqsv.so
 oracle:
 	$(MAKE) -C oracle
 emu: tests/emu/libqsv_emu.so
 
-quantr_b200/libqsv.so: $(HOST_SRCS) $(CUDA_SRCS) $(HDRS)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(HOST_SRCS) $(CUDA_SRCS) -lcudart -ldl
+$(OBJ)/pass_kernel_t%.o: $(CSRC)/pass_kernel.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVCCFLAGS) -DQSV_TILE_BITS=$* -c -o $@ $<
+
+$(OBJ)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVCCFLAGS) -c -o $@ $<
+
+$(OBJ)/%.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVCCFLAGS) -c -o $@ $<
+
+quantr_b200/libqsv.so: $(LIB_OBJS)
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(LIB_OBJS) -lcudart -ldl
 
 tests/emu/libqsv_emu.so: tests/emu/qsv_emu.cpp $(HOST_SRCS) $(HDRS)
 	$(HOSTCXX) $(HOSTFLAGS) -shared -Wl,-Bsymbolic -o $@ tests/emu/qsv_emu.cpp $(HOST_SRCS)
 
 clean:
-	rm -f quantr_b200/libqsv.so tests/emu/libqsv_emu.so
+	rm -rf build quantr_b200/libqsv.so tests/emu/libqsv_emu.so
 	$(MAKE) -C oracle clean
 
 .PHONY: all lib oracle emu clean

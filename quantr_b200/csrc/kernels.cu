@@ -25,118 +25,18 @@ __device__ __forceinline__ cplx ld_stream(const cplx* p) {
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
 
 // ---------------------------------------------------------------------------------------------
-// Fused pass.  Shared memory: [tile: 2^T cplx][header + rounds + ops copied from the blob][ext phases]
+// Fused pass: dispatch to the per-tile-size objects built from pass_kernel.cu.
 // ---------------------------------------------------------------------------------------------
-template <int T>
-__global__ void __launch_bounds__(kThreads, (T >= 13) ? 1 : 2)
-pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t rank_hi) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr uint32_t kTileLen = 1u << T;
-    constexpr uint32_t kGroups = kTileLen >> kRegBits;
-    constexpr uint32_t kLoadsPerThread = (kTileLen + kThreads - 1) / kThreads;
-    cplx* tile = reinterpret_cast<cplx*>(smem);
-    uint8_t* meta = smem + sizeof(cplx) * kTileLen;
-    const uint32_t tid = threadIdx.x;
-
-    const DevPass* gP = reinterpret_cast<const DevPass*>(blob);
-    const uint32_t meta_bytes = gP->ops_off + gP->n_ops * (uint32_t)sizeof(DevOp);
-    for (uint32_t i = tid * 16u; i < meta_bytes; i += kThreads * 16u)
-        *reinterpret_cast<uint4*>(meta + i) = *reinterpret_cast<const uint4*>(blob + i);
-    __syncthreads();
-    const DevPass& P = *reinterpret_cast<const DevPass*>(meta);
-    const DevRound* rounds = reinterpret_cast<const DevRound*>(meta + P.rounds_off);
-    const DevOp* ops = reinterpret_cast<const DevOp*>(meta + P.ops_off);
-    cplx* ext_phase = reinterpret_cast<cplx*>(meta + meta_bytes);
-    const uint32_t n_tile_segs = P.n_tile_segs, n_ext_segs = P.n_ext_segs;
-
-    for (uint64_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
-        const uint64_t base = deposit(t, P.ext_segs, n_ext_segs);
-        const uint64_t base_full = base | rank_hi;
-        cplx* gtile = state + base;
-        {
-            cplx v[kLoadsPerThread];
-#pragma unroll
-            for (uint32_t i = 0; i < kLoadsPerThread; ++i) {
-                const uint32_t l = i * kThreads + tid;
-                if (l < kTileLen) v[i] = ld_stream(gtile + deposit(l, P.tile_segs, n_tile_segs));
-            }
-#pragma unroll
-            for (uint32_t i = 0; i < kLoadsPerThread; ++i) {
-                const uint32_t l = i * kThreads + tid;
-                if (l < kTileLen) tile[swz(l)] = v[i];
-            }
-        }
-        for (uint32_t o = tid; o < P.n_ops; o += kThreads)
-            if (ops[o].type == OP_DIAG) ext_phase[ops[o].diag_index] = diag_ext_phase(ops[o], blob, base_full);
-        __syncthreads();
-
-        for (uint32_t r = 0; r < P.n_rounds; ++r) {
-            const DevRound& R = rounds[r];
-            if (R.type == ROUND_REG) {
-                for (uint32_t e = tid; e < kGroups; e += kThreads) reg_round(R, ops, blob, ext_phase, base_full, e, tile);
-            } else {
-                const DevDense& D = *reinterpret_cast<const DevDense*>(blob + ops[R.first_op].dense_off);
-                constexpr uint32_t kIter = (kGroups + kThreads - 1) / kThreads;
-                cplx out[kIter][kSlots];
-#pragma unroll
-                for (uint32_t it = 0; it < kIter; ++it) {
-                    const uint32_t e = it * kThreads + tid;
-                    if (e < kGroups) dense_compute(D, blob, e, tile, out[it]);
-                }
-                __syncthreads();
-#pragma unroll
-                for (uint32_t it = 0; it < kIter; ++it) {
-                    const uint32_t e = it * kThreads + tid;
-                    if (e < kGroups) dense_store(e, tile, out[it]);
-                }
-            }
-            __syncthreads();
-        }
-
-#pragma unroll
-        for (uint32_t i = 0; i < kLoadsPerThread; ++i) {
-            const uint32_t l = i * kThreads + tid;
-            if (l < kTileLen) st_stream(gtile + deposit(l, P.tile_segs, n_tile_segs), tile[swz(l)]);
-        }
-        __syncthreads();
-    }
-}
-
-template <int T>
-static cudaError_t launch_pass_t(cplx* state, const uint8_t* blob, const DevPass& hdr, uint64_t rank_hi, int sm_count, cudaStream_t stream) {
-    const size_t smem = sizeof(cplx) * (size_t(1) << T) + hdr.ops_off + hdr.n_ops * sizeof(DevOp) + sizeof(cplx) * (hdr.n_diag + 1);
-    static int blocks_per_sm[2] = {0, 0};  // cached for the largest smem seen (conservative)
-    static size_t smem_cfg = 0;
-    cudaError_t err;
-    if (smem > smem_cfg) {
-        const size_t want = sizeof(cplx) * (size_t(1) << T) + sizeof(DevPass) + kMaxRounds * sizeof(DevRound) + kMaxOps * sizeof(DevOp) + sizeof(cplx) * (kMaxOps + 1);
-        err = cudaFuncSetAttribute(pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
-        if (err != cudaSuccess) return err;
-        smem_cfg = want;
-        int nb = 0;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pass_kernel<T>, kThreads, want);
-        if (err != cudaSuccess) return err;
-        blocks_per_sm[0] = nb > 0 ? nb : 1;
-    }
-    uint64_t grid = (uint64_t)sm_count * (uint64_t)blocks_per_sm[0];
-    if (grid > hdr.n_tiles) grid = hdr.n_tiles;
-    pass_kernel<T><<<(unsigned)grid, kThreads, smem, stream>>>(state, blob, rank_hi);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const DevPass& hdr, uint64_t rank_hi, int sm_count, cudaStream_t stream) {
-    switch (hdr.tile_bits) {
-        case 4: return launch_pass_t<4>(state, dev_blob, hdr, rank_hi, sm_count, stream);
-        case 5: return launch_pass_t<5>(state, dev_blob, hdr, rank_hi, sm_count, stream);
-        case 6: return launch_pass_t<6>(state, dev_blob, hdr, rank_hi, sm_count, stream);
-        case 7: return launch_pass_t<7>(state, dev_blob, hdr, rank_hi, sm_count, stream);
-        case 8: return launch_pass_t<8>(state, dev_blob, hdr, rank_hi, sm_count, stream);
-        case 9: return launch_pass_t<9>(state, dev_blob, hdr, rank_hi, sm_count, stream);
-        case 10: return launch_pass_t<10>(state, dev_blob, hdr, rank_hi, sm_count, stream);
-        case 11: return launch_pass_t<11>(state, dev_blob, hdr, rank_hi, sm_count, stream);
-        case 12: return launch_pass_t<12>(state, dev_blob, hdr, rank_hi, sm_count, stream);
-        case 13: return launch_pass_t<13>(state, dev_blob, hdr, rank_hi, sm_count, stream);
-        default: return cudaErrorInvalidValue;
+cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream) {
+    const uint32_t tile_bits = reinterpret_cast<const DevPass*>(host_blob)->tile_bits;
+    switch (tile_bits) {
+        case 10: return launch_pass_tile<10>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+        case 11: return launch_pass_tile<11>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+        case 12: return launch_pass_tile<12>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+        case 13: return launch_pass_tile<13>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+        default:
+            if (tile_bits >= (uint32_t)kRegBits && tile_bits <= 9) return launch_pass_tile<0>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+            return cudaErrorInvalidValue;
     }
 }
 

@@ -7,7 +7,13 @@
 
 namespace qsv {
 
-cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const DevPass& hdr, uint64_t rank_hi, int sm_count, cudaStream_t stream);
+// host_blob: the pass blob in host memory (its header/rounds/ops travel as kernel parameters);
+// dev_blob: the same blob in device memory (tables, external phase terms, Custom matrices).
+cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream);
+// defined in pass_kernel.cu, one explicit specialisation per tile size (0 = runtime tile size <= 9 bits)
+template <int TILE_BITS>
+cudaError_t launch_pass_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream);
+
 cudaError_t launch_set_amp(cplx* state, uint64_t index, double re, double im, cudaStream_t stream);
 cudaError_t launch_gather(const cplx* state, const uint64_t* idx, cplx* out, uint64_t count, cudaStream_t stream);
 cudaError_t launch_prob_block_sums(const cplx* state, double* sums, uint64_t n_blocks, uint32_t block_bits, int sm_count, cudaStream_t stream);

@@ -91,7 +91,7 @@ void lower_gates(uint32_t n, const qsv_op* ops, size_t n_ops, std::vector<LOp>& 
         const int c1 = op.n_controls > 1 ? (int)(n - 1 - op.controls[1]) : -1;
         const uint64_t cm0 = c0 >= 0 ? (1ull << c0) : 0, cm1 = c1 >= 0 ? (1ull << c1) : 0;
         switch (op.kind) {
-            case QSV_GATE_H: out.push_back(make_mat(src, OP_MAT_REAL, t, 0, S2, 0, S2, 0, S2, 0, -S2, 0)); break;
+            case QSV_GATE_H: out.push_back(make_mat(src, OP_MAT_HADAMARD, t, 0, S2, 0, S2, 0, S2, 0, -S2, 0)); break;
             case QSV_GATE_X: out.push_back(make_xswap(src, t, 0)); break;
             case QSV_GATE_Y: out.push_back(make_mat(src, OP_MAT_ANTIDIAG, t, 0, 0, 0, 0, -1, 0, 1, 0, 0)); break;
             case QSV_GATE_Z: out.push_back(make_diag(src, 0, 0, {{t, 1.0}})); break;
@@ -258,6 +258,14 @@ void emit_pass(Plan& plan, const PassB& pb) {
     for (size_t i = 0; i < tsegs.size(); ++i) hdr.tile_segs[i] = tsegs[i];
     for (size_t i = 0; i < esegs.size(); ++i) hdr.ext_segs[i] = esegs[i];
 
+    DevLoads loads;
+    memset(&loads, 0, sizeof(loads));
+    for (uint32_t i = 0; i < (uint32_t)kMaxLoads && (uint64_t)i * kThreads < (1ull << T); ++i) {
+        loads.goff[i] = deposit((uint64_t)i * kThreads, hdr.tile_segs, hdr.n_tile_segs);
+        loads.soff[i] = swz(i * kThreads) << 4;
+    }
+    uint32_t n_hadamard = 0;
+
     std::vector<DevRound> rounds;
     std::vector<DevOp> ops;
     std::vector<uint8_t> aux;  // appended after header/rounds/ops; offsets fixed up below
@@ -320,6 +328,11 @@ void emit_pass(Plan& plan, const PassB& pb) {
         if (thsegs.size() > (size_t)kMaxThrSegs) fail("internal: too many thread segments");
         dr.n_thr_segs = (uint32_t)thsegs.size();
         for (size_t i = 0; i < thsegs.size(); ++i) dr.thr_segs[i] = thsegs[i];
+        for (int sl = 0; sl < kSlots; ++sl) {
+            uint32_t off = 0;
+            for (int j = 0; j < kRegBits; ++j) if ((sl >> j) & 1) off |= 1u << reg_local[j];
+            dr.xoff[sl] = swz(off) << 4;
+        }
 
         auto split_cmask = [&](uint64_t cmask, DevOp& d) {
             for (int b = 0; b < 64; ++b) {
@@ -341,6 +354,7 @@ void emit_pass(Plan& plan, const PassB& pb) {
                 if (lp < 0 || slot_of[lp] < 0) fail("internal: MAT target not a register bit");
                 d.slot = (uint32_t)slot_of[lp];
                 memcpy(d.m, lop.m, sizeof(d.m));
+                if (lop.mtype == OP_MAT_HADAMARD) ++n_hadamard;
             } else {
                 d.type = OP_DIAG;
                 d.diag_index = n_diag++;
@@ -386,7 +400,8 @@ void emit_pass(Plan& plan, const PassB& pb) {
     hdr.n_rounds = (uint32_t)rounds.size();
     hdr.n_ops = (uint32_t)ops.size();
     hdr.n_diag = n_diag;
-    hdr.rounds_off = (uint32_t)sizeof(DevPass);
+    hdr.final_scale = ldexp((n_hadamard & 1) ? 0.70710678118654752440 : 1.0, -(int)(n_hadamard / 2));
+    hdr.rounds_off = (uint32_t)(sizeof(DevPass) + sizeof(DevLoads));
     hdr.ops_off = hdr.rounds_off + (uint32_t)(rounds.size() * sizeof(DevRound));
     const uint32_t aux_base = hdr.ops_off + (uint32_t)(ops.size() * sizeof(DevOp));
     for (auto& f : fixes) {
@@ -406,6 +421,7 @@ void emit_pass(Plan& plan, const PassB& pb) {
 
     std::vector<uint8_t> blob(hdr.blob_bytes);
     memcpy(blob.data(), &hdr, sizeof(hdr));
+    memcpy(blob.data() + sizeof(hdr), &loads, sizeof(loads));
     if (!rounds.empty()) memcpy(blob.data() + hdr.rounds_off, rounds.data(), rounds.size() * sizeof(DevRound));
     if (!ops.empty()) memcpy(blob.data() + hdr.ops_off, ops.data(), ops.size() * sizeof(DevOp));
     if (!aux.empty()) memcpy(blob.data() + aux_base, aux.data(), aux.size());

@@ -29,7 +29,10 @@ constexpr int kMaxSegs = 16;
 constexpr int kMaxThrSegs = 8;
 constexpr int kMaxRounds = 32;
 constexpr int kMaxOps = 96;
+constexpr int kSmallRounds = 8;   // capacity classes of the kernel-parameter pass descriptor
+constexpr int kSmallOps = 24;
 constexpr int kThreads = 256;
+constexpr int kMaxLoads = (1 << kMaxTileBits) / kThreads;  // global loads per thread per tile
 constexpr uint32_t kPassMagic = 0x51535631u;  // "QSV1"
 
 struct alignas(16) cplx {
@@ -43,11 +46,13 @@ struct Seg {
 
 enum OpType : uint32_t {
     OP_MAT_GENERAL = 0,   // complex 2x2 on one register bit
-    OP_MAT_REAL = 1,      // real 2x2 (H, Ry)
+    OP_MAT_REAL = 1,      // real 2x2 (Ry)
     OP_MAT_ANTIDIAG = 2,  // a0' = m01*a1, a1' = m10*a0 (Y, X90, CY, ...)
     OP_MAT_XSWAP = 3,     // a0 <-> a1 (X, CNot, Toffoli)
     OP_DIAG = 4,          // amp *= exp(i*pi*(theta0 + sum_b coef_b*bit_b)) where control mask holds
-    OP_DENSE = 5          // k-qubit Custom matrix (dense round)
+    OP_DENSE = 5,         // k-qubit Custom matrix (dense round)
+    OP_MAT_HADAMARD = 6   // unnormalised butterfly a0' = a0+a1, a1' = a0-a1; the 1/sqrt2 factors of a pass are
+                          // collected in DevPass::final_scale and applied once when the tile is stored
 };
 
 enum DiagFlags : uint32_t { DIAG_HAS_THR_LO = 1, DIAG_HAS_THR_HI = 2, DIAG_HAS_REG = 4 };
@@ -77,7 +82,7 @@ struct DevOp {
 };
 static_assert(sizeof(DevOp) == 128, "DevOp layout");
 
-// 64 bytes
+// 128 bytes
 struct DevRound {
     uint32_t type;
     uint32_t first_op;
@@ -86,8 +91,9 @@ struct DevRound {
     uint8_t reg_pos[4];  // tile-local positions of the 4 register bits, ascending
     uint32_t pad[3];
     Seg thr_segs[kMaxThrSegs];  // thread index e -> tile-local index with register bits zero
+    uint32_t xoff[kSlots];      // byte offset of swz(slot s's tile-local offset): address = (swz(lb) << 4) ^ xoff[s]
 };
-static_assert(sizeof(DevRound) == 64, "DevRound layout");
+static_assert(sizeof(DevRound) == 128, "DevRound layout");
 
 struct DevDense {
     uint32_t k;
@@ -112,11 +118,31 @@ struct DevPass {
     uint32_t rounds_off;  // byte offsets in the pass blob
     uint32_t ops_off;
     uint32_t blob_bytes;
-    uint32_t pad[3];
+    uint32_t pad;
+    double final_scale;       // product of the deferred 1/sqrt2 factors of the pass's Hadamards
     Seg tile_segs[kMaxSegs];  // tile-local index -> physical (local) offset
     Seg ext_segs[kMaxSegs];   // tile id -> physical (local) base
 };
 static_assert(sizeof(DevPass) == 192, "DevPass layout");
+
+// Per-load constants of the tile load/store phase: thread `tid` moves tile-local elements l = i*kThreads + tid.
+// deposit() and swz() are linear over disjoint bit sets, so both split into a per-thread and a per-i part.
+struct DevLoads {
+    uint64_t goff[kMaxLoads];  // deposit(i * kThreads, tile_segs): element offset in the state
+    uint32_t soff[kMaxLoads];  // swz(i * kThreads) << 4: byte offset in the shared-memory tile
+};
+static_assert(sizeof(DevLoads) == 384, "DevLoads layout");
+
+// The part of a pass blob the kernel receives by value (kernel-parameter constant bank): header, load constants,
+// rounds and ops.  Tables, external phase terms and Custom matrices stay in the blob in global memory.
+template <int NR, int NO>
+struct PassParams {
+    DevPass hdr;
+    DevLoads loads;
+    DevRound rounds[NR];
+    DevOp ops[NO];
+};
+static_assert(sizeof(PassParams<kMaxRounds, kMaxOps>) < 32000, "kernel parameter limit");
 
 QSV_HD uint64_t deposit(uint64_t v, const Seg* segs, uint32_t n) {
     uint64_t r = 0;

@@ -160,8 +160,7 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     s->prefix_valid = false;
     if (s->timing) QSV_CUDA(s, cudaEventRecord(s->ev0, s->stream));
     for (size_t i = 0; i < plan.passes.size(); ++i) {
-        const DevPass& hdr = *reinterpret_cast<const DevPass*>(plan.passes[i].data());
-        QSV_CUDA(s, launch_pass(s->d_state, static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[i], hdr, rank_base(s), s->sm_count, s->stream));
+        QSV_CUDA(s, launch_pass(s->d_state, static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[i], plan.passes[i].data(), rank_base(s), s->sm_count, s->stream));
     }
     if (stats) {
         memset(stats, 0, sizeof(*stats));

@@ -17,26 +17,32 @@
 using namespace qsv;
 
 static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
-    const DevPass* P = reinterpret_cast<const DevPass*>(blob);
-    const DevRound* rounds = reinterpret_cast<const DevRound*>(blob + P->rounds_off);
-    const DevOp* ops = reinterpret_cast<const DevOp*>(blob + P->ops_off);
-    const uint32_t T = P->tile_bits;
+    static PassParams<kMaxRounds, kMaxOps> P;  // what the kernel receives by value
+    if (!fill_params(blob, P)) return;
+    const uint32_t T = P.hdr.tile_bits;
     const uint32_t tile_len = 1u << T, groups = 1u << (T - kRegBits);
+    const uint32_t n_loads = (tile_len + kThreads - 1) / kThreads;
     std::vector<cplx> tile(tile_len);
     std::vector<cplx> ext_phase(kMaxOps);
     std::vector<cplx> dense_out((size_t)groups * kSlots);
-    for (uint64_t t = 0; t < P->n_tiles; ++t) {
-        const uint64_t base = deposit(t, P->ext_segs, P->n_ext_segs);
+    char* tb = reinterpret_cast<char*>(tile.data());
+    for (uint64_t t = 0; t < P.hdr.n_tiles; ++t) {
+        const uint64_t base = deposit(t, P.hdr.ext_segs, P.hdr.n_ext_segs);
         const uint64_t base_full = base | rank_hi;
-        for (uint32_t l = 0; l < tile_len; ++l) tile[swz(l)] = state[base + deposit(l, P->tile_segs, P->n_tile_segs)];
-        for (uint32_t o = 0; o < P->n_ops; ++o)
-            if (ops[o].type == OP_DIAG) ext_phase[ops[o].diag_index] = diag_ext_phase(ops[o], blob, base_full);
-        for (uint32_t r = 0; r < P->n_rounds; ++r) {
-            const DevRound& R = rounds[r];
+        for (uint32_t tid = 0; tid < (uint32_t)kThreads; ++tid) {  // load phase exactly as the kernel addresses it
+            const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, P.hdr.n_tile_segs);
+            const uint32_t soff_t = swz(tid) << 4;
+            for (uint32_t i = 0; i < n_loads; ++i)
+                if (i * kThreads + tid < tile_len) *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) = state[base + goff_t + P.loads.goff[i]];
+        }
+        for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
+            if (P.ops[o].type == OP_DIAG) ext_phase[P.ops[o].diag_index] = diag_ext_phase(P.ops[o], blob, base_full);
+        for (uint32_t r = 0; r < P.hdr.n_rounds; ++r) {
+            const DevRound& R = P.rounds[r];
             if (R.type == ROUND_REG) {
-                for (uint32_t e = 0; e < groups; ++e) reg_round(R, ops, blob, ext_phase.data(), base_full, e, tile.data());
+                for (uint32_t e = 0; e < groups; ++e) reg_round(R, P.ops, blob, ext_phase.data(), base_full, e, tile.data());
             } else {
-                const DevDense* D = reinterpret_cast<const DevDense*>(blob + ops[R.first_op].dense_off);
+                const DevDense* D = reinterpret_cast<const DevDense*>(blob + P.ops[R.first_op].dense_off);
                 for (uint32_t e = 0; e < groups; ++e) {
                     cplx out[kSlots];
                     dense_compute(*D, blob, e, tile.data(), out);
@@ -49,7 +55,17 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
                 }
             }
         }
-        for (uint32_t l = 0; l < tile_len; ++l) state[base + deposit(l, P->tile_segs, P->n_tile_segs)] = tile[swz(l)];
+        const double sc = P.hdr.final_scale;
+        for (uint32_t tid = 0; tid < (uint32_t)kThreads; ++tid) {
+            const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, P.hdr.n_tile_segs);
+            const uint32_t soff_t = swz(tid) << 4;
+            for (uint32_t i = 0; i < n_loads; ++i)
+                if (i * kThreads + tid < tile_len) {
+                    cplx v = *reinterpret_cast<const cplx*>(tb + (soff_t ^ P.loads.soff[i]));
+                    if (sc != 1.0) { v.x *= sc; v.y *= sc; }
+                    state[base + goff_t + P.loads.goff[i]] = v;
+                }
+        }
     }
 }
 
