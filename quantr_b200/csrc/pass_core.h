@@ -55,7 +55,7 @@ inline bool fill_params(const uint8_t* blob, PassParams<NR, NO>& out) {
 
 // External phase of a DIAG op for one tile: exp(i*pi*(theta0 + sum over bits outside the tile)).
 QSV_HD cplx diag_ext_phase(const DevOp& op, const uint8_t* blob, uint64_t base_full) {
-    double ang = op.m[0];
+    double ang = op.theta0;
     const DiagExtTerm* terms = reinterpret_cast<const DiagExtTerm*>(blob + op.ext_off);
     for (uint32_t i = 0; i < op.n_ext; ++i)
         if ((base_full >> terms[i].bit) & 1ull) ang += terms[i].coef;
@@ -199,65 +199,123 @@ QSV_HD void mat_xswap(cplx (&a)[kSlots], const double (&)[8], uint32_t cm) {
     }
 }
 
-#define QSV_MAT_DISPATCH(FN)                                   \
-    if (op.cmask_reg == 0) {                                   \
-        switch (op.slot) {                                     \
-            case 0: FN<0, false>(a, op.m, 0u); break;          \
-            case 1: FN<1, false>(a, op.m, 0u); break;          \
-            case 2: FN<2, false>(a, op.m, 0u); break;          \
-            default: FN<3, false>(a, op.m, 0u); break;         \
-        }                                                      \
-    } else {                                                   \
-        switch (op.slot) {                                     \
-            case 0: FN<0, true>(a, op.m, op.cmask_reg); break; \
-            case 1: FN<1, true>(a, op.m, op.cmask_reg); break; \
-            case 2: FN<2, true>(a, op.m, op.cmask_reg); break; \
-            default: FN<3, true>(a, op.m, op.cmask_reg); break;\
-        }                                                      \
-    }
+// Depth-first doubling over the free register bits: multiplies a[s | S] by f * prod_{k in S} r_k for every subset S of
+// the bits in FREE (a 4-bit mask), holding at most one factor per level in registers.  No table loads: the four
+// r_k = exp(i*pi*coef_k) are uniform operands from the constant bank.
+template <int FREE>
+QSV_HD void diag_dfs(cplx (&a)[kSlots], const double (&r)[8], int s, cplx f) {
+    c_mul_ip(a[s], f.x, f.y);
+    if (FREE & 1) diag_dfs<0>(a, r, s | 1, cmul(f, cplx{r[0], r[1]}));
+    if (FREE & 2) diag_dfs<(FREE & 1)>(a, r, s | 2, cmul(f, cplx{r[2], r[3]}));
+    if (FREE & 4) diag_dfs<(FREE & 3)>(a, r, s | 4, cmul(f, cplx{r[4], r[5]}));
+    if (FREE & 8) diag_dfs<(FREE & 7)>(a, r, s | 8, cmul(f, cplx{r[6], r[7]}));
+}
 
-// amp[s] *= f for the slots selected by the register-control mask; MASK_BIT < 0: all 16 slots,
-// MASK_BIT = j: the 8 slots with register bit j set, MASK_BIT = 4: generic runtime mask.
-template <int MASK_BIT, bool HAS_REG>
-QSV_HD void diag_apply(cplx (&a)[kSlots], cplx w, const cplx* reg_tbl, uint32_t cm) {
-    constexpr bool kSingle = MASK_BIT >= 0 && MASK_BIT < 4;
-    constexpr int kShift = kSingle ? MASK_BIT : 0;
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-        if (kSingle && !((s >> kShift) & 1)) continue;
-        if (MASK_BIT == 4 && (s & cm) != cm) continue;
+// amp[s] *= w * R[s] for the slots selected by the register-control mask, R[s] = prod_{k: bit k of s} r_k.
+// SEL = 0: all 16 slots, SEL = 1..4: the 8 slots with register bit SEL-1 set, SEL = 5: generic runtime mask.
+// tbl: the op's thread-phase table lo[32], hi[16] (shared memory for small passes, global otherwise).
+template <int SEL, bool HAS_REG>
+QSV_HD void diag_apply(cplx (&a)[kSlots], const DevOp& op, const cplx* tbl, uint32_t e, cplx w) {
+    if (op.flags & DIAG_HAS_THR_LO) w = cmul(w, tbl[e & 31u]);
+    if (op.flags & DIAG_HAS_THR_HI) w = cmul(w, tbl[32u + (e >> 5)]);
+    constexpr bool kSingle = SEL >= 1 && SEL <= 4;
+    constexpr int kBit = kSingle ? (1 << (SEL - 1)) : 0;
+    if (SEL <= 4) {
         if (HAS_REG) {
-            const cplx f = cmul(w, reg_tbl[s]);
-            c_mul_ip(a[s], f.x, f.y);
+            diag_dfs<(15 & ~kBit)>(a, op.m, kBit, w);  // the control bit itself carries no linear term
         } else {
-            c_mul_ip(a[s], w.x, w.y);
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                if (kSingle && !(s & kBit)) continue;
+                c_mul_ip(a[s], w.x, w.y);
+            }
+        }
+    } else {
+        const uint32_t cm = op.cmask_reg;
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+            if ((s & cm) != cm) continue;
+            cplx f = w;
+            if (HAS_REG) {
+                if (s & 1) f = cmul(f, cplx{op.m[0], op.m[1]});
+                if (s & 2) f = cmul(f, cplx{op.m[2], op.m[3]});
+                if (s & 4) f = cmul(f, cplx{op.m[4], op.m[5]});
+                if (s & 8) f = cmul(f, cplx{op.m[6], op.m[7]});
+            }
+            c_mul_ip(a[s], f.x, f.y);
         }
     }
 }
 
-QSV_HD void apply_diag(cplx (&a)[kSlots], const DevOp& op, const uint8_t* blob, uint32_t e, cplx w) {
-    const cplx* tbl = reinterpret_cast<const cplx*>(blob + op.tbl_off);
-    if (op.flags & DIAG_HAS_THR_LO) w = cmul(w, tbl[e & 31u]);
-    if (op.flags & DIAG_HAS_THR_HI) w = cmul(w, tbl[32u + (e >> 5)]);
-    const uint32_t cm = op.cmask_reg;
-    const cplx* rt = tbl + 64;
-    if (op.flags & DIAG_HAS_REG) {
-        switch (cm) {
-            case 0: diag_apply<-1, true>(a, w, rt, cm); break;
-            case 1: diag_apply<0, true>(a, w, rt, cm); break;
-            case 2: diag_apply<1, true>(a, w, rt, cm); break;
-            case 4: diag_apply<2, true>(a, w, rt, cm); break;
-            case 8: diag_apply<3, true>(a, w, rt, cm); break;
-            default: diag_apply<4, true>(a, w, rt, cm); break;
-        }
-    } else {
-        switch (cm) {
-            case 0: diag_apply<-1, false>(a, w, rt, cm); break;
-            case 1: diag_apply<0, false>(a, w, rt, cm); break;
-            case 2: diag_apply<1, false>(a, w, rt, cm); break;
-            case 4: diag_apply<2, false>(a, w, rt, cm); break;
-            case 8: diag_apply<3, false>(a, w, rt, cm); break;
-            default: diag_apply<4, false>(a, w, rt, cm); break;
+// Dispatch code of a lowered op inside a register round (host side; see kCode* in qsv_types.h).
+inline uint32_t op_dispatch_code(const DevOp& op) {
+    int kind = -1;
+    switch (op.type) {
+        case OP_MAT_HADAMARD: kind = 0; break;
+        case OP_MAT_XSWAP: kind = 1; break;
+        case OP_MAT_REAL: kind = 2; break;
+        case OP_MAT_GENERAL: kind = 3; break;
+        case OP_MAT_ANTIDIAG: kind = 4; break;
+        default: break;
+    }
+    if (kind >= 0) return kCodeMatBase + (uint32_t)kind * 8u + (op.cmask_reg ? 4u : 0u) + op.slot;
+    if (op.type == OP_DIAG) {
+        uint32_t sel = 5;
+        if (op.cmask_reg == 0) sel = 0;
+        else if ((op.cmask_reg & (op.cmask_reg - 1)) == 0) sel = 1 + (op.cmask_reg == 1 ? 0 : op.cmask_reg == 2 ? 1 : op.cmask_reg == 4 ? 2 : 3);
+        return kCodeDiagBase + ((op.flags & DIAG_HAS_REG) ? 6u : 0u) + sel;
+    }
+    return kCodeNop;
+}
+
+#define QSV_MAT_CASES(KIND, FN)                                                              \
+    case kCodeMatBase + KIND * 8 + 0: FN<0, false>(a, op.m, 0u); break;                      \
+    case kCodeMatBase + KIND * 8 + 1: FN<1, false>(a, op.m, 0u); break;                      \
+    case kCodeMatBase + KIND * 8 + 2: FN<2, false>(a, op.m, 0u); break;                      \
+    case kCodeMatBase + KIND * 8 + 3: FN<3, false>(a, op.m, 0u); break;                      \
+    case kCodeMatBase + KIND * 8 + 4: FN<0, true>(a, op.m, op.cmask_reg); break;             \
+    case kCodeMatBase + KIND * 8 + 5: FN<1, true>(a, op.m, op.cmask_reg); break;             \
+    case kCodeMatBase + KIND * 8 + 6: FN<2, true>(a, op.m, op.cmask_reg); break;             \
+    case kCodeMatBase + KIND * 8 + 7: FN<3, true>(a, op.m, op.cmask_reg); break;
+
+#define QSV_DIAG_CASES(HAS_REG)                                                                                                    \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 0: diag_apply<0, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 1: diag_apply<1, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 2: diag_apply<2, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 3: diag_apply<3, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 4: diag_apply<4, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 5: diag_apply<5, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;
+
+// Which ops of the pass act on thread-group e (controls among the thread's fixed tile-local bits).  Tile-independent:
+// the kernel evaluates it once per launch.  W words of 32 op bits.
+template <int W>
+QSV_HD void thread_active_mask(const DevPass& hdr, const DevRound* rounds, const DevOp* ops, uint32_t e, uint32_t (&act)[W]) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) act[w] = 0xffffffffu;
+    for (uint32_t r = 0; r < hdr.n_rounds; ++r) {
+        if (rounds[r].type != ROUND_REG) continue;
+        const uint32_t lb = (uint32_t)deposit(e, rounds[r].thr_segs, rounds[r].n_thr_segs);
+        for (uint32_t o = rounds[r].first_op; o < rounds[r].first_op + rounds[r].n_ops; ++o)
+            if ((lb & ops[o].cmask_thr) != ops[o].cmask_thr) {
+#pragma unroll
+                for (int w = 0; w < W; ++w)
+                    if ((int)(o >> 5) == w) act[w] &= ~(1u << (o & 31u));
+            }
+    }
+}
+
+// Clears the ops whose controls outside the tile are not satisfied for this tile (uniform over the CTA).
+template <int W>
+QSV_HD void tile_active_mask(const DevPass& hdr, const DevOp* ops, uint64_t base_full, uint32_t (&act)[W]) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        uint32_t m = hdr.ext_ctrl_mask[w];
+        while (m) {
+            const uint32_t bit = m & (0u - m);
+            m ^= bit;
+            uint32_t o = 32u * w;
+            for (uint32_t t = bit; t > 1; t >>= 1) ++o;
+            if ((base_full & ops[o].cmask_ext) != ops[o].cmask_ext) act[w] &= ~bit;
         }
     }
 }
@@ -266,26 +324,35 @@ QSV_HD void apply_diag(cplx (&a)[kSlots], const DevOp& op, const uint8_t* blob, 
 //   tile      : the tile in (swizzled) shared memory
 //   ops       : the pass's op array
 //   ext_phase : per-tile external phases of the pass's DIAG ops
-//   base_full : physical index of the tile's first amplitude, rank bits included
-QSV_HD void reg_round(const DevRound& R, const DevOp* ops, const uint8_t* blob, const cplx* ext_phase,
-                      uint64_t base_full, uint32_t e, cplx* tile) {
+//   act       : bit o set = op o acts on this thread-group for this tile
+//   thr_tbl   : when non-null, the DIAG thread-phase tables staged in shared memory (kDiagTblLen entries per diag_index);
+//               otherwise they are read from the blob in global memory
+#define QSV_DIAG_TBL (thr_tbl ? thr_tbl + op.diag_index * kDiagTblLen : reinterpret_cast<const cplx*>(blob + op.tbl_off))
+template <int W>
+QSV_HD void reg_round(const DevRound& R, const DevOp* ops, const uint8_t* blob, const cplx* ext_phase, const cplx* thr_tbl,
+                      const uint32_t (&act)[W], uint32_t e, cplx* tile) {
     const uint32_t lb = (uint32_t)deposit(e, R.thr_segs, R.n_thr_segs);
     const uint32_t sb = swz(lb) << 4;
     char* tb = reinterpret_cast<char*>(tile);
     cplx a[kSlots];
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const cplx*>(tb + (sb ^ R.xoff[s]));
-    for (uint32_t o = 0; o < R.n_ops; ++o) {
-        const DevOp& op = ops[R.first_op + o];
-        if ((base_full & op.cmask_ext) != op.cmask_ext) continue;  // uniform over the tile
-        if ((lb & op.cmask_thr) != op.cmask_thr) continue;         // uniform over the thread's 16 amplitudes
-        switch (op.type) {
-            case OP_MAT_HADAMARD: QSV_MAT_DISPATCH(mat_hadamard) break;
-            case OP_DIAG: apply_diag(a, op, blob, e, ext_phase[op.diag_index]); break;
-            case OP_MAT_XSWAP: QSV_MAT_DISPATCH(mat_xswap) break;
-            case OP_MAT_REAL: QSV_MAT_DISPATCH(mat_real) break;
-            case OP_MAT_GENERAL: QSV_MAT_DISPATCH(mat_general) break;
-            case OP_MAT_ANTIDIAG: QSV_MAT_DISPATCH(mat_antidiag) break;
+    const uint32_t first = R.first_op, last = R.first_op + R.n_ops;
+    for (uint32_t o = first; o < last; ++o) {
+        uint32_t word = act[0];
+#pragma unroll
+        for (int w = 1; w < W; ++w)
+            if ((int)(o >> 5) == w) word = act[w];
+        if (!((word >> (o & 31u)) & 1u)) continue;
+        const DevOp& op = ops[o];
+        switch (op.code) {
+            QSV_MAT_CASES(0, mat_hadamard)
+            QSV_MAT_CASES(1, mat_xswap)
+            QSV_MAT_CASES(2, mat_real)
+            QSV_MAT_CASES(3, mat_general)
+            QSV_MAT_CASES(4, mat_antidiag)
+            QSV_DIAG_CASES(false)
+            QSV_DIAG_CASES(true)
             default: break;
         }
     }

@@ -260,10 +260,14 @@ void emit_pass(Plan& plan, const PassB& pb) {
 
     DevLoads loads;
     memset(&loads, 0, sizeof(loads));
-    for (uint32_t i = 0; i < (uint32_t)kMaxLoads && (uint64_t)i * kThreads < (1ull << T); ++i) {
-        loads.goff[i] = deposit((uint64_t)i * kThreads, hdr.tile_segs, hdr.n_tile_segs);
-        loads.soff[i] = swz(i * kThreads) << 4;
+    const uint32_t threads = tile_threads((uint32_t)T);
+    hdr.threads = threads;
+    for (uint32_t i = 0; i < (uint32_t)kMaxLoads && (uint64_t)i * threads < (1ull << T); ++i) {
+        loads.goff[i] = deposit((uint64_t)i * threads, hdr.tile_segs, hdr.n_tile_segs);
+        loads.soff[i] = swz(i * threads) << 4;
     }
+    hdr.pf_step = (8ull * threads < (1ull << T)) ? deposit(8ull * threads, hdr.tile_segs, hdr.n_tile_segs) : 0;
+    if (plan.opt.l2_prefetch) hdr.flags |= PASS_L2_PREFETCH;
     uint32_t n_hadamard = 0;
 
     std::vector<DevRound> rounds;
@@ -358,7 +362,7 @@ void emit_pass(Plan& plan, const PassB& pb) {
             } else {
                 d.type = OP_DIAG;
                 d.diag_index = n_diag++;
-                d.m[0] = lop.theta0;
+                d.theta0 = lop.theta0;
                 double thr_coef[16] = {0}, reg_coef[4] = {0};
                 std::vector<DiagExtTerm> ext;
                 for (auto& t : lop.lin) {
@@ -368,28 +372,34 @@ void emit_pass(Plan& plan, const PassB& pb) {
                     else if (slot_of[lp] >= 0) reg_coef[slot_of[lp]] += t.second;
                     else thr_coef[thr_index[lp]] += t.second;
                 }
-                std::vector<cplx> tbl(80);
+                std::vector<cplx> tbl(kDiagTblLen);
                 bool has_lo = false, has_hi = false, has_reg = false;
                 for (int i = 0; i < 32; ++i) {
-                    double alo = 0, ahi = 0;
-                    for (int b = 0; b < 5; ++b) {
-                        if ((i >> b) & 1) { alo += thr_coef[b]; if (5 + b < 16) ahi += thr_coef[5 + b]; }
-                    }
+                    double alo = 0;
+                    for (int b = 0; b < 5; ++b) if ((i >> b) & 1) alo += thr_coef[b];
                     tbl[i] = unit_phase(alo);
+                }
+                for (int i = 0; i < 16; ++i) {
+                    double ahi = 0;
+                    for (int b = 0; b < 4; ++b) if ((i >> b) & 1) ahi += thr_coef[5 + b];
                     tbl[32 + i] = unit_phase(ahi);
                 }
-                for (int b = 0; b < 5; ++b) { has_lo |= thr_coef[b] != 0.0; has_hi |= thr_coef[5 + b] != 0.0; }
-                for (int s = 0; s < 16; ++s) {
-                    double a = 0;
-                    for (int j = 0; j < 4; ++j) if ((s >> j) & 1) a += reg_coef[j];
-                    tbl[64 + s] = unit_phase(a);
+                for (int b = 0; b < 5; ++b) has_lo |= thr_coef[b] != 0.0;
+                for (int b = 5; b < 9; ++b) has_hi |= thr_coef[b] != 0.0;
+                for (int j = 0; j < 4; ++j) {
+                    const cplx r = unit_phase(reg_coef[j]);
+                    d.m[2 * j] = r.x;
+                    d.m[2 * j + 1] = r.y;
+                    has_reg |= reg_coef[j] != 0.0;
                 }
-                for (int j = 0; j < 4; ++j) has_reg |= reg_coef[j] != 0.0;
                 d.flags = (has_lo ? (uint32_t)DIAG_HAS_THR_LO : 0u) | (has_hi ? (uint32_t)DIAG_HAS_THR_HI : 0u) | (has_reg ? (uint32_t)DIAG_HAS_REG : 0u);
                 d.n_ext = (uint32_t)ext.size();
                 if (!ext.empty()) { d.ext_off = (uint32_t)append(aux, ext.data(), ext.size()); fixes.push_back({ops.size(), 0}); }
-                if (d.flags) { d.tbl_off = (uint32_t)append(aux, tbl.data(), tbl.size()); fixes.push_back({ops.size(), 1}); }
+                d.tbl_off = (uint32_t)append(aux, tbl.data(), tbl.size());  // always present: the kernel stages it in shared memory
+                fixes.push_back({ops.size(), 1});
             }
+            d.code = op_dispatch_code(d);
+            if (d.cmask_ext) hdr.ext_ctrl_mask[ops.size() >> 5] |= 1u << (ops.size() & 31);
             ops.push_back(d);
         }
         dr.n_ops = (uint32_t)ops.size() - dr.first_op;

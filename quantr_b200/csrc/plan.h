@@ -39,6 +39,7 @@ struct PlanOptions {
     int tile_bits = 12;
     int low_bits = 3;
     int fuse = 1;
+    int l2_prefetch = 1;  // prefetch the CTA's next tile into L2 while the current one is processed
 };
 
 struct Plan {

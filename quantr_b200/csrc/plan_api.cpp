@@ -1,5 +1,6 @@
 // plan_api.cpp — C ABI for the host-only part of the library (lowering + scheduling).
 // Needs no GPU; see include/qsv.h.
+#include <stdlib.h>
 #include <string.h>
 
 #include <stdexcept>
@@ -26,6 +27,7 @@ int qsv_plan_create(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubits, 
         if (tile_bits) opt.tile_bits = (int)tile_bits;
         if (low_bits) opt.low_bits = (int)low_bits;
         opt.fuse = fuse;
+        if (const char* env = getenv("QSV_L2_PREFETCH")) opt.l2_prefetch = atoi(env) != 0;
         try {
             qsv::build_plan(p->plan, n_qubits, n_local_qubits, ops, n_ops, opt);
         } catch (...) {

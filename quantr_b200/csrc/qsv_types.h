@@ -31,8 +31,11 @@ constexpr int kMaxRounds = 32;
 constexpr int kMaxOps = 96;
 constexpr int kSmallRounds = 8;   // capacity classes of the kernel-parameter pass descriptor
 constexpr int kSmallOps = 24;
-constexpr int kThreads = 256;
-constexpr int kMaxLoads = (1 << kMaxTileBits) / kThreads;  // global loads per thread per tile
+constexpr int kMaxLoads = kSlots;   // global loads per thread per tile: one CTA thread per 16 amplitudes
+constexpr int kSmallTileThreads = 64; // CTA size for tiles below 2^10 amplitudes
+
+// CTA size for a tile of 2^T amplitudes: one thread per register group of 16 amplitudes.
+QSV_HD constexpr uint32_t tile_threads(uint32_t T) { return T >= 10 ? (1u << (T - kRegBits)) : (uint32_t)kSmallTileThreads; }
 constexpr uint32_t kPassMagic = 0x51535631u;  // "QSV1"
 
 struct alignas(16) cplx {
@@ -55,6 +58,13 @@ enum OpType : uint32_t {
                           // collected in DevPass::final_scale and applied once when the tile is stored
 };
 
+// Fully resolved dispatch code of an op inside a register round (one jump-table entry per routine):
+//   MAT : 1 + kind*8 + ctrl*4 + slot, kind = 0 HADAMARD, 1 XSWAP, 2 REAL, 3 GENERAL, 4 ANTIDIAG; ctrl = has register controls
+//   DIAG: 41 + has_reg*6 + sel,        sel = 0 all slots, 1..4 slots with register bit sel-1 set, 5 runtime mask
+constexpr int kDiagTblLen = 48;  // lo[32] (thread-index bits 0-4) + hi[16] (bits 5-8)
+constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeCount = 53;
+enum PassFlags : uint32_t { PASS_L2_PREFETCH = 1 };
+
 enum DiagFlags : uint32_t { DIAG_HAS_THR_LO = 1, DIAG_HAS_THR_HI = 2, DIAG_HAS_REG = 4 };
 enum RoundType : uint32_t { ROUND_REG = 0, ROUND_DENSE = 1 };
 
@@ -73,12 +83,14 @@ struct DevOp {
     uint64_t cmask_ext;   // controls outside the tile (physical bit positions, rank bits included)
     uint32_t flags;       // DIAG: DiagFlags
     uint32_t diag_index;  // DIAG: slot in the per-tile external-phase array
-    double m[8];          // MAT: m00 m01 m10 m11 (re, im);  DIAG: m[0] = theta0 (half-turns)
+    double m[8];          // MAT: m00 m01 m10 m11 (re, im);  DIAG: r_0..r_3 = exp(i*pi*coef of register bit j) (re, im)
     uint32_t ext_off;     // DIAG: byte offset in the pass blob of DiagExtTerm[n_ext]
     uint32_t n_ext;
-    uint32_t tbl_off;     // DIAG: byte offset of cplx lo[32], hi[32], reg[16]
+    uint32_t tbl_off;     // DIAG: byte offset of the thread-phase table cplx lo[32], hi[16] (kDiagTblLen entries)
     uint32_t dense_off;   // DENSE: byte offset of DevDense
-    uint32_t pad[4];
+    uint32_t code;        // dispatch code (see kCode*)
+    uint32_t pad;
+    double theta0;        // DIAG: constant term (half-turns)
 };
 static_assert(sizeof(DevOp) == 128, "DevOp layout");
 
@@ -118,20 +130,24 @@ struct DevPass {
     uint32_t rounds_off;  // byte offsets in the pass blob
     uint32_t ops_off;
     uint32_t blob_bytes;
-    uint32_t pad;
+    uint32_t threads;         // CTA size = tile_threads(tile_bits)
     double final_scale;       // product of the deferred 1/sqrt2 factors of the pass's Hadamards
+    uint32_t ext_ctrl_mask[3];// bit o set: op o has controls outside the tile (evaluated once per tile)
+    uint32_t pad;
+    uint64_t pf_step;         // deposit(8 * threads, tile_segs): element offset between a thread's two L2-prefetch lines
     Seg tile_segs[kMaxSegs];  // tile-local index -> physical (local) offset
     Seg ext_segs[kMaxSegs];   // tile id -> physical (local) base
 };
-static_assert(sizeof(DevPass) == 192, "DevPass layout");
+static_assert(sizeof(DevPass) == 216, "DevPass layout");
 
-// Per-load constants of the tile load/store phase: thread `tid` moves tile-local elements l = i*kThreads + tid.
+// Per-load constants of the tile load/store phase: thread `tid` moves tile-local elements l = i*threads + tid.
 // deposit() and swz() are linear over disjoint bit sets, so both split into a per-thread and a per-i part.
 struct DevLoads {
-    uint64_t goff[kMaxLoads];  // deposit(i * kThreads, tile_segs): element offset in the state
-    uint32_t soff[kMaxLoads];  // swz(i * kThreads) << 4: byte offset in the shared-memory tile
+    uint64_t goff[kMaxLoads];  // deposit(i * threads, tile_segs): element offset in the state
+    uint32_t soff[kMaxLoads];  // swz(i * threads) << 4: byte offset in the shared-memory tile
+    uint32_t pad[2];
 };
-static_assert(sizeof(DevLoads) == 384, "DevLoads layout");
+static_assert(sizeof(DevLoads) == 200, "DevLoads layout");
 
 // The part of a pass blob the kernel receives by value (kernel-parameter constant bank): header, load constants,
 // rounds and ops.  Tables, external phase terms and Custom matrices stay in the blob in global memory.

@@ -19,28 +19,46 @@ using namespace qsv;
 static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
     static PassParams<kMaxRounds, kMaxOps> P;  // what the kernel receives by value
     if (!fill_params(blob, P)) return;
+    constexpr int W = kMaxOps / 32;
     const uint32_t T = P.hdr.tile_bits;
-    const uint32_t tile_len = 1u << T, groups = 1u << (T - kRegBits);
-    const uint32_t n_loads = (tile_len + kThreads - 1) / kThreads;
+    const uint32_t tile_len = 1u << T, groups = 1u << (T - kRegBits), threads = P.hdr.threads;
+    const uint32_t n_loads = (tile_len + threads - 1) / threads;
     std::vector<cplx> tile(tile_len);
     std::vector<cplx> ext_phase(kMaxOps);
     std::vector<cplx> dense_out((size_t)groups * kSlots);
+    std::vector<uint32_t> thr_act((size_t)groups * W);
+    for (uint32_t e = 0; e < groups; ++e) {  // the kernel does this once per launch
+        uint32_t act[W];
+        thread_active_mask<W>(P.hdr, P.rounds, P.ops, e, act);
+        memcpy(&thr_act[(size_t)e * W], act, sizeof(act));
+    }
+    // the kernel stages the DIAG thread-phase tables in shared memory for small passes; exercise both paths
+    const bool use_smem_tbl = P.hdr.n_rounds <= (uint32_t)kSmallRounds && P.hdr.n_ops <= (uint32_t)kSmallOps;
+    std::vector<cplx> thr_tbl((size_t)kMaxOps * kDiagTblLen);
+    for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
+        if (P.ops[o].type == OP_DIAG)
+            memcpy(&thr_tbl[(size_t)P.ops[o].diag_index * kDiagTblLen], blob + P.ops[o].tbl_off, sizeof(cplx) * kDiagTblLen);
     char* tb = reinterpret_cast<char*>(tile.data());
     for (uint64_t t = 0; t < P.hdr.n_tiles; ++t) {
         const uint64_t base = deposit(t, P.hdr.ext_segs, P.hdr.n_ext_segs);
         const uint64_t base_full = base | rank_hi;
-        for (uint32_t tid = 0; tid < (uint32_t)kThreads; ++tid) {  // load phase exactly as the kernel addresses it
+        for (uint32_t tid = 0; tid < threads; ++tid) {  // load phase exactly as the kernel addresses it
             const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, P.hdr.n_tile_segs);
             const uint32_t soff_t = swz(tid) << 4;
             for (uint32_t i = 0; i < n_loads; ++i)
-                if (i * kThreads + tid < tile_len) *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) = state[base + goff_t + P.loads.goff[i]];
+                if (i * threads + tid < tile_len) *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) = state[base + goff_t + P.loads.goff[i]];
         }
         for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
             if (P.ops[o].type == OP_DIAG) ext_phase[P.ops[o].diag_index] = diag_ext_phase(P.ops[o], blob, base_full);
         for (uint32_t r = 0; r < P.hdr.n_rounds; ++r) {
             const DevRound& R = P.rounds[r];
             if (R.type == ROUND_REG) {
-                for (uint32_t e = 0; e < groups; ++e) reg_round(R, P.ops, blob, ext_phase.data(), base_full, e, tile.data());
+                for (uint32_t e = 0; e < groups; ++e) {
+                    uint32_t act[W];
+                    memcpy(act, &thr_act[(size_t)e * W], sizeof(act));
+                    tile_active_mask<W>(P.hdr, P.ops, base_full, act);
+                    reg_round<W>(R, P.ops, blob, ext_phase.data(), use_smem_tbl ? thr_tbl.data() : nullptr, act, e, tile.data());
+                }
             } else {
                 const DevDense* D = reinterpret_cast<const DevDense*>(blob + P.ops[R.first_op].dense_off);
                 for (uint32_t e = 0; e < groups; ++e) {
@@ -56,11 +74,11 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
             }
         }
         const double sc = P.hdr.final_scale;
-        for (uint32_t tid = 0; tid < (uint32_t)kThreads; ++tid) {
+        for (uint32_t tid = 0; tid < threads; ++tid) {
             const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, P.hdr.n_tile_segs);
             const uint32_t soff_t = swz(tid) << 4;
             for (uint32_t i = 0; i < n_loads; ++i)
-                if (i * kThreads + tid < tile_len) {
+                if (i * threads + tid < tile_len) {
                     cplx v = *reinterpret_cast<const cplx*>(tb + (soff_t ^ P.loads.soff[i]));
                     if (sc != 1.0) { v.x *= sc; v.y *= sc; }
                     state[base + goff_t + P.loads.goff[i]] = v;
