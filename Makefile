@@ -5,9 +5,13 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 HOSTCXX := $(shell command -v /usr/bin/g++ || echo g++)
 CSRC := quantr_b200/csrc
-OBJ := build/obj
-NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas -ccbin $(HOSTCXX)
-HOSTFLAGS := -O2 -std=c++17 -fPIC -Wall -Wextra -Wno-unknown-pragmas -pthread
+# amplitudes per thread = 2^QSV_REG_BITS (3 or 4); host scheduler, kernels and the emulation harness must agree
+QSV_REG_BITS ?= 4
+OBJ ?= build/obj$(QSV_REG_BITS)
+LIB ?= quantr_b200/libqsv.so
+QSV_OCC_NUM ?= 2
+NVCCFLAGS := -DQSV_REG_BITS=$(QSV_REG_BITS) -DQSV_OCC_NUM=$(QSV_OCC_NUM) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas -ccbin $(HOSTCXX)
+HOSTFLAGS := -DQSV_REG_BITS=$(QSV_REG_BITS) -DQSV_OCC_NUM=$(QSV_OCC_NUM) -O2 -std=c++17 -fPIC -Wall -Wextra -Wno-unknown-pragmas -pthread
 
 HOST_SRCS := $(CSRC)/plan.cpp $(CSRC)/plan_api.cpp
 HDRS := include/qsv.h $(wildcard $(CSRC)/*.h)
@@ -18,7 +22,7 @@ LIB_OBJS := $(OBJ)/plan.o $(OBJ)/plan_api.o $(OBJ)/kernels.o $(OBJ)/state_api.o 
 all:
 	$(MAKE) -j8 lib oracle emu
 
-lib: quantr_b200/libqsv.so
+lib: $(LIB)
 oracle:
 	$(MAKE) -C oracle
 emu: tests/emu/libqsv_emu.so
@@ -35,7 +39,7 @@ $(OBJ)/%.o: $(CSRC)/%.cpp $(HDRS)
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVCCFLAGS) -c -o $@ $<
 
-quantr_b200/libqsv.so: $(LIB_OBJS)
+$(LIB): $(LIB_OBJS)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(LIB_OBJS) -lcudart -ldl
 
 tests/emu/libqsv_emu.so: tests/emu/qsv_emu.cpp $(HOST_SRCS) $(HDRS)

@@ -152,8 +152,8 @@ const char* qsv_last_error(const qsv_state* s);
 
 /* ---- options ----------------------------------------------------------- */
 
-/* key: "tile_bits" (8..13), "low_bits" (contiguous low index bits kept in every
- * tile, >= 2), "timing" (0/1: record CUDA-event times in qsv_stats),
+/* key: "tile_bits" (4..13), "low_bits" (contiguous low index bits kept in every
+ * tile; 0 = chosen per circuit by the scheduler's cost model), "timing" (0/1: record CUDA-event times in qsv_stats),
  * "fuse" (0: one pass per gate, 1: fused passes). */
 int qsv_set_option(qsv_state* s, const char* key, int64_t value);
 int qsv_get_info(const qsv_state* s, const char* key, int64_t* value);

@@ -12,7 +12,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqsv.so")
+LIB_PATH = os.environ.get("QSV_LIB", os.path.join(_HERE, "libqsv.so"))  # QSV_LIB: developer override (A/B builds)
 
 # gate kinds, src/circuit/gate.rs:19-106 in declaration order (include/qsv.h)
 (GATE_ID, GATE_H, GATE_X, GATE_Y, GATE_Z, GATE_S, GATE_SDAG, GATE_T, GATE_TDAG, GATE_RX, GATE_RY, GATE_RZ,

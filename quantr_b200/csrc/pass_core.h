@@ -41,6 +41,14 @@ QSV_HD void sincospi_hd(double x, double* s, double* c) {
 #endif
 }
 
+QSV_HD uint32_t ctz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)(__ffs((int)v) - 1);
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
+}
+
 // Copies the by-value part of a pass blob into the kernel-parameter struct (host side).
 template <int NR, int NO>
 inline bool fill_params(const uint8_t* blob, PassParams<NR, NO>& out) {
@@ -104,6 +112,7 @@ QSV_HD void c_mul_ip(cplx& a, double fr, double fi) {
 
 template <int J, bool CTRL>
 QSV_HD void mat_general(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
+    if constexpr (J < kRegBits) {
     const double ar = m[0], ai = m[1], br = m[2], bi = m[3], cr = m[4], ci = m[5], dr = m[6], di = m[7];
 #pragma unroll
     for (int s0 = 0; s0 < kSlots; ++s0) {
@@ -129,10 +138,12 @@ QSV_HD void mat_general(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
         f_fma_self(y.x, dr, t2);
         f_fma_self(y.y, dr, t3);
     }
+    }  // J < kRegBits
 }
 
 template <int J, bool CTRL>
 QSV_HD void mat_real(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
+    if constexpr (J < kRegBits) {
     const double ar = m[0], br = m[2], cr = m[4], dr = m[6];
 #pragma unroll
     for (int s0 = 0; s0 < kSlots; ++s0) {
@@ -148,10 +159,12 @@ QSV_HD void mat_real(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
         f_fma_self(x.x, ar, t0);
         f_fma_self(x.y, ar, t1);
     }
+    }  // J < kRegBits
 }
 
 template <int J, bool CTRL>
 QSV_HD void mat_hadamard(cplx (&a)[kSlots], const double (&)[8], uint32_t cm) {
+    if constexpr (J < kRegBits) {
 #pragma unroll
     for (int s0 = 0; s0 < kSlots; ++s0) {
         if ((s0 >> J) & 1) continue;
@@ -161,10 +174,12 @@ QSV_HD void mat_hadamard(cplx (&a)[kSlots], const double (&)[8], uint32_t cm) {
         f_bfly(x.x, y.x);
         f_bfly(x.y, y.y);
     }
+    }  // J < kRegBits
 }
 
 template <int J, bool CTRL>
 QSV_HD void mat_antidiag(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
+    if constexpr (J < kRegBits) {
     const double br = m[2], bi = m[3], cr = m[4], ci = m[5];
 #pragma unroll
     for (int s0 = 0; s0 < kSlots; ++s0) {
@@ -183,10 +198,12 @@ QSV_HD void mat_antidiag(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
         f_mov(x.y, t1);
         f_add_ip(x.y, s1v);
     }
+    }  // J < kRegBits
 }
 
 template <int J, bool CTRL>
 QSV_HD void mat_xswap(cplx (&a)[kSlots], const double (&)[8], uint32_t cm) {
+    if constexpr (J < kRegBits) {
 #pragma unroll
     for (int s0 = 0; s0 < kSlots; ++s0) {
         if ((s0 >> J) & 1) continue;
@@ -197,6 +214,7 @@ QSV_HD void mat_xswap(cplx (&a)[kSlots], const double (&)[8], uint32_t cm) {
         f_mov(t, x.x); f_mov(x.x, y.x); f_mov(y.x, t);
         f_mov(t, x.y); f_mov(x.y, y.y); f_mov(y.y, t);
     }
+    }  // J < kRegBits
 }
 
 // Depth-first doubling over the free register bits: multiplies a[s | S] by f * prod_{k in S} r_k for every subset S of
@@ -205,24 +223,71 @@ QSV_HD void mat_xswap(cplx (&a)[kSlots], const double (&)[8], uint32_t cm) {
 template <int FREE>
 QSV_HD void diag_dfs(cplx (&a)[kSlots], const double (&r)[8], int s, cplx f) {
     c_mul_ip(a[s], f.x, f.y);
-    if (FREE & 1) diag_dfs<0>(a, r, s | 1, cmul(f, cplx{r[0], r[1]}));
-    if (FREE & 2) diag_dfs<(FREE & 1)>(a, r, s | 2, cmul(f, cplx{r[2], r[3]}));
-    if (FREE & 4) diag_dfs<(FREE & 3)>(a, r, s | 4, cmul(f, cplx{r[4], r[5]}));
-    if (FREE & 8) diag_dfs<(FREE & 7)>(a, r, s | 8, cmul(f, cplx{r[6], r[7]}));
+    if constexpr ((FREE & 1) != 0) diag_dfs<0>(a, r, s | 1, cmul(f, cplx{r[0], r[1]}));
+    if constexpr ((FREE & 2) != 0) diag_dfs<(FREE & 1)>(a, r, s | 2, cmul(f, cplx{r[2], r[3]}));
+    if constexpr ((FREE & 4) != 0) diag_dfs<(FREE & 3)>(a, r, s | 4, cmul(f, cplx{r[4], r[5]}));
+    if constexpr ((FREE & 8) != 0 && kRegBits >= 4) diag_dfs<(FREE & 7)>(a, r, s | 8, cmul(f, cplx{r[6], r[7]}));
 }
 
 // amp[s] *= w * R[s] for the slots selected by the register-control mask, R[s] = prod_{k: bit k of s} r_k.
 // SEL = 0: all 16 slots, SEL = 1..4: the 8 slots with register bit SEL-1 set, SEL = 5: generic runtime mask.
 // tbl: the op's thread-phase table lo[32], hi[16] (shared memory for small passes, global otherwise).
-template <int SEL, bool HAS_REG>
-QSV_HD void diag_apply(cplx (&a)[kSlots], const DevOp& op, const cplx* tbl, uint32_t e, cplx w) {
-    if (op.flags & DIAG_HAS_THR_LO) w = cmul(w, tbl[e & 31u]);
+// Where a pass keeps the thread-dependent phase factors of its DIAG ops, given the shared memory one CTA may use
+// while keeping the intended number of CTAs per SM (launcher and host emulation must agree):
+//   2: per-thread phases [n_diag][threads] in shared memory, computed once per launch
+//   1: the lo/hi tables [n_diag][48] in shared memory      0: tables read from global memory
+#ifndef QSV_OCC_NUM
+#define QSV_OCC_NUM 2  // CTAs per SM at T = 12 (x2 at T = 11, x4 at T = 10, /2 at T = 13); build parameter for occupancy experiments
+#endif
+QSV_HD constexpr uint32_t tile_min_blocks(uint32_t T) { return T >= 13 ? (QSV_OCC_NUM / 2 ? QSV_OCC_NUM / 2 : 1u) : T == 12 ? QSV_OCC_NUM : T == 11 ? 2u * QSV_OCC_NUM : 4u * QSV_OCC_NUM; }
+inline size_t pass_smem_bytes(uint32_t T, uint32_t n_diag, int mode) {
+    size_t b = (sizeof(cplx) << T) + sizeof(cplx) * (n_diag + 1);
+    if (mode == 2) b += sizeof(cplx) * (size_t)n_diag * tile_threads(T);
+    if (mode == 1) b += sizeof(cplx) * (size_t)n_diag * kDiagTblLen;
+    return b;
+}
+inline int choose_diag_mode(uint32_t T, uint32_t n_diag) {
+    if (n_diag == 0) return 0;
+    const size_t budget = (size_t)(227 * 1024) / tile_min_blocks(T) - 1024;
+    if (pass_smem_bytes(T, n_diag, 1) <= budget) return 1;  // measured faster than mode 2 on B200 (less shared memory per CTA)
+    if (pass_smem_bytes(T, n_diag, 2) <= budget) return 2;
+    return 0;
+}
+
+// Thread phase of a DIAG op: product of its lo/hi table entries for thread-group e (tile-independent).
+QSV_HD cplx diag_thread_phase(const DevOp& op, const cplx* tbl, uint32_t e) {
+    cplx w{1.0, 0.0};
+    if (op.flags & DIAG_HAS_THR_LO) w = tbl[e & 31u];
     if (op.flags & DIAG_HAS_THR_HI) w = cmul(w, tbl[32u + (e >> 5)]);
-    constexpr bool kSingle = SEL >= 1 && SEL <= 4;
+    return w;
+}
+
+// ctx.thr_phase != null: per-thread phases precomputed once per launch ([diag_index * threads + e], shared memory);
+// otherwise ctx.thr_tbl (shared memory) or the blob (global memory) holds the lo/hi tables.
+struct DiagCtx {
+    const uint8_t* blob;
+    const cplx* ext_phase;
+    const cplx* thr_tbl;
+    const cplx* thr_phase;
+    uint32_t threads;
+};
+
+template <int SEL, bool HAS_REG>
+QSV_HD void diag_apply(cplx (&a)[kSlots], const DevOp& op, const DiagCtx& ctx, uint32_t e) {
+    cplx w = ctx.ext_phase[op.diag_index];
+    if (ctx.thr_phase) {
+        if (op.flags & (DIAG_HAS_THR_LO | DIAG_HAS_THR_HI)) w = cmul(w, ctx.thr_phase[op.diag_index * ctx.threads + e]);
+    } else {
+        const cplx* tbl = ctx.thr_tbl ? ctx.thr_tbl + op.diag_index * kDiagTblLen : reinterpret_cast<const cplx*>(ctx.blob + op.tbl_off);
+        if (op.flags & DIAG_HAS_THR_LO) w = cmul(w, tbl[e & 31u]);
+        if (op.flags & DIAG_HAS_THR_HI) w = cmul(w, tbl[32u + (e >> 5)]);
+    }
+    constexpr bool kSingle = SEL >= 1 && SEL <= kRegBits;
     constexpr int kBit = kSingle ? (1 << (SEL - 1)) : 0;
+    if constexpr (SEL > kRegBits && SEL <= 4) return;  // no such register bit in this build
     if (SEL <= 4) {
         if (HAS_REG) {
-            diag_dfs<(15 & ~kBit)>(a, op.m, kBit, w);  // the control bit itself carries no linear term
+            diag_dfs<((kSlots - 1) & ~kBit)>(a, op.m, kBit, w);  // the control bit itself carries no linear term
         } else {
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) {
@@ -279,12 +344,12 @@ inline uint32_t op_dispatch_code(const DevOp& op) {
     case kCodeMatBase + KIND * 8 + 7: FN<3, true>(a, op.m, op.cmask_reg); break;
 
 #define QSV_DIAG_CASES(HAS_REG)                                                                                                    \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 0: diag_apply<0, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;           \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 1: diag_apply<1, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;           \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 2: diag_apply<2, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;           \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 3: diag_apply<3, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;           \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 4: diag_apply<4, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;           \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 5: diag_apply<5, HAS_REG>(a, op, QSV_DIAG_TBL, e, ext_phase[op.diag_index]); break;
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 0: diag_apply<0, HAS_REG>(a, op, ctx, e); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 1: diag_apply<1, HAS_REG>(a, op, ctx, e); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 2: diag_apply<2, HAS_REG>(a, op, ctx, e); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 3: diag_apply<3, HAS_REG>(a, op, ctx, e); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 4: diag_apply<4, HAS_REG>(a, op, ctx, e); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 5: diag_apply<5, HAS_REG>(a, op, ctx, e); break;
 
 // Which ops of the pass act on thread-group e (controls among the thread's fixed tile-local bits).  Tile-independent:
 // the kernel evaluates it once per launch.  W words of 32 op bits.
@@ -311,41 +376,60 @@ QSV_HD void tile_active_mask(const DevPass& hdr, const DevOp* ops, uint64_t base
     for (int w = 0; w < W; ++w) {
         uint32_t m = hdr.ext_ctrl_mask[w];
         while (m) {
-            const uint32_t bit = m & (0u - m);
-            m ^= bit;
-            uint32_t o = 32u * w;
-            for (uint32_t t = bit; t > 1; t >>= 1) ++o;
-            if ((base_full & ops[o].cmask_ext) != ops[o].cmask_ext) act[w] &= ~bit;
+            const uint32_t b = ctz32(m);
+            m &= m - 1;
+            const uint32_t o = 32u * w + b;
+            if ((base_full & ops[o].cmask_ext) != ops[o].cmask_ext) act[w] &= ~(1u << b);
         }
     }
 }
 
-// One register round for thread-group index e (0 <= e < 2^(T-4)).
-//   tile      : the tile in (swizzled) shared memory
-//   ops       : the pass's op array
-//   ext_phase : per-tile external phases of the pass's DIAG ops
-//   act       : bit o set = op o acts on this thread-group for this tile
-//   thr_tbl   : when non-null, the DIAG thread-phase tables staged in shared memory (kDiagTblLen entries per diag_index);
-//               otherwise they are read from the blob in global memory
-#define QSV_DIAG_TBL (thr_tbl ? thr_tbl + op.diag_index * kDiagTblLen : reinterpret_cast<const cplx*>(blob + op.tbl_off))
-template <int W>
-QSV_HD void reg_round(const DevRound& R, const DevOp* ops, const uint8_t* blob, const cplx* ext_phase, const cplx* thr_tbl,
-                      const uint32_t (&act)[W], uint32_t e, cplx* tile) {
-    const uint32_t lb = (uint32_t)deposit(e, R.thr_segs, R.n_thr_segs);
+// A register round for thread-group e (0 <= e < 2^(T-4)) is: round_load (16 amplitudes from the swizzled tile into
+// registers), round_ops (the round's ops, in place), then round_store_tile or - for the last round of a pass flagged
+// PASS_DIRECT_STORE - round_store_global.
+QSV_HD uint32_t round_thread_base(const DevRound& R, uint32_t e) { return (uint32_t)deposit(e, R.thr_segs, R.n_thr_segs); }
+
+QSV_HD void round_load(const DevRound& R, uint32_t lb, const cplx* tile, cplx (&a)[kSlots]) {
     const uint32_t sb = swz(lb) << 4;
-    char* tb = reinterpret_cast<char*>(tile);
-    cplx a[kSlots];
+    const char* tb = reinterpret_cast<const char*>(tile);
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const cplx*>(tb + (sb ^ R.xoff[s]));
-    const uint32_t first = R.first_op, last = R.first_op + R.n_ops;
-    for (uint32_t o = first; o < last; ++o) {
-        uint32_t word = act[0];
+}
+
+QSV_HD void round_store_tile(const DevRound& R, uint32_t lb, cplx* tile, const cplx (&a)[kSlots]) {
+    const uint32_t sb = swz(lb) << 4;
+    char* tb = reinterpret_cast<char*>(tile);
 #pragma unroll
-        for (int w = 1; w < W; ++w)
-            if ((int)(o >> 5) == w) word = act[w];
-        if (!((word >> (o & 31u)) & 1u)) continue;
-        const DevOp& op = ops[o];
-        switch (op.code) {
+    for (int s = 0; s < kSlots; ++s) *reinterpret_cast<cplx*>(tb + (sb ^ R.xoff[s])) = a[s];
+}
+
+//   act : bit o set = op o of the pass acts on this thread-group for this tile (W words)
+template <int W>
+QSV_HD void round_ops(const DevRound& R, const DevOp* ops, const DiagCtx& ctx, const uint32_t (&act)[W], uint32_t e, cplx (&a)[kSlots]) {
+    const uint32_t first = R.first_op, n = R.n_ops;  // n <= kMaxRoundOps
+    if (n == 0) return;
+    // the round's slice of the active mask, bit j = op first + j
+    uint32_t lo = act[0], hi = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        if ((int)(first >> 5) == w) lo = act[w];
+        if ((int)(first >> 5) + 1 == w) hi = act[w];
+    }
+    const uint32_t sh = first & 31u;
+    uint32_t m = sh ? ((lo >> sh) | (hi << (32u - sh))) : lo;
+    if (n < 32u) m &= (1u << n) - 1u;
+    if (!m) return;
+    uint32_t j = ctz32(m);
+    uint32_t code = ops[first + j].code;
+    while (true) {
+        const DevOp& op = ops[first + j];
+        m &= m - 1;
+        uint32_t jn = 0, next_code = kCodeNop;
+        if (m) {  // fetch the next op's dispatch code before running this one
+            jn = ctz32(m);
+            next_code = ops[first + jn].code;
+        }
+        switch (code) {
             QSV_MAT_CASES(0, mat_hadamard)
             QSV_MAT_CASES(1, mat_xswap)
             QSV_MAT_CASES(2, mat_real)
@@ -355,9 +439,10 @@ QSV_HD void reg_round(const DevRound& R, const DevOp* ops, const uint8_t* blob, 
             QSV_DIAG_CASES(true)
             default: break;
         }
+        if (!m) break;
+        j = jn;
+        code = next_code;
     }
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) *reinterpret_cast<cplx*>(tb + (sb ^ R.xoff[s])) = a[s];
 }
 
 // Dense (Custom) round, phase 1: thread-group e computes outputs l = 16*e .. 16*e+15 from the

@@ -5,6 +5,7 @@
 // Replaces Circuit::apply_gate (src/circuit/simulation.rs:64-135) for a fused list of gates.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "pass_core.h"
@@ -21,8 +22,6 @@ __device__ __forceinline__ cplx ld_stream(const cplx* p) {
 }
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // ---------------------------------------------------------------------------------------------
 // Fused pass.  One thread per register group of 16 amplitudes: a tile of 2^T amplitudes is worked on by
 // 2^(T-4) threads (T = 12: 256 threads, 2 CTAs/SM; T = 11: 128 threads, 4 CTAs/SM; T = 13: 512 threads, 1 CTA/SM).
@@ -34,13 +33,13 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 template <int T_STATIC>
 struct TileCfg {
     static constexpr uint32_t kThreads = T_STATIC ? (1u << (T_STATIC - kRegBits)) : (uint32_t)kSmallTileThreads;
-    static constexpr uint32_t kMinBlocks = T_STATIC >= 13 ? 1 : T_STATIC == 12 ? 2 : T_STATIC == 11 ? 4 : 8;
+    static constexpr uint32_t kMinBlocks = T_STATIC ? tile_min_blocks(T_STATIC) : 8;
     static constexpr uint32_t kLoads = T_STATIC ? (uint32_t)kSlots : 8u;  // runtime T <= 9: 2^9 / 64
 };
 
 template <int T_STATIC, int NR, int NO>
 __global__ void __launch_bounds__(TileCfg<T_STATIC>::kThreads, TileCfg<T_STATIC>::kMinBlocks)
-pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t rank_hi, const __grid_constant__ PassParams<NR, NO> P) {
+pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t rank_hi, int diag_mode, const __grid_constant__ PassParams<NR, NO> P) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr uint32_t kThreads = TileCfg<T_STATIC>::kThreads;
     constexpr uint32_t kLoads = TileCfg<T_STATIC>::kLoads;
@@ -51,26 +50,32 @@ pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t
     cplx* tile = reinterpret_cast<cplx*>(smem);
     char* tb = reinterpret_cast<char*>(smem);
     cplx* ext_phase = reinterpret_cast<cplx*>(smem + sizeof(cplx) * tile_len);
-    // small passes keep the DIAG thread-phase tables in shared memory (no global loads in the op loop)
-    constexpr bool kTblSmem = (NO == kSmallOps);
-    cplx* thr_tbl = kTblSmem ? ext_phase + (P.hdr.n_diag + 1) : nullptr;
+    cplx* diag_smem = ext_phase + (P.hdr.n_diag + 1);  // mode 2: [n_diag][threads] thread phases; mode 1: [n_diag][48] tables
     const uint32_t tid = threadIdx.x;
-    if (kTblSmem) {
+    const bool active = T_STATIC || tid < groups;      // runtime-T kernel: more threads than register groups
+    const uint32_t n_tile_segs = P.hdr.n_tile_segs, n_ext_segs = P.hdr.n_ext_segs, n_rounds = P.hdr.n_rounds;
+    const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, n_tile_segs);
+    const uint32_t soff_t = swz(tid) << 4;
+    const double final_scale = P.hdr.final_scale;
+    const bool direct = (P.hdr.flags & PASS_DIRECT_STORE) != 0;
+
+    // ---- once per launch: thread-dependent pieces that do not depend on the tile ----------------------
+    uint32_t thr_act[W];
+    thread_active_mask<W>(P.hdr, P.rounds, P.ops, tid, thr_act);
+    if (diag_mode & 3) {
         for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
             if (P.ops[o].type == OP_DIAG) {
                 const cplx* src = reinterpret_cast<const cplx*>(blob + P.ops[o].tbl_off);
-                for (uint32_t i = tid; i < (uint32_t)kDiagTblLen; i += kThreads) thr_tbl[P.ops[o].diag_index * kDiagTblLen + i] = src[i];
+                if ((diag_mode & 3) == 2) {
+                    if (active) diag_smem[P.ops[o].diag_index * kThreads + tid] = diag_thread_phase(P.ops[o], src, tid);
+                } else {
+                    for (uint32_t i = tid; i < (uint32_t)kDiagTblLen; i += kThreads) diag_smem[P.ops[o].diag_index * kDiagTblLen + i] = src[i];
+                }
             }
     }
-    const uint32_t n_tile_segs = P.hdr.n_tile_segs, n_ext_segs = P.hdr.n_ext_segs;
-    const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, n_tile_segs);
-    const uint64_t pf_t = deposit(8ull * tid, P.hdr.tile_segs, n_tile_segs);
-    const uint32_t soff_t = swz(tid) << 4;
-    const double final_scale = P.hdr.final_scale;
-    const bool l2_prefetch = (P.hdr.flags & PASS_L2_PREFETCH) != 0;
-
-    uint32_t thr_act[W];
-    thread_active_mask<W>(P.hdr, P.rounds, P.ops, tid, thr_act);
+    const DiagCtx ctx{blob, ext_phase, (diag_mode & 3) == 1 ? diag_smem : nullptr, (diag_mode & 3) == 2 ? diag_smem : nullptr, kThreads};
+    // direct store: element offset of this thread's 16 amplitudes in the last round
+    const uint64_t gstore_t = (direct && n_rounds) ? deposit(round_thread_base(P.rounds[n_rounds - 1], tid), P.hdr.tile_segs, n_tile_segs) : 0;
 
     for (uint64_t t = blockIdx.x; t < P.hdr.n_tiles; t += gridDim.x) {
         const uint64_t base = deposit(t, P.hdr.ext_segs, n_ext_segs);
@@ -85,32 +90,46 @@ pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t
             for (uint32_t i = 0; i < kLoads; ++i)
                 if (T_STATIC || i * kThreads + tid < tile_len) *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) = v[i];
         }
-        if (l2_prefetch && t + gridDim.x < P.hdr.n_tiles && (T_STATIC || 8u * tid < tile_len)) {
-            // pull the CTA's next tile into L2 while this one is processed: two 128-byte lines per thread
-            const cplx* nxt = state + deposit(t + gridDim.x, P.hdr.ext_segs, n_ext_segs) + pf_t;
-            prefetch_l2(nxt);
-            if (T_STATIC) prefetch_l2(nxt + P.hdr.pf_step);
-        }
         for (uint32_t o = tid; o < P.hdr.n_ops; o += kThreads)
-            if (P.ops[o].type == OP_DIAG) ext_phase[P.ops[o].diag_index] = diag_ext_phase(P.ops[o], blob, base_full);
+            if (P.ops[o].type == OP_DIAG) ext_phase[P.ops[o].diag_index] = (diag_mode & 8) ? cplx{1.0, 0.0} : diag_ext_phase(P.ops[o], blob, base_full);
         uint32_t act[W];
 #pragma unroll
         for (int w = 0; w < W; ++w) act[w] = thr_act[w];
         tile_active_mask<W>(P.hdr, P.ops, base_full, act);
         __syncthreads();
 
-        for (uint32_t r = 0; r < P.hdr.n_rounds; ++r) {
+        for (uint32_t r = 0; r < n_rounds; ++r) {
             if (P.rounds[r].type == ROUND_REG) {
-                if (T_STATIC || tid < groups) reg_round<W>(P.rounds[r], P.ops, blob, ext_phase, thr_tbl, act, tid, tile);
+                if (active) {
+                    const uint32_t lb = round_thread_base(P.rounds[r], tid);
+                    cplx a[kSlots];
+                    round_load(P.rounds[r], lb, tile, a);
+                    round_ops<W>(P.rounds[r], P.ops, ctx, act, tid, a);
+                    if (direct && r + 1 == n_rounds) {
+                        cplx* g = state + base + gstore_t;
+#pragma unroll
+                        for (int s = 0; s < kSlots; ++s) {
+                            cplx v = a[s];
+                            if (final_scale != 1.0) {
+                                v.x *= final_scale;
+                                v.y *= final_scale;
+                            }
+                            st_stream(g + P.loads.store_goff[s], v);
+                        }
+                    } else {
+                        round_store_tile(P.rounds[r], lb, tile, a);
+                    }
+                }
             } else {
                 const DevDense& D = *reinterpret_cast<const DevDense*>(blob + P.ops[P.rounds[r].first_op].dense_off);
                 cplx out[kSlots];
-                if (T_STATIC || tid < groups) dense_compute(D, blob, tid, tile, out);
+                if (active) dense_compute(D, blob, tid, tile, out);
                 __syncthreads();
-                if (T_STATIC || tid < groups) dense_store(tid, tile, out);
+                if (active) dense_store(tid, tile, out);
             }
             __syncthreads();
         }
+        if (direct) continue;  // the barrier after the last round already protects the tile buffer
 
 #pragma unroll
         for (uint32_t i = 0; i < kLoads; ++i) {
@@ -134,21 +153,25 @@ static cudaError_t launch_pass_t(cplx* state, const uint8_t* dev_blob, const uin
     const DevPass& hdr = params.hdr;
     constexpr uint32_t kThreads = TileCfg<T_STATIC>::kThreads;
     if (hdr.threads != kThreads) return cudaErrorInvalidValue;
-    constexpr bool kTblSmem = (NO == kSmallOps);
-    const size_t smem = sizeof(cplx) * (size_t(1) << hdr.tile_bits) + sizeof(cplx) * (hdr.n_diag + 1) + (kTblSmem ? sizeof(cplx) * kDiagTblLen * hdr.n_diag : 0);
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        const size_t want = sizeof(cplx) * (size_t(1) << (T_STATIC ? T_STATIC : 9)) + sizeof(cplx) * (NO + 1) + (kTblSmem ? sizeof(cplx) * kDiagTblLen * NO : 0);
-        cudaError_t err = cudaFuncSetAttribute(pass_kernel<T_STATIC, NR, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    static const int mode_cap = getenv("QSV_DIAG_MODE") ? atoi(getenv("QSV_DIAG_MODE")) : 2;  // developer A/B switch
+    int mode = choose_diag_mode(hdr.tile_bits, hdr.n_diag);
+    if (mode > mode_cap) mode = mode_cap;
+    const size_t smem = pass_smem_bytes(hdr.tile_bits, hdr.n_diag, mode);
+    static size_t smem_cfg = 0;
+    if (smem_cfg == 0) {
+        smem_cfg = (size_t)(227 * 1024) - 1024;  // opt-in maximum; the per-launch size decides the occupancy
+        cudaError_t err = cudaFuncSetAttribute(pass_kernel<T_STATIC, NR, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cfg);
         if (err != cudaSuccess) return err;
-        int nb = 0;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pass_kernel<T_STATIC, NR, NO>, (int)kThreads, want);
-        if (err != cudaSuccess) return err;
-        blocks_per_sm = nb > 0 ? nb : 1;
     }
-    uint64_t grid = (uint64_t)sm_count * (uint64_t)blocks_per_sm;
+    if (smem > smem_cfg) return cudaErrorInvalidValue;
+    static const size_t pad = getenv("QSV_SMEM_PAD") ? (size_t)atol(getenv("QSV_SMEM_PAD")) : 0;  // occupancy experiments
+    const size_t smem_launch = (smem + pad <= smem_cfg) ? smem + pad : smem;
+    int nb = 0;
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pass_kernel<T_STATIC, NR, NO>, (int)kThreads, smem_launch);
+    if (err != cudaSuccess) return err;
+    uint64_t grid = (uint64_t)sm_count * (uint64_t)(nb > 0 ? nb : 1);
     if (grid > hdr.n_tiles) grid = hdr.n_tiles;
-    pass_kernel<T_STATIC, NR, NO><<<(unsigned)grid, kThreads, smem, stream>>>(state, dev_blob, rank_hi, params);
+    pass_kernel<T_STATIC, NR, NO><<<(unsigned)grid, kThreads, smem_launch, stream>>>(state, dev_blob, rank_hi, mode | (getenv("QSV_SKIP_EXT") ? 8 : 0), params);
     return cudaGetLastError();
 }
 

@@ -379,14 +379,14 @@ void emit_pass(Plan& plan, const PassB& pb) {
                     for (int b = 0; b < 5; ++b) if ((i >> b) & 1) alo += thr_coef[b];
                     tbl[i] = unit_phase(alo);
                 }
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 32; ++i) {
                     double ahi = 0;
-                    for (int b = 0; b < 4; ++b) if ((i >> b) & 1) ahi += thr_coef[5 + b];
+                    for (int b = 0; b < 5; ++b) if ((i >> b) & 1) ahi += thr_coef[5 + b];
                     tbl[32 + i] = unit_phase(ahi);
                 }
                 for (int b = 0; b < 5; ++b) has_lo |= thr_coef[b] != 0.0;
-                for (int b = 5; b < 9; ++b) has_hi |= thr_coef[b] != 0.0;
-                for (int j = 0; j < 4; ++j) {
+                for (int b = 5; b < 10; ++b) has_hi |= thr_coef[b] != 0.0;
+                for (int j = 0; j < 4; ++j) {  // unused register slots (j >= kRegBits) stay at phase 1
                     const cplx r = unit_phase(reg_coef[j]);
                     d.m[2 * j] = r.x;
                     d.m[2 * j + 1] = r.y;
@@ -407,6 +407,21 @@ void emit_pass(Plan& plan, const PassB& pb) {
     }
     if (rounds.size() > (size_t)kMaxRounds || ops.size() > (size_t)kMaxOps) fail("internal: pass exceeds round/op caps");
 
+    // Last round of the pass: if it is a register round whose register bits leave the three lowest tile bits to the
+    // threads, its 16 amplitudes per thread go straight from registers to global memory (still 128-byte coalesced).
+    if (!rounds.empty() && rounds.back().type == ROUND_REG && T >= 7 && plan.opt.direct_store) {
+        const DevRound& lr = rounds.back();
+        bool ok = true;
+        for (int j = 0; j < kRegBits; ++j) ok &= lr.reg_pos[j] >= 3;
+        if (ok) {
+            hdr.flags |= PASS_DIRECT_STORE;
+            for (int sl = 0; sl < kSlots; ++sl) {
+                uint32_t off = 0;
+                for (int j = 0; j < kRegBits; ++j) if ((sl >> j) & 1) off |= 1u << lr.reg_pos[j];
+                loads.store_goff[sl] = deposit(off, hdr.tile_segs, hdr.n_tile_segs);
+            }
+        }
+    }
     hdr.n_rounds = (uint32_t)rounds.size();
     hdr.n_ops = (uint32_t)ops.size();
     hdr.n_diag = n_diag;
@@ -456,52 +471,95 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
 
     const int nloc = (int)plan.n_alloc;
     const int T = std::min<int>(plan.opt.tile_bits, nloc);
-    const int L = std::max(0, std::min<int>(plan.opt.low_bits, T - 1));
-    const uint64_t low_mask = (T == nloc) ? 0 : ((1ull << L) - 1);  // single-tile states: every bit is a tile bit
     const uint64_t local_mask = (nloc >= 64) ? ~0ull : ((1ull << n_local) - 1);
-
-    PassB cur;
-    auto close_pass = [&]() {
-        if (!cur.empty()) emit_pass(plan, cur);
-        cur = PassB();
-    };
-    for (size_t i = 0; i < plan.lops.size(); ++i) {
-        const LOp& lop = plan.lops[i];
+    for (const LOp& lop : plan.lops) {
         const uint64_t tg = lop.targets();
         if (tg & ~local_mask) fail("gate " + std::to_string(lop.src_gate) + " targets a qubit held across ranks; global-qubit remap is required");
         if (lop.kind == LOp::DENSE && popcnt(tg) > T) fail("Custom gate is wider than the tile (" + std::to_string(T) + " bits)");
-        if (!plan.opt.fuse) close_pass();
-        // Can the op join the open pass?  Its targets must fit next to the pass's tile bits and the
-        // low passenger bits, and the pass must stay within the kernel's round/op caps.
-        const bool can_join = !cur.relaxed_low && popcnt(cur.req | tg | low_mask) <= T &&
-                              cur.n_ops + 1 <= (size_t)kMaxOps && cur.rounds.size() + 1 <= (size_t)kMaxRounds;
-        if (!can_join) close_pass();
-        // A Custom gate wider than T - low_bits gets a pass of its own without passenger bits.
-        const bool relaxed = popcnt(cur.req | tg | low_mask) > T;
-        cur.req |= tg;
-        cur.relaxed_low |= relaxed;
-        if (lop.kind == LOp::DENSE) {
-            RoundB r;
-            r.dense = true;
-            r.ops.push_back(i);
-            cur.rounds.push_back(std::move(r));
-        } else {
-            if (cur.rounds.empty() || cur.rounds.back().dense) cur.rounds.push_back(RoundB());
-            if (lop.kind == LOp::MAT) {
-                RoundB* r = &cur.rounds.back();
-                if (std::find(r->reg.begin(), r->reg.end(), lop.target) == r->reg.end()) {
-                    if ((int)r->reg.size() == kRegBits) { cur.rounds.push_back(RoundB()); r = &cur.rounds.back(); }
-                    r->reg.push_back(lop.target);
-                }
-                r->ops.push_back(i);
-            } else {
-                cur.rounds.back().ops.push_back(i);
-            }
-        }
-        cur.n_ops++;
-        if (relaxed) close_pass();
     }
-    close_pass();
+
+    // Greedy in-order grouping of the lowered ops into passes for a given number of low passenger bits.
+    auto schedule = [&](int L, std::vector<PassB>& out) {
+        out.clear();
+        const uint64_t low_mask = (T == nloc) ? 0 : ((1ull << L) - 1);  // single-tile states: every bit is a tile bit
+        PassB cur;
+        auto close_pass = [&]() {
+            if (!cur.empty()) out.push_back(std::move(cur));
+            cur = PassB();
+        };
+        for (size_t i = 0; i < plan.lops.size(); ++i) {
+            const LOp& lop = plan.lops[i];
+            const uint64_t tg = lop.targets();
+            if (!plan.opt.fuse) close_pass();
+            // Can the op join the open pass?  Its targets must fit next to the pass's tile bits and the
+            // low passenger bits, and the pass must stay within the kernel's round/op caps.
+            const bool can_join = !cur.relaxed_low && popcnt(cur.req | tg | low_mask) <= T &&
+                                  cur.n_ops + 1 <= (size_t)kMaxOps && cur.rounds.size() + 2 <= (size_t)kMaxRounds;
+            if (!can_join) close_pass();
+            // A Custom gate wider than T - low_bits gets a pass of its own without passenger bits.
+            const bool relaxed = popcnt(cur.req | tg | low_mask) > T;
+            cur.req |= tg;
+            cur.relaxed_low |= relaxed;
+            if (lop.kind == LOp::DENSE) {
+                RoundB r;
+                r.dense = true;
+                r.ops.push_back(i);
+                cur.rounds.push_back(std::move(r));
+            } else {
+                if (cur.rounds.empty() || cur.rounds.back().dense) cur.rounds.push_back(RoundB());
+                if (cur.rounds.back().ops.size() >= (size_t)kMaxRoundOps) cur.rounds.push_back(RoundB());
+                if (lop.kind == LOp::MAT) {
+                    RoundB* r = &cur.rounds.back();
+                    if (std::find(r->reg.begin(), r->reg.end(), lop.target) == r->reg.end()) {
+                        if ((int)r->reg.size() == kRegBits) { cur.rounds.push_back(RoundB()); r = &cur.rounds.back(); }
+                        r->reg.push_back(lop.target);
+                    }
+                    r->ops.push_back(i);
+                } else {
+                    cur.rounds.back().ops.push_back(i);
+                }
+            }
+            cur.n_ops++;
+            if (relaxed) close_pass();
+        }
+        close_pass();
+    };
+
+    // Cost model (units: one pass streamed at the HBM roofline = 1).  Memory: measured streaming efficiency of a
+    // tile whose contiguous runs are 16 B << run_bits (tools/stream_probe.py on B200).  The arithmetic of the ops is
+    // the same for every candidate, so only the memory term and the number of passes decide.
+    auto plan_cost = [&](const std::vector<PassB>& passes) {
+        double total = 0;
+        for (const PassB& pb : passes) {
+            uint64_t tile_mask = pb.req;
+            for (int b = 0; b < nloc && popcnt(tile_mask) < T; ++b) tile_mask |= 1ull << b;
+            int run_bits = 0;
+            while (run_bits < nloc && ((tile_mask >> run_bits) & 1)) ++run_bits;
+            const double eff = run_bits <= 3 ? 0.47 : run_bits == 4 ? 0.68 : run_bits == 5 ? 0.75 : run_bits == 6 ? 0.80 : run_bits == 7 ? 0.85 : 0.90;
+            total += 1.0 / eff;
+        }
+        return total;
+    };
+
+    std::vector<PassB> best;
+    if (plan.opt.low_bits > 0 || T == nloc || !plan.opt.fuse) {
+        const int L = std::max(0, std::min<int>(plan.opt.low_bits > 0 ? plan.opt.low_bits : 3, T - 1));
+        plan.opt.low_bits = L;
+        schedule(L, best);
+    } else {
+        // low_bits = 0: pick the number of passenger bits that minimises the modelled cost (longer runs stream
+        // better, fewer passenger bits fuse more gates per pass); ties go to the longer runs.
+        double best_cost = 0;
+        int best_L = 3;
+        std::vector<PassB> cand;
+        for (int L = std::min(8, T - 1); L >= 3; --L) {
+            schedule(L, cand);
+            const double c = plan_cost(cand);
+            if (best.empty() || c < best_cost - 1e-9) { best_cost = c; best_L = L; best.swap(cand); }
+        }
+        plan.opt.low_bits = best_L;
+    }
+    for (const PassB& pb : best) emit_pass(plan, pb);
 }
 
 std::string describe_plan(const Plan& plan) {

@@ -37,9 +37,10 @@ struct LOp {
 
 struct PlanOptions {
     int tile_bits = 12;
-    int low_bits = 3;
+    int low_bits = 0;     // contiguous low index bits kept in every tile; 0 = chosen per circuit by the cost model
     int fuse = 1;
-    int l2_prefetch = 1;  // prefetch the CTA's next tile into L2 while the current one is processed
+    int direct_store = 1; // last round stores registers straight to global memory when that stays coalesced
+    int l2_prefetch = 0;  // prefetch the CTA's next tile into L2 while the current one is processed
 };
 
 struct Plan {

@@ -28,6 +28,7 @@ int qsv_plan_create(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubits, 
         if (low_bits) opt.low_bits = (int)low_bits;
         opt.fuse = fuse;
         if (const char* env = getenv("QSV_L2_PREFETCH")) opt.l2_prefetch = atoi(env) != 0;
+        if (const char* env = getenv("QSV_DIRECT_STORE")) opt.direct_store = atoi(env) != 0;
         try {
             qsv::build_plan(p->plan, n_qubits, n_local_qubits, ops, n_ops, opt);
         } catch (...) {

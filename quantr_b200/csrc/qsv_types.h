@@ -21,8 +21,13 @@
 
 namespace qsv {
 
-constexpr int kRegBits = 4;
+#ifndef QSV_REG_BITS
+#define QSV_REG_BITS 4  // amplitudes per thread = 2^QSV_REG_BITS (build parameter; host and device must agree)
+#endif
+constexpr int kRegBits = QSV_REG_BITS;
 constexpr int kSlots = 1 << kRegBits;
+constexpr int kMaxSlots = 16;         // array extents in the blob layout (independent of the build parameter)
+static_assert(kRegBits == 3 || kRegBits == 4, "QSV_REG_BITS must be 3 or 4");
 constexpr int kMinQubits = 4;      // states smaller than one register group are padded with idle top bits
 constexpr int kMaxTileBits = 13;
 constexpr int kMaxSegs = 16;
@@ -31,7 +36,7 @@ constexpr int kMaxRounds = 32;
 constexpr int kMaxOps = 96;
 constexpr int kSmallRounds = 8;   // capacity classes of the kernel-parameter pass descriptor
 constexpr int kSmallOps = 24;
-constexpr int kMaxLoads = kSlots;   // global loads per thread per tile: one CTA thread per 16 amplitudes
+constexpr int kMaxLoads = kMaxSlots; // global loads per thread per tile (= kSlots: one CTA thread per register group)
 constexpr int kSmallTileThreads = 64; // CTA size for tiles below 2^10 amplitudes
 
 // CTA size for a tile of 2^T amplitudes: one thread per register group of 16 amplitudes.
@@ -61,9 +66,14 @@ enum OpType : uint32_t {
 // Fully resolved dispatch code of an op inside a register round (one jump-table entry per routine):
 //   MAT : 1 + kind*8 + ctrl*4 + slot, kind = 0 HADAMARD, 1 XSWAP, 2 REAL, 3 GENERAL, 4 ANTIDIAG; ctrl = has register controls
 //   DIAG: 41 + has_reg*6 + sel,        sel = 0 all slots, 1..4 slots with register bit sel-1 set, 5 runtime mask
-constexpr int kDiagTblLen = 48;  // lo[32] (thread-index bits 0-4) + hi[16] (bits 5-8)
+constexpr int kDiagTblLen = 64;  // lo[32] (thread-index bits 0-4) + hi[32] (bits 5-9)
 constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeCount = 53;
-enum PassFlags : uint32_t { PASS_L2_PREFETCH = 1 };
+enum PassFlags : uint32_t {
+    PASS_L2_PREFETCH = 1,
+    PASS_DIRECT_STORE = 2  // the last round writes its registers straight to global memory (coalesced: its register bits
+                           // exclude the three lowest tile bits)
+};
+constexpr int kMaxRoundOps = 32;  // ops per register round (one 32-bit active mask)
 
 enum DiagFlags : uint32_t { DIAG_HAS_THR_LO = 1, DIAG_HAS_THR_HI = 2, DIAG_HAS_REG = 4 };
 enum RoundType : uint32_t { ROUND_REG = 0, ROUND_DENSE = 1 };
@@ -103,7 +113,7 @@ struct DevRound {
     uint8_t reg_pos[4];  // tile-local positions of the 4 register bits, ascending
     uint32_t pad[3];
     Seg thr_segs[kMaxThrSegs];  // thread index e -> tile-local index with register bits zero
-    uint32_t xoff[kSlots];      // byte offset of swz(slot s's tile-local offset): address = (swz(lb) << 4) ^ xoff[s]
+    uint32_t xoff[kMaxSlots];   // byte offset of swz(slot s's tile-local offset): address = (swz(lb) << 4) ^ xoff[s]
 };
 static_assert(sizeof(DevRound) == 128, "DevRound layout");
 
@@ -146,8 +156,9 @@ struct DevLoads {
     uint64_t goff[kMaxLoads];  // deposit(i * threads, tile_segs): element offset in the state
     uint32_t soff[kMaxLoads];  // swz(i * threads) << 4: byte offset in the shared-memory tile
     uint32_t pad[2];
+    uint64_t store_goff[kMaxSlots];  // PASS_DIRECT_STORE: deposit(slot s's tile-local offset in the last round, tile_segs)
 };
-static_assert(sizeof(DevLoads) == 200, "DevLoads layout");
+static_assert(sizeof(DevLoads) == 328, "DevLoads layout");
 
 // The part of a pass blob the kernel receives by value (kernel-parameter constant bank): header, load constants,
 // rounds and ops.  Tables, external phase terms and Custom matrices stay in the blob in global memory.

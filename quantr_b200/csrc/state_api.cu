@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -159,8 +160,29 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     if (rc != QSV_OK) return rc;
     s->prefix_valid = false;
     if (s->timing) QSV_CUDA(s, cudaEventRecord(s->ev0, s->stream));
+    static const bool trace_passes = getenv("QSV_TRACE_PASSES") != nullptr;  // developer aid: per-pass device times on stderr
+    std::vector<cudaEvent_t> evs;
+    if (trace_passes) {
+        evs.resize(plan.passes.size() + 1);
+        for (auto& e : evs) cudaEventCreate(&e);
+        cudaEventRecord(evs[0], s->stream);
+    }
     for (size_t i = 0; i < plan.passes.size(); ++i) {
         QSV_CUDA(s, launch_pass(s->d_state, static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[i], plan.passes[i].data(), rank_base(s), s->sm_count, s->stream));
+        if (trace_passes) cudaEventRecord(evs[i + 1], s->stream);
+    }
+    if (trace_passes) {
+        cudaEventSynchronize(evs.back());
+        for (size_t i = 0; i < plan.passes.size(); ++i) {
+            const DevPass& h = *reinterpret_cast<const DevPass*>(plan.passes[i].data());
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+            int run_bits = 0;
+            if (h.n_tile_segs && h.tile_segs[0].dst_lo == 0) run_bits = h.tile_segs[0].width;
+            fprintf(stderr, "[qsv] pass %zu: T=%u run=%uB rounds=%u ops=%u diag=%u flags=%u  %.3f ms  %.0f GB/s\n", i, h.tile_bits, 16u << run_bits, h.n_rounds,
+                    h.n_ops, h.n_diag, h.flags, ms, 32.0 * (double)(1ull << s->n_alloc) / (ms * 1e-3) / 1e9);
+        }
+        for (auto& e : evs) cudaEventDestroy(e);
     }
     if (stats) {
         memset(stats, 0, sizeof(*stats));

@@ -32,12 +32,18 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
         thread_active_mask<W>(P.hdr, P.rounds, P.ops, e, act);
         memcpy(&thr_act[(size_t)e * W], act, sizeof(act));
     }
-    // the kernel stages the DIAG thread-phase tables in shared memory for small passes; exercise both paths
-    const bool use_smem_tbl = P.hdr.n_rounds <= (uint32_t)kSmallRounds && P.hdr.n_ops <= (uint32_t)kSmallOps;
-    std::vector<cplx> thr_tbl((size_t)kMaxOps * kDiagTblLen);
+    // DIAG thread phases: same placement decision as the launcher
+    const int mode = choose_diag_mode(T, P.hdr.n_diag);
+    std::vector<cplx> thr_tbl((size_t)kMaxOps * kDiagTblLen), thr_phase((size_t)kMaxOps * threads);
     for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
-        if (P.ops[o].type == OP_DIAG)
-            memcpy(&thr_tbl[(size_t)P.ops[o].diag_index * kDiagTblLen], blob + P.ops[o].tbl_off, sizeof(cplx) * kDiagTblLen);
+        if (P.ops[o].type == OP_DIAG) {
+            const cplx* src = reinterpret_cast<const cplx*>(blob + P.ops[o].tbl_off);
+            memcpy(&thr_tbl[(size_t)P.ops[o].diag_index * kDiagTblLen], src, sizeof(cplx) * kDiagTblLen);
+            for (uint32_t e = 0; e < groups; ++e) thr_phase[(size_t)P.ops[o].diag_index * threads + e] = diag_thread_phase(P.ops[o], src, e);
+        }
+    DiagCtx ctx{blob, ext_phase.data(), mode == 1 ? thr_tbl.data() : nullptr, mode == 2 ? thr_phase.data() : nullptr, threads};
+    const bool direct = (P.hdr.flags & PASS_DIRECT_STORE) != 0;
+    const double sc = P.hdr.final_scale;
     char* tb = reinterpret_cast<char*>(tile.data());
     for (uint64_t t = 0; t < P.hdr.n_tiles; ++t) {
         const uint64_t base = deposit(t, P.hdr.ext_segs, P.hdr.n_ext_segs);
@@ -57,7 +63,20 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
                     uint32_t act[W];
                     memcpy(act, &thr_act[(size_t)e * W], sizeof(act));
                     tile_active_mask<W>(P.hdr, P.ops, base_full, act);
-                    reg_round<W>(R, P.ops, blob, ext_phase.data(), use_smem_tbl ? thr_tbl.data() : nullptr, act, e, tile.data());
+                    const uint32_t lb = round_thread_base(R, e);
+                    cplx a[kSlots];
+                    round_load(R, lb, tile.data(), a);
+                    round_ops<W>(R, P.ops, ctx, act, e, a);
+                    if (direct && r + 1 == P.hdr.n_rounds) {
+                        const uint64_t g = base + deposit(lb, P.hdr.tile_segs, P.hdr.n_tile_segs);
+                        for (int s = 0; s < kSlots; ++s) {
+                            cplx v = a[s];
+                            if (sc != 1.0) { v.x *= sc; v.y *= sc; }
+                            state[g + P.loads.store_goff[s]] = v;
+                        }
+                    } else {
+                        round_store_tile(R, lb, tile.data(), a);
+                    }
                 }
             } else {
                 const DevDense* D = reinterpret_cast<const DevDense*>(blob + P.ops[R.first_op].dense_off);
@@ -73,7 +92,7 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
                 }
             }
         }
-        const double sc = P.hdr.final_scale;
+        if (direct) continue;
         for (uint32_t tid = 0; tid < threads; ++tid) {
             const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, P.hdr.n_tile_segs);
             const uint32_t soff_t = swz(tid) << 4;
