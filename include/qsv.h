@@ -183,7 +183,23 @@ int qsv_apply(qsv_state* s, const qsv_op* ops, size_t n_ops, qsv_stats* stats);
 int qsv_plan_create(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubits,
                     const qsv_op* ops, size_t n_ops, uint32_t tile_bits, uint32_t low_bits,
                     int fuse);
+/* Same, for sharded registers.  `layout[b]` = physical position of logical index bit b (bit b of the canonical
+ * amplitude index; positions >= n_local_qubits live in the rank id); NULL = identity.  With `free_layout` != 0 the
+ * scheduler chooses the initial layout itself (valid when the register is a basis state, which has no data to move):
+ * it parks the qubits that are targeted last in the rank id.  Gates that target a qubit held in the rank id make the
+ * plan insert a global-qubit remap (QSV_STEP_EXCHANGE) before them. */
+int qsv_plan_create_ex(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubits, const qsv_op* ops, size_t n_ops,
+                       uint32_t tile_bits, uint32_t low_bits, int fuse, const uint8_t* layout, int free_layout);
 int qsv_plan_destroy(qsv_plan* p);
+
+/* Plan introspection (host-side tests, sharded drivers).  Step kinds: */
+enum { QSV_STEP_PASS = 0, QSV_STEP_EXCHANGE = 1 };
+int qsv_plan_num_steps(const qsv_plan* p, size_t* n_steps);
+/* kind: QSV_STEP_*; pass_index: for PASS; partner_bits[0..n_global): for EXCHANGE, the local physical bit swapped
+ * with rank bit j (cap = capacity of partner_bits). */
+int qsv_plan_get_step(const qsv_plan* p, size_t i, int* kind, uint32_t* pass_index, uint8_t* partner_bits, size_t cap);
+/* which = 0: layout the plan starts from, 1: layout after the last step.  out_layout holds n_qubits bytes. */
+int qsv_plan_get_layout(const qsv_plan* p, int which, uint8_t* out_layout, size_t cap);
 int qsv_plan_stats(const qsv_plan* p, qsv_stats* stats);
 /* Serialised schedule (for inspection and for the host-side schedule tests):
  * writes up to `cap` bytes, returns the full size in *size. */
@@ -204,6 +220,10 @@ int qsv_sample(qsv_state* s, const double* uniforms, uint64_t shots, uint64_t* o
 
 /* sum |amp|^2 over the local state (sharded: over all ranks). */
 int qsv_norm_sqr(qsv_state* s, double* out);
+
+/* Current layout of the handle: out_layout[b] = physical position of logical index bit b (identity unless a sharded
+ * plan with remaps has run). */
+int qsv_get_layout(const qsv_state* s, uint8_t* out_layout, size_t cap);
 
 /* Blocks until all work queued on the handle's stream has finished. */
 int qsv_synchronize(qsv_state* s);

@@ -194,6 +194,11 @@ class DeviceState:
                                     out.ctypes.data_as(C.POINTER(C.c_uint64))), self.handle)
         return out
 
+    def layout(self) -> list:
+        buf = (C.c_uint8 * self.n_qubits)()
+        F.check(self.lib.qsv_get_layout(self.handle, buf, self.n_qubits), self.handle)
+        return list(buf)
+
     def norm_sqr(self) -> float:
         out = C.c_double()
         F.check(self.lib.qsv_norm_sqr(self.handle, C.byref(out)), self.handle)
@@ -206,12 +211,18 @@ class DeviceState:
 class Plan:
     """A lowered + scheduled circuit (`qsv_plan*`).  Host-only to build."""
 
-    def __init__(self, n_qubits: int, enc: EncodedOps, *, n_local: int | None = None, tile_bits: int = 0, low_bits: int = 0, fuse: bool = True):
-        self.lib = F.load_library()
+    def __init__(self, n_qubits: int, enc: EncodedOps, *, n_local: int | None = None, tile_bits: int = 0, low_bits: int = 0, fuse: bool = True,
+                 layout=None, free_layout: bool = False, lib=None):
+        self.lib = lib or F.load_library()
         self.handle = C.c_void_p()
         self.enc = enc
-        F.check_plan(self.lib.qsv_plan_create(C.byref(self.handle), n_qubits, n_qubits if n_local is None else n_local,
-                                              enc.ops, enc.n_ops, tile_bits, low_bits, 1 if fuse else 0))
+        self.n_qubits = n_qubits
+        self.n_local = n_qubits if n_local is None else n_local
+        lay = None
+        if layout is not None:
+            lay = (C.c_uint8 * n_qubits)(*[int(x) for x in layout])
+        F.check_plan(self.lib.qsv_plan_create_ex(C.byref(self.handle), n_qubits, self.n_local, enc.ops, enc.n_ops, tile_bits, low_bits,
+                                                 1 if fuse else 0, lay, 1 if free_layout else 0))
 
     def close(self):
         if getattr(self, "handle", None) and self.handle.value:
@@ -224,6 +235,25 @@ class Plan:
         s = F.QsvStats()
         F.check_plan(self.lib.qsv_plan_stats(self.handle, C.byref(s)))
         return s.as_dict()
+
+    def steps(self) -> list:
+        """[("pass", pass_index) | ("exchange", [local physical bit swapped with rank bit j, ...])]"""
+        n = C.c_size_t()
+        F.check_plan(self.lib.qsv_plan_num_steps(self.handle, C.byref(n)))
+        g = self.n_qubits - self.n_local
+        out = []
+        for i in range(n.value):
+            kind, pidx = C.c_int(), C.c_uint32()
+            partners = (C.c_uint8 * 8)()
+            F.check_plan(self.lib.qsv_plan_get_step(self.handle, i, C.byref(kind), C.byref(pidx), partners, 8))
+            out.append(("pass", pidx.value) if kind.value == 0 else ("exchange", [partners[j] for j in range(g)]))
+        return out
+
+    def layout(self, final: bool = False) -> list:
+        """layout[b] = physical position of logical index bit b, before the first / after the last step."""
+        buf = (C.c_uint8 * self.n_qubits)()
+        F.check_plan(self.lib.qsv_plan_get_layout(self.handle, 1 if final else 0, buf, self.n_qubits))
+        return list(buf)
 
     def describe(self) -> dict:
         import json

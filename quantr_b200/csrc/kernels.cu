@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) sample_shots_kernel(const cplx* __restric
     for (uint64_t s = warp_global; s < shots; s += n_warps) {
         const double u = uniforms[s];
         uint64_t result = UINT64_MAX;
-        if (u < prefix[n_blocks]) {
+        if (u >= 0.0 && u < prefix[n_blocks]) {  // negative: a shot that belongs to a lower rank of a sharded register
             // largest b with prefix[b] <= u  (prefix is non-decreasing, prefix[0] = 0 <= u)
             uint64_t lo = 0, hi = n_blocks;  // invariant: prefix[lo] <= u, (hi == n_blocks or prefix[hi] > u)
             while (hi - lo > 1) {

@@ -234,7 +234,7 @@ cplx unit_phase(double half_turns) {
     return r;
 }
 
-void emit_pass(Plan& plan, const PassB& pb) {
+void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
     const int T = std::min<int>(plan.opt.tile_bits, (int)plan.n_alloc);
     const int nloc = (int)plan.n_alloc;
     // tile bits = required bits + lowest free bits
@@ -285,7 +285,7 @@ void emit_pass(Plan& plan, const PassB& pb) {
         if (rb.dense) {
             dr.type = ROUND_DENSE;
             dr.n_ops = 1;
-            const LOp& lop = plan.lops[rb.ops[0]];
+            const LOp& lop = lops[rb.ops[0]];
             DevOp dop;
             memset(&dop, 0, sizeof(dop));
             dop.type = OP_DENSE;
@@ -348,7 +348,7 @@ void emit_pass(Plan& plan, const PassB& pb) {
             }
         };
         for (size_t oi : rb.ops) {
-            const LOp& lop = plan.lops[oi];
+            const LOp& lop = lops[oi];
             DevOp d;
             memset(&d, 0, sizeof(d));
             split_cmask(lop.cmask, d);
@@ -456,7 +456,23 @@ void emit_pass(Plan& plan, const PassB& pb) {
 
 }  // namespace
 
-void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* ops, size_t n_ops, const PlanOptions& opt_in) {
+// Maps a lowered op from logical to physical bit space.
+static LOp remap_lop(const LOp& in, const std::vector<uint8_t>& layout) {
+    LOp o = in;
+    auto mask = [&](uint64_t m) {
+        uint64_t r = 0;
+        for (int b = 0; b < 64; ++b) if ((m >> b) & 1) r |= 1ull << layout[b];
+        return r;
+    };
+    o.cmask = mask(in.cmask);
+    if (in.kind == LOp::MAT) o.target = layout[in.target];
+    for (auto& t : o.lin) t.first = layout[t.first];
+    for (auto& b : o.bits) b = layout[b];
+    return o;
+}
+
+void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* ops, size_t n_ops, const PlanOptions& opt_in,
+                const uint8_t* initial_layout, bool free_layout) {
     if (n_local == 0 || n_local > n_qubits) fail("n_local_qubits must be in 1..n_qubits");
     plan.n_qubits = n_qubits;
     plan.n_local = n_local;
@@ -464,6 +480,7 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
     plan.opt = opt_in;
     plan.opt.tile_bits = std::max<int>(kRegBits, std::min<int>(opt_in.tile_bits, kMaxTileBits));
     plan.passes.clear();
+    plan.steps.clear();
     plan.lops.clear();
     plan.n_rounds = 0;
     lower_gates(n_qubits, ops, n_ops, plan.lops, &plan.n_gates);
@@ -471,15 +488,49 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
 
     const int nloc = (int)plan.n_alloc;
     const int T = std::min<int>(plan.opt.tile_bits, nloc);
-    const uint64_t local_mask = (nloc >= 64) ? ~0ull : ((1ull << n_local) - 1);
-    for (const LOp& lop : plan.lops) {
-        const uint64_t tg = lop.targets();
-        if (tg & ~local_mask) fail("gate " + std::to_string(lop.src_gate) + " targets a qubit held across ranks; global-qubit remap is required");
-        if (lop.kind == LOp::DENSE && popcnt(tg) > T) fail("Custom gate is wider than the tile (" + std::to_string(T) + " bits)");
-    }
+    const int n = (int)n_qubits, g = n - (int)n_local;
+    for (const LOp& lop : plan.lops)
+        if (lop.kind == LOp::DENSE && popcnt(lop.targets()) > T) fail("Custom gate is wider than the tile (" + std::to_string(T) + " bits)");
 
-    // Greedy in-order grouping of the lowered ops into passes for a given number of low passenger bits.
-    auto schedule = [&](int L, std::vector<PassB>& out) {
+    // ---- layout: physical position of every logical index bit ------------------------------------------------
+    const size_t n_lops = plan.lops.size();
+    auto next_target_use = [&](int bit, size_t from) {  // first op >= from that needs `bit` as a tile bit
+        for (size_t i = from; i < n_lops; ++i)
+            if ((plan.lops[i].targets() >> bit) & 1) return i;
+        return n_lops;
+    };
+    std::vector<uint8_t> layout(64);
+    for (int b = 0; b < 64; ++b) layout[b] = (uint8_t)b;
+    plan.free_initial_layout = false;
+    if (initial_layout) {
+        for (int b = 0; b < n; ++b) layout[b] = initial_layout[b];
+    } else if (free_layout && g > 0) {
+        // the g logical bits whose first use as a target comes last go to the rank id; the rest keep their order
+        std::vector<std::pair<size_t, int>> first_use;
+        for (int b = 0; b < n; ++b) first_use.push_back({next_target_use(b, 0), b});
+        std::stable_sort(first_use.begin(), first_use.end(), [](const std::pair<size_t, int>& x, const std::pair<size_t, int>& y) { return x.first > y.first; });
+        std::vector<int> global_bits;
+        for (int j = 0; j < g; ++j) global_bits.push_back(first_use[j].second);
+        std::sort(global_bits.begin(), global_bits.end());
+        int next_local = 0;
+        for (int b = 0; b < n; ++b) {
+            auto it = std::find(global_bits.begin(), global_bits.end(), b);
+            if (it == global_bits.end()) layout[b] = (uint8_t)next_local++;
+            else layout[b] = (uint8_t)(n_local + (it - global_bits.begin()));
+        }
+        plan.free_initial_layout = true;
+    }
+    {  // validate: a permutation of 0..n-1
+        uint64_t seen = 0;
+        for (int b = 0; b < n; ++b) {
+            if (layout[b] >= n || ((seen >> layout[b]) & 1)) fail("initial layout is not a permutation of the index bits");
+            seen |= 1ull << layout[b];
+        }
+    }
+    plan.initial_layout.assign(layout.begin(), layout.begin() + n);
+
+    // Greedy in-order grouping of (physical-space) ops into passes for a given number of low passenger bits.
+    auto schedule = [&](const std::vector<LOp>& lops, int L, std::vector<PassB>& out) {
         out.clear();
         const uint64_t low_mask = (T == nloc) ? 0 : ((1ull << L) - 1);  // single-tile states: every bit is a tile bit
         PassB cur;
@@ -487,8 +538,8 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
             if (!cur.empty()) out.push_back(std::move(cur));
             cur = PassB();
         };
-        for (size_t i = 0; i < plan.lops.size(); ++i) {
-            const LOp& lop = plan.lops[i];
+        for (size_t i = 0; i < lops.size(); ++i) {
+            const LOp& lop = lops[i];
             const uint64_t tg = lop.targets();
             if (!plan.opt.fuse) close_pass();
             // Can the op join the open pass?  Its targets must fit next to the pass's tile bits and the
@@ -541,25 +592,81 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
         return total;
     };
 
-    std::vector<PassB> best;
-    if (plan.opt.low_bits > 0 || T == nloc || !plan.opt.fuse) {
-        const int L = std::max(0, std::min<int>(plan.opt.low_bits > 0 ? plan.opt.low_bits : 3, T - 1));
-        plan.opt.low_bits = L;
-        schedule(L, best);
-    } else {
-        // low_bits = 0: pick the number of passenger bits that minimises the modelled cost (longer runs stream
-        // better, fewer passenger bits fuse more gates per pass); ties go to the longer runs.
-        double best_cost = 0;
-        int best_L = 3;
-        std::vector<PassB> cand;
-        for (int L = std::min(8, T - 1); L >= 3; --L) {
-            schedule(L, cand);
-            const double c = plan_cost(cand);
-            if (best.empty() || c < best_cost - 1e-9) { best_cost = c; best_L = L; best.swap(cand); }
+    // Schedules one segment (ops whose targets are all local under the current layout) and emits its passes.
+    int chosen_L = plan.opt.low_bits;
+    auto emit_segment = [&](size_t i0, size_t i1) {
+        if (i0 == i1) return;
+        std::vector<LOp> seg;
+        seg.reserve(i1 - i0);
+        for (size_t i = i0; i < i1; ++i) seg.push_back(remap_lop(plan.lops[i], layout));
+        std::vector<PassB> best;
+        if (plan.opt.low_bits > 0 || T == nloc || !plan.opt.fuse) {
+            const int L = std::max(0, std::min<int>(plan.opt.low_bits > 0 ? plan.opt.low_bits : 3, T - 1));
+            chosen_L = L;
+            schedule(seg, L, best);
+        } else {
+            // low_bits = 0: pick the number of passenger bits that minimises the modelled cost (longer runs stream
+            // better, fewer passenger bits fuse more gates per pass); ties go to the longer runs.
+            double best_cost = 0;
+            std::vector<PassB> cand;
+            for (int L = std::min(8, T - 1); L >= 3; --L) {
+                schedule(seg, L, cand);
+                const double c = plan_cost(cand);
+                if (best.empty() || c < best_cost - 1e-9) { best_cost = c; chosen_L = L; best.swap(cand); }
+            }
         }
-        plan.opt.low_bits = best_L;
+        for (const PassB& pb : best) {
+            emit_pass(plan, pb, seg);
+            PlanStep st;
+            st.kind = PlanStep::PASS;
+            st.pass_index = (uint32_t)plan.passes.size() - 1;
+            plan.steps.push_back(std::move(st));
+        }
+    };
+
+    size_t seg_start = 0;
+    for (size_t i = 0; i < n_lops; ++i) {
+        bool needs_global = false;
+        const uint64_t tg = plan.lops[i].targets();
+        for (int b = 0; b < n; ++b)
+            if (((tg >> b) & 1) && layout[b] >= n_local) needs_global = true;
+        if (!needs_global) continue;
+        if (g == 0) fail("internal: global target without ranks");
+        emit_segment(seg_start, i);
+        seg_start = i;
+        // Global-qubit remap: all g rank bits are swapped with the g local physical bits whose logical bits are
+        // needed as targets furthest in the future (Belady), preferring high positions so the exchanged chunks are large.
+        std::vector<int> logical_at(n, -1);
+        for (int b = 0; b < n; ++b) logical_at[layout[b]] = b;
+        const int min_partner = std::max(0, (int)n_local - 10);
+        std::vector<std::pair<size_t, int>> cand;  // (next use, physical position)
+        for (int p = min_partner; p < (int)n_local; ++p) {
+            const int lb = logical_at[p];
+            if ((tg >> lb) & 1) continue;  // needed right now
+            cand.push_back({next_target_use(lb, i), p});
+        }
+        if ((int)cand.size() < g) fail("gate " + std::to_string(plan.lops[i].src_gate) + ": cannot bring its qubits onto one rank");
+        std::stable_sort(cand.begin(), cand.end(), [](const std::pair<size_t, int>& x, const std::pair<size_t, int>& y) {
+            return x.first != y.first ? x.first > y.first : x.second > y.second;
+        });
+        std::vector<int> partners;
+        for (int j = 0; j < g; ++j) partners.push_back(cand[j].second);
+        std::sort(partners.begin(), partners.end());
+        PlanStep st;
+        st.kind = PlanStep::EXCHANGE;
+        for (int j = 0; j < g; ++j) {
+            st.partner_bits.push_back((uint8_t)partners[j]);
+            const int lg = logical_at[n_local + j], ll = logical_at[partners[j]];
+            std::swap(layout[lg], layout[ll]);
+        }
+        plan.steps.push_back(std::move(st));
+        // the op must be local now
+        for (int b = 0; b < n; ++b)
+            if (((tg >> b) & 1) && layout[b] >= n_local) fail("gate " + std::to_string(plan.lops[i].src_gate) + " needs more qubits on one rank than a remap provides");
     }
-    for (const PassB& pb : best) emit_pass(plan, pb);
+    emit_segment(seg_start, n_lops);
+    plan.opt.low_bits = chosen_L;
+    plan.final_layout.assign(layout.begin(), layout.begin() + n);
 }
 
 std::string describe_plan(const Plan& plan) {

@@ -43,13 +43,25 @@ struct PlanOptions {
     int l2_prefetch = 0;  // prefetch the CTA's next tile into L2 while the current one is processed
 };
 
+// One step of a plan: a fused pass over the local shard, or a global-qubit remap that swaps the index bits held in
+// the rank id with `n_global` local physical bits (pairwise amplitude exchange between ranks).
+struct PlanStep {
+    enum Kind { PASS = 0, EXCHANGE = 1 } kind = PASS;
+    uint32_t pass_index = 0;             // PASS: index into Plan::passes
+    std::vector<uint8_t> partner_bits;   // EXCHANGE: local physical bit swapped with rank bit j, ascending
+};
+
 struct Plan {
     uint32_t n_qubits = 0;        // logical qubits of the circuit
     uint32_t n_local = 0;         // logical index bits held by this rank
     uint32_t n_alloc = 0;         // allocated local bits (>= kMinQubits)
     PlanOptions opt;
-    std::vector<LOp> lops;                        // after lowering + diagonal merging
-    std::vector<std::vector<uint8_t>> passes;     // device blobs
+    std::vector<LOp> lops;                        // after lowering + diagonal merging, in LOGICAL bit space (bit = n-1-wire)
+    std::vector<std::vector<uint8_t>> passes;     // device blobs (physical bit space)
+    std::vector<PlanStep> steps;                  // execution order
+    // layout[b] = physical position of logical index bit b (positions >= n_local live in the rank id)
+    std::vector<uint8_t> initial_layout, final_layout;
+    bool free_initial_layout = false;             // the scheduler chose initial_layout (register must be a basis state)
     uint64_t n_gates = 0, n_rounds = 0;
     // device residency (owned by the state API)
     void* dev_blob = nullptr;
@@ -60,7 +72,9 @@ struct Plan {
 // Throws std::runtime_error with a message on invalid input / unsupported circuits.
 void lower_gates(uint32_t n_qubits, const qsv_op* ops, size_t n_ops, std::vector<LOp>& out, uint64_t* n_gates);
 void merge_diagonals(std::vector<LOp>& lops);
-void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* ops, size_t n_ops, const PlanOptions& opt);
+// initial_layout: nullptr = identity; free_layout: let the scheduler choose the initial layout (sharded basis states).
+void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* ops, size_t n_ops, const PlanOptions& opt,
+                const uint8_t* initial_layout = nullptr, bool free_layout = false);
 std::string describe_plan(const Plan& plan);
 
 void host_sincospi(double x, double* s, double* c);

@@ -15,6 +15,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -48,6 +49,7 @@ bool load_nccl(std::string& err) {
     QSV_SYM(CommInitRank, "ncclCommInitRank");
     QSV_SYM(CommDestroy, "ncclCommDestroy");
     QSV_SYM(AllReduce, "ncclAllReduce");
+    QSV_SYM(AllGather, "ncclAllGather");
     QSV_SYM(Send, "ncclSend");
     QSV_SYM(Recv, "ncclRecv");
     QSV_SYM(GroupStart, "ncclGroupStart");
@@ -70,7 +72,7 @@ struct ShardComm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     cudaStream_t stream = nullptr;
-    double* d_scalar = nullptr;
+    double* d_scalar = nullptr;  // 1 + world doubles
 };
 
 bool shard_unique_id(void* out, size_t out_bytes, std::string& err) {
@@ -92,7 +94,7 @@ ShardComm* shard_comm_create(int rank, int world, const void* unique_id, size_t 
     c->world = world;
     c->stream = stream;
     if (!nccl_ok(g_nccl.CommInitRank(&c->comm, world, id, rank), "ncclCommInitRank", err)) { delete c; return nullptr; }
-    if (cudaMalloc(&c->d_scalar, sizeof(double)) != cudaSuccess) { err = "cudaMalloc failed"; g_nccl.CommDestroy(c->comm); delete c; return nullptr; }
+    if (cudaMalloc(&c->d_scalar, sizeof(double) * (size_t)(1 + world)) != cudaSuccess) { err = "cudaMalloc failed"; g_nccl.CommDestroy(c->comm); delete c; return nullptr; }
     return c;
 }
 
@@ -109,6 +111,66 @@ bool shard_allreduce_sum(ShardComm* c, double* value, std::string& err) {
     if (cudaMemcpyAsync(value, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
         err = "all-reduce of a scalar failed";
         return false;
+    }
+    return true;
+}
+
+bool shard_allreduce_sum_f64(ShardComm* c, double* d_buf, size_t count, std::string& err) {
+    return nccl_ok(g_nccl.AllReduce(d_buf, d_buf, count, ncclFloat64, ncclSum, c->comm, c->stream), "ncclAllReduce", err);
+}
+
+bool shard_allreduce_min_u64(ShardComm* c, uint64_t* d_buf, size_t count, std::string& err) {
+    return nccl_ok(g_nccl.AllReduce(d_buf, d_buf, count, ncclUint64, ncclMin, c->comm, c->stream), "ncclAllReduce", err);
+}
+
+bool shard_allgather_f64(ShardComm* c, double value, double* out, std::string& err) {
+    if (cudaMemcpyAsync(c->d_scalar, &value, sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { err = "cudaMemcpyAsync failed"; return false; }
+    if (!nccl_ok(g_nccl.AllGather(c->d_scalar, c->d_scalar + 1, 1, ncclFloat64, c->comm, c->stream), "ncclAllGather", err)) return false;
+    if (cudaMemcpyAsync(out, c->d_scalar + 1, sizeof(double) * (size_t)c->world, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        err = "all-gather of a scalar failed";
+        return false;
+    }
+    return true;
+}
+
+bool shard_exchange_bits(ShardComm* c, void* base, uint32_t n_local, const uint8_t* partner, uint32_t g, void* staging, size_t staging_bytes,
+                         std::string& err) {
+    if ((1 << g) != c->world) { err = "exchange: partner count does not match the communicator"; return false; }
+    char* b = static_cast<char*>(base);
+    char* stage[2] = {static_cast<char*>(staging), static_cast<char*>(staging) + staging_bytes};
+    const uint64_t amp = 16;
+    const uint64_t run = (uint64_t)1 << partner[0];             // contiguous amplitudes below the lowest partner bit
+    uint64_t partner_mask = 0;
+    for (uint32_t j = 0; j < g; ++j) partner_mask |= (uint64_t)1 << partner[j];
+    const uint64_t n_runs = ((uint64_t)1 << n_local) >> (partner[0] + g);  // runs per peer block
+    int slot = 0;
+    // Round-robin pairing (peer = rank ^ step): every step is a perfect matching over NVSwitch.
+    for (int step = 1; step < c->world; ++step) {
+        const int peer = c->rank ^ step;
+        uint64_t peer_bits = 0;  // the block whose partner bits spell `peer`
+        for (uint32_t j = 0; j < g; ++j) if ((peer >> j) & 1) peer_bits |= (uint64_t)1 << partner[j];
+        for (uint64_t r = 0; r < n_runs; ++r) {
+            // r enumerates the index bits above partner[0] that are not partner bits
+            uint64_t idx = 0, rest = r;
+            for (uint32_t bit = partner[0]; bit < n_local; ++bit) {
+                if ((partner_mask >> bit) & 1) continue;
+                idx |= (rest & 1) << bit;
+                rest >>= 1;
+            }
+            char* chunk = b + (idx | peer_bits) * amp;
+            const uint64_t bytes = run * amp;
+            for (uint64_t off = 0; off < bytes; off += staging_bytes) {
+                const size_t len = (size_t)(bytes - off < staging_bytes ? bytes - off : staging_bytes);
+                char* st = stage[slot];
+                slot ^= 1;
+                if (!nccl_ok(g_nccl.GroupStart(), "ncclGroupStart", err)) return false;
+                if (!nccl_ok(g_nccl.Send(chunk + off, len, ncclUint8, peer, c->comm, c->stream), "ncclSend", err)) return false;
+                if (!nccl_ok(g_nccl.Recv(st, len, ncclUint8, peer, c->comm, c->stream), "ncclRecv", err)) return false;
+                if (!nccl_ok(g_nccl.GroupEnd(), "ncclGroupEnd", err)) return false;
+                if (cudaMemcpyAsync(chunk + off, st, len, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { err = "staging copy failed"; return false; }
+            }
+        }
     }
     return true;
 }

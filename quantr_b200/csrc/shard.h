@@ -18,6 +18,15 @@ bool shard_unique_id(void* out, size_t out_bytes, std::string& err);
 ShardComm* shard_comm_create(int rank, int world, const void* unique_id, size_t unique_id_bytes, cudaStream_t stream, std::string& err);
 void shard_comm_destroy(ShardComm* c);
 bool shard_allreduce_sum(ShardComm* c, double* value, std::string& err);
+// device buffers, enqueued on the comm's stream
+bool shard_allreduce_sum_f64(ShardComm* c, double* d_buf, size_t count, std::string& err);
+bool shard_allreduce_min_u64(ShardComm* c, uint64_t* d_buf, size_t count, std::string& err);
+// host in/out: out[r] = rank r's value (synchronises the stream)
+bool shard_allgather_f64(ShardComm* c, double value, double* out, std::string& err);
+// Global-qubit remap on a shard of 2^n_local 16-byte amplitudes at `base`: rank bit j <-> local bit partner[j]
+// (ascending).  Staged through two buffers of `staging_bytes` each.  Enqueued on the comm's stream.
+bool shard_exchange_bits(ShardComm* c, void* base, uint32_t n_local, const uint8_t* partner, uint32_t g, void* staging, size_t staging_bytes,
+                         std::string& err);
 // In-place pairwise exchange: for every peer p != rank, the `slot_bytes` at `base + p*slot_bytes` are swapped with
 // the peer's slot `rank`.  Staged through `staging` (>= chunk_bytes) in chunks.  Enqueued on the comm's stream.
 bool shard_exchange_slots(ShardComm* c, void* base, size_t slot_bytes, void* staging, size_t chunk_bytes, std::string& err);

@@ -41,6 +41,15 @@ struct qsv_state {
     double total_prob = 0.0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ShardComm* comm = nullptr;
+    // layout[b] = physical position of logical index bit b (positions >= n_local live in the rank id)
+    uint8_t layout[64];
+    bool layout_identity = true;
+    // a freshly initialised register is a basis state that has not been written to HBM yet: the next plan may pick
+    // its own initial layout (nothing to move) and the memset is issued just before the first pass
+    bool lazy_basis = false;
+    uint64_t lazy_index = 0;
+    void* d_staging = nullptr;  // exchange staging (sharded handles)
+    size_t staging_bytes = 0;
     std::string error;
 };
 
@@ -71,6 +80,39 @@ int set_error(qsv_state* s, int code, const char* fmt, ...) {
 
 uint64_t local_len(const qsv_state* s) { return 1ull << s->n_local; }
 uint64_t rank_base(const qsv_state* s) { return (uint64_t)s->rank << s->n_local; }
+
+// canonical (logical) index -> physical index (rank bits on top) under the handle's layout, and back
+uint64_t to_physical(const qsv_state* s, uint64_t logical) {
+    if (s->layout_identity) return logical;
+    uint64_t p = 0;
+    for (uint32_t b = 0; b < s->n_qubits; ++b) p |= ((logical >> b) & 1ull) << s->layout[b];
+    return p;
+}
+uint64_t to_logical(const qsv_state* s, uint64_t physical) {
+    if (s->layout_identity) return physical;
+    uint64_t l = 0;
+    for (uint32_t b = 0; b < s->n_qubits; ++b) l |= ((physical >> s->layout[b]) & 1ull) << b;
+    return l;
+}
+void set_layout(qsv_state* s, const uint8_t* layout) {
+    s->layout_identity = true;
+    for (uint32_t b = 0; b < s->n_qubits; ++b) {
+        s->layout[b] = layout ? layout[b] : (uint8_t)b;
+        if (s->layout[b] != b) s->layout_identity = false;
+    }
+}
+
+// Writes a pending basis state to HBM (under the current layout).
+int materialize(qsv_state* s) {
+    if (!s->lazy_basis) return QSV_OK;
+    s->lazy_basis = false;
+    QSV_CUDA(s, cudaMemsetAsync(s->d_state, 0, sizeof(cplx) << s->n_alloc, s->stream));
+    const uint64_t phys = to_physical(s, s->lazy_index);
+    if ((phys >> s->n_local) == (uint64_t)s->rank)
+        QSV_CUDA(s, launch_set_amp(s->d_state, phys & (local_len(s) - 1), 1.0, 0.0, s->stream));
+    s->prefix_valid = false;
+    return QSV_OK;
+}
 
 int create_common(qsv_state** out, uint32_t n_qubits, int device, int rank, int world) {
     if (!out) return set_error(nullptr, QSV_ERR_INVALID_ARG, "out is NULL");
@@ -114,6 +156,7 @@ int create_common(qsv_state** out, uint32_t n_qubits, int device, int rank, int 
     }
     cudaEventCreate(&s->ev0);
     cudaEventCreate(&s->ev1);
+    set_layout(s, nullptr);
     *out = s;
     return QSV_OK;
 }
@@ -152,38 +195,88 @@ int upload_plan(qsv_state* s, qsv_plan* p) {
     return QSV_OK;
 }
 
+// Global-qubit remap: rank bit j <-> local physical bit partner[j] (ascending).  The amplitudes whose partner bits
+// spell peer rank v go to rank v and land where the partner bits spell this rank; the block that spells this rank
+// stays.  Contiguous chunks of 2^partner[0] amplitudes, staged through a bounded buffer, grouped ncclSend/ncclRecv.
+int run_exchange(qsv_state* s, const PlanStep& st, double* ms_out) {
+    if (!s->comm) return set_error(s, QSV_ERR_INTERNAL, "exchange step on an unsharded handle");
+    const uint32_t g = s->n_qubits - s->n_local;
+    if (st.partner_bits.size() != g) return set_error(s, QSV_ERR_INTERNAL, "exchange step does not match the handle");
+    if (!s->d_staging) {
+        size_t want = (size_t)1 << 30;  // 1 GiB per direction, double-buffered below
+        const size_t shard = sizeof(cplx) << s->n_local;
+        if (want > shard / 4) want = shard / 4 ? shard / 4 : sizeof(cplx);
+        if (const char* env = getenv("QSV_STAGING_BYTES")) want = (size_t)atoll(env);
+        QSV_CUDA(s, cudaMalloc(&s->d_staging, want * 2));
+        s->staging_bytes = want;
+    }
+    if (s->timing) QSV_CUDA(s, cudaEventRecord(s->ev0, s->stream));
+    std::string err;
+    if (!shard_exchange_bits(s->comm, s->d_state, s->n_local, st.partner_bits.data(), g, s->d_staging, s->staging_bytes, err))
+        return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
+    if (s->timing) {
+        QSV_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+        QSV_CUDA(s, cudaEventSynchronize(s->ev1));
+        float ms = 0.f;
+        QSV_CUDA(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        if (ms_out) *ms_out += ms;
+    }
+    return QSV_OK;
+}
+
 int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     Plan& plan = p->plan;
     if (plan.n_qubits != s->n_qubits || plan.n_local != s->n_local)
         return set_error(s, QSV_ERR_INVALID_ARG, "plan was made for %u/%u qubits, the handle holds %u/%u", plan.n_qubits, plan.n_local, s->n_qubits, s->n_local);
-    int rc = upload_plan(s, p);
+    // layout handshake: a pending basis state adopts the plan's initial layout (nothing to move); otherwise they must agree
+    if (s->lazy_basis) {
+        set_layout(s, plan.initial_layout.data());
+    } else if (memcmp(s->layout, plan.initial_layout.data(), s->n_qubits) != 0) {
+        return set_error(s, QSV_ERR_INVALID_ARG, "the plan starts from a different qubit layout than the register is in");
+    }
+    int rc = materialize(s);
+    if (rc != QSV_OK) return rc;
+    rc = upload_plan(s, p);
     if (rc != QSV_OK) return rc;
     s->prefix_valid = false;
-    if (s->timing) QSV_CUDA(s, cudaEventRecord(s->ev0, s->stream));
-    static const bool trace_passes = getenv("QSV_TRACE_PASSES") != nullptr;  // developer aid: per-pass device times on stderr
-    std::vector<cudaEvent_t> evs;
-    if (trace_passes) {
-        evs.resize(plan.passes.size() + 1);
-        for (auto& e : evs) cudaEventCreate(&e);
-        cudaEventRecord(evs[0], s->stream);
-    }
-    for (size_t i = 0; i < plan.passes.size(); ++i) {
-        QSV_CUDA(s, launch_pass(s->d_state, static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[i], plan.passes[i].data(), rank_base(s), s->sm_count, s->stream));
-        if (trace_passes) cudaEventRecord(evs[i + 1], s->stream);
-    }
-    if (trace_passes) {
-        cudaEventSynchronize(evs.back());
-        for (size_t i = 0; i < plan.passes.size(); ++i) {
-            const DevPass& h = *reinterpret_cast<const DevPass*>(plan.passes[i].data());
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
-            int run_bits = 0;
-            if (h.n_tile_segs && h.tile_segs[0].dst_lo == 0) run_bits = h.tile_segs[0].width;
-            fprintf(stderr, "[qsv] pass %zu: T=%u run=%uB rounds=%u ops=%u diag=%u flags=%u  %.3f ms  %.0f GB/s\n", i, h.tile_bits, 16u << run_bits, h.n_rounds,
-                    h.n_ops, h.n_diag, h.flags, ms, 32.0 * (double)(1ull << s->n_alloc) / (ms * 1e-3) / 1e9);
+    static const bool trace_passes = getenv("QSV_TRACE_PASSES") != nullptr;  // developer aid: per-step device times on stderr
+    double pass_ms = 0.0, exch_ms = 0.0;
+    uint64_t n_exch = 0;
+    for (size_t i = 0; i < plan.steps.size(); ++i) {
+        const PlanStep& st = plan.steps[i];
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        const bool timed = (s->timing || trace_passes) && st.kind == PlanStep::PASS;
+        if (timed) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, s->stream);
         }
-        for (auto& e : evs) cudaEventDestroy(e);
+        if (st.kind == PlanStep::PASS) {
+            QSV_CUDA(s, launch_pass(s->d_state, static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[st.pass_index], plan.passes[st.pass_index].data(),
+                                    rank_base(s), s->sm_count, s->stream));
+        } else {
+            rc = run_exchange(s, st, &exch_ms);
+            if (rc != QSV_OK) return rc;
+            ++n_exch;
+        }
+        if (timed) {
+            cudaEventRecord(e1, s->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            pass_ms += ms;
+            if (trace_passes) {
+                const DevPass& h = *reinterpret_cast<const DevPass*>(plan.passes[st.pass_index].data());
+                int run_bits = 0;
+                if (h.n_tile_segs && h.tile_segs[0].dst_lo == 0) run_bits = h.tile_segs[0].width;
+                fprintf(stderr, "[qsv] pass %u: T=%u run=%uB rounds=%u ops=%u diag=%u flags=%u  %.3f ms  %.0f GB/s\n", st.pass_index, h.tile_bits, 16u << run_bits,
+                        h.n_rounds, h.n_ops, h.n_diag, h.flags, ms, 32.0 * (double)(1ull << s->n_alloc) / (ms * 1e-3) / 1e9);
+            }
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
     }
+    set_layout(s, plan.final_layout.data());
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->n_gates = plan.n_gates;
@@ -191,13 +284,11 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
         stats->n_rounds = plan.n_rounds;
         stats->n_kernel_launches = plan.passes.size();
         stats->bytes_per_pass = 32ull << s->n_alloc;
-    }
-    if (s->timing) {
-        QSV_CUDA(s, cudaEventRecord(s->ev1, s->stream));
-        QSV_CUDA(s, cudaEventSynchronize(s->ev1));
-        float ms = 0.f;
-        QSV_CUDA(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-        if (stats) stats->device_ms = ms;
+        stats->n_exchanges = n_exch;
+        const uint32_t g = s->n_qubits - s->n_local;
+        stats->exchange_bytes = n_exch * (((16ull << s->n_local) >> g) * ((1ull << g) - 1));
+        stats->device_ms = pass_ms;
+        stats->exchange_ms = exch_ms;
     }
     return QSV_OK;
 }
@@ -267,6 +358,7 @@ int qsv_destroy(qsv_state* s) {
     if (s->d_state) cudaFree(s->d_state);
     if (s->d_sums) cudaFree(s->d_sums);
     if (s->d_prefix) cudaFree(s->d_prefix);
+    if (s->d_staging) cudaFree(s->d_staging);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -314,9 +406,10 @@ int qsv_get_info(const qsv_state* s, const char* key, int64_t* value) {
 int qsv_init_basis(qsv_state* s, uint64_t index) {
     QSV_ENTER(s);
     if (index >> s->n_qubits) return set_error(s, QSV_ERR_INVALID_ARG, "basis index out of range");
-    QSV_CUDA(s, cudaMemsetAsync(s->d_state, 0, sizeof(cplx) << s->n_alloc, s->stream));
-    if ((index >> s->n_local) == (uint64_t)s->rank)
-        QSV_CUDA(s, launch_set_amp(s->d_state, index & (local_len(s) - 1), 1.0, 0.0, s->stream));
+    // lazy: written to HBM right before the first pass (or first read), so a sharded plan can still pick its layout
+    s->lazy_basis = true;
+    s->lazy_index = index;
+    set_layout(s, nullptr);
     s->prefix_valid = false;
     return QSV_OK;
 }
@@ -325,6 +418,8 @@ int qsv_upload(qsv_state* s, const double* host_amps, uint64_t first, uint64_t c
     QSV_ENTER(s);
     if (!host_amps && count) return set_error(s, QSV_ERR_INVALID_ARG, "host_amps is NULL");
     if (first < rank_base(s) || first - rank_base(s) + count > local_len(s)) return set_error(s, QSV_ERR_INVALID_ARG, "range is outside this rank's shard");
+    if (!s->lazy_basis && !s->layout_identity) return set_error(s, QSV_ERR_UNSUPPORTED, "the register is in a remapped qubit layout: re-initialise it before uploading ranges");
+    { int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
     QSV_CUDA(s, cudaMemcpyAsync(s->d_state + (first - rank_base(s)), host_amps, sizeof(cplx) * count, cudaMemcpyHostToDevice, s->stream));
     QSV_CUDA(s, cudaStreamSynchronize(s->stream));
     s->prefix_valid = false;
@@ -335,6 +430,8 @@ int qsv_download(qsv_state* s, double* host_amps, uint64_t first, uint64_t count
     QSV_ENTER(s);
     if (!host_amps && count) return set_error(s, QSV_ERR_INVALID_ARG, "host_amps is NULL");
     if (first < rank_base(s) || first - rank_base(s) + count > local_len(s)) return set_error(s, QSV_ERR_INVALID_ARG, "range is outside this rank's shard");
+    { int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
+    if (!s->layout_identity) return set_error(s, QSV_ERR_UNSUPPORTED, "the register is in a remapped qubit layout (see qsv_get_layout): use qsv_gather");
     QSV_CUDA(s, cudaMemcpyAsync(host_amps, s->d_state + (first - rank_base(s)), sizeof(cplx) * count, cudaMemcpyDeviceToHost, s->stream));
     QSV_CUDA(s, cudaStreamSynchronize(s->stream));
     return QSV_OK;
@@ -344,11 +441,18 @@ int qsv_gather(qsv_state* s, const uint64_t* indices, uint64_t count, double* ho
     QSV_ENTER(s);
     if (count == 0) return QSV_OK;
     if (!indices || !host_amps) return set_error(s, QSV_ERR_INVALID_ARG, "NULL argument");
+    { int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
     try {
+        // canonical index -> (rank, local) under the current layout; entries held by other ranks come back as 0 here
+        // and are filled in by the sum over ranks below (collective on sharded handles)
         std::vector<uint64_t> local(count);
+        std::vector<uint8_t> mine(count);
         for (uint64_t i = 0; i < count; ++i) {
-            if (indices[i] < rank_base(s) || indices[i] - rank_base(s) >= local_len(s)) return set_error(s, QSV_ERR_INVALID_ARG, "index %llu is outside this rank's shard", (unsigned long long)indices[i]);
-            local[i] = indices[i] - rank_base(s);
+            if (indices[i] >> s->n_qubits) return set_error(s, QSV_ERR_INVALID_ARG, "index %llu out of range", (unsigned long long)indices[i]);
+            const uint64_t phys = to_physical(s, indices[i]);
+            mine[i] = (phys >> s->n_local) == (uint64_t)s->rank;
+            if (!mine[i] && !s->comm) return set_error(s, QSV_ERR_INVALID_ARG, "index %llu is outside this rank's shard", (unsigned long long)indices[i]);
+            local[i] = mine[i] ? (phys & (local_len(s) - 1)) : 0;
         }
         uint64_t* d_idx = nullptr;
         cplx* d_out = nullptr;
@@ -361,6 +465,16 @@ int qsv_gather(qsv_state* s, const uint64_t* indices, uint64_t count, double* ho
             (e = cudaMemcpyAsync(host_amps, d_out, sizeof(cplx) * count, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess ||
             (e = cudaStreamSynchronize(s->stream)) != cudaSuccess)
             rc = set_error(s, QSV_ERR_CUDA, "gather: %s", cudaGetErrorString(e));
+        if (rc == QSV_OK && s->comm) {
+            for (uint64_t i = 0; i < count; ++i)
+                if (!mine[i]) host_amps[2 * i] = host_amps[2 * i + 1] = 0.0;
+            std::string err;
+            if ((e = cudaMemcpyAsync(d_out, host_amps, sizeof(cplx) * count, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess ||
+                !shard_allreduce_sum_f64(s->comm, reinterpret_cast<double*>(d_out), 2 * count, err) ||
+                (e = cudaMemcpyAsync(host_amps, d_out, sizeof(cplx) * count, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess ||
+                (e = cudaStreamSynchronize(s->stream)) != cudaSuccess)
+                rc = set_error(s, QSV_ERR_NCCL, "gather across ranks: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
+        }
         cudaFree(d_idx);
         cudaFree(d_out);
         return rc;
@@ -372,7 +486,9 @@ int qsv_gather(qsv_state* s, const uint64_t* indices, uint64_t count, double* ho
 int qsv_apply(qsv_state* s, const qsv_op* ops, size_t n_ops, qsv_stats* stats) {
     QSV_ENTER(s);
     qsv_plan* p = nullptr;
-    int rc = qsv_plan_create(&p, s->n_qubits, s->n_local, ops, n_ops, (uint32_t)s->opt.tile_bits, (uint32_t)s->opt.low_bits, s->opt.fuse);
+    // a pending basis state has no data to move, so the scheduler may choose the initial layout of a sharded register
+    int rc = qsv_plan_create_ex(&p, s->n_qubits, s->n_local, ops, n_ops, (uint32_t)s->opt.tile_bits, (uint32_t)s->opt.low_bits, s->opt.fuse,
+                                s->lazy_basis ? nullptr : s->layout, s->lazy_basis && s->world > 1);
     if (rc != QSV_OK) return set_error(s, rc, "%s", qsv_plan_last_error());
     try {
         rc = run_plan_impl(s, p, stats);
@@ -405,27 +521,49 @@ int qsv_sample(qsv_state* s, const double* uniforms, uint64_t shots, uint64_t* o
     QSV_ENTER(s);
     if (shots == 0) return QSV_OK;
     if (!uniforms || !out_indices) return set_error(s, QSV_ERR_INVALID_ARG, "NULL argument");
-    if (s->world > 1) return set_error(s, QSV_ERR_UNSUPPORTED, "sampling on a sharded handle is not supported yet");
+    { int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
     int rc = ensure_prefix(s);
     if (rc != QSV_OK) return rc;
+    // Sharded: the cumulative sums run over the physical order (rank 0's shard first); every rank receives the same
+    // uniforms, answers the shots that fall into its interval and the minimum over ranks assembles the result.
+    double offset = 0.0;
+    if (s->comm) {
+        std::string err;
+        std::vector<double> totals(s->world, 0.0);
+        if (!shard_allgather_f64(s->comm, s->total_prob, totals.data(), err)) return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
+        for (int r = 0; r < s->rank; ++r) offset += totals[r];
+    }
     double* d_u = nullptr;
     uint64_t* d_out = nullptr;
     QSV_CUDA(s, cudaMalloc(&d_u, sizeof(double) * shots));
     cudaError_t e = cudaMalloc(&d_out, sizeof(uint64_t) * shots);
     if (e != cudaSuccess) { cudaFree(d_u); return set_error(s, QSV_ERR_OUT_OF_MEMORY, "cudaMalloc: %s", cudaGetErrorString(e)); }
-    if ((e = cudaMemcpyAsync(d_u, uniforms, sizeof(double) * shots, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess ||
+    std::vector<double> shifted;
+    const double* src = uniforms;
+    if (s->comm) {  // shots below this rank's interval get a negative uniform (-> not mine), shots above fall off the end
+        shifted.resize(shots);
+        for (uint64_t i = 0; i < shots; ++i) shifted[i] = uniforms[i] - offset;
+        src = shifted.data();
+    }
+    std::string err;
+    if ((e = cudaMemcpyAsync(d_u, src, sizeof(double) * shots, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess ||
         (e = launch_sample_shots(s->d_state, s->d_prefix, s->n_blocks, s->block_bits, d_u, shots, rank_base(s), d_out, s->sm_count, s->stream)) != cudaSuccess ||
+        (s->comm && !shard_allreduce_min_u64(s->comm, d_out, shots, err)) ||
         (e = cudaMemcpyAsync(out_indices, d_out, sizeof(uint64_t) * shots, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(s->stream)) != cudaSuccess)
-        rc = set_error(s, QSV_ERR_CUDA, "sample: %s", cudaGetErrorString(e));
+        rc = set_error(s, err.empty() ? QSV_ERR_CUDA : QSV_ERR_NCCL, "sample: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
     cudaFree(d_u);
     cudaFree(d_out);
+    if (rc == QSV_OK && !s->layout_identity)
+        for (uint64_t i = 0; i < shots; ++i)
+            if (out_indices[i] != UINT64_MAX) out_indices[i] = to_logical(s, out_indices[i]);
     return rc;
 }
 
 int qsv_norm_sqr(qsv_state* s, double* out) {
     QSV_ENTER(s);
     if (!out) return set_error(s, QSV_ERR_INVALID_ARG, "out is NULL");
+    { int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
     int rc = ensure_prefix(s);
     if (rc != QSV_OK) return rc;
     double total = s->total_prob;
@@ -437,6 +575,12 @@ int qsv_norm_sqr(qsv_state* s, double* out) {
     return QSV_OK;
 }
 
+int qsv_get_layout(const qsv_state* s, uint8_t* out_layout, size_t cap) {
+    if (!s || !out_layout || cap < s->n_qubits) return set_error(nullptr, QSV_ERR_INVALID_ARG, "bad argument");
+    memcpy(out_layout, s->layout, s->n_qubits);
+    return QSV_OK;
+}
+
 int qsv_synchronize(qsv_state* s) {
     QSV_ENTER(s);
     QSV_CUDA(s, cudaStreamSynchronize(s->stream));
@@ -445,6 +589,7 @@ int qsv_synchronize(qsv_state* s) {
 
 int qsv_device_pointer(qsv_state* s, void** dev_ptr, void** cuda_stream) {
     if (!s) return set_error(nullptr, QSV_ERR_INVALID_ARG, "handle is NULL");
+    { cudaSetDevice(s->device); int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
     if (dev_ptr) *dev_ptr = s->d_state;
     if (cuda_stream) *cuda_stream = s->stream;
     return QSV_OK;

@@ -106,10 +106,20 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
     }
 }
 
+// Runs every PASS step in order on one rank's shard (plans without EXCHANGE steps).
 extern "C" int qsv_emu_run_plan(const qsv_plan* p, double* amps, uint64_t rank) {
     if (!p || !amps) return 1;
     const uint64_t rank_hi = rank << p->plan.n_local;
-    for (const auto& blob : p->plan.passes) run_pass(blob.data(), reinterpret_cast<cplx*>(amps), rank_hi);
+    for (const auto& st : p->plan.steps) {
+        if (st.kind != PlanStep::PASS) return 2;  // the caller must drive exchanges (qsv_emu_run_pass per step)
+        run_pass(p->plan.passes[st.pass_index].data(), reinterpret_cast<cplx*>(amps), rank_hi);
+    }
+    return 0;
+}
+
+extern "C" int qsv_emu_run_pass(const qsv_plan* p, uint32_t pass_index, double* amps, uint64_t rank) {
+    if (!p || !amps || pass_index >= p->plan.passes.size()) return 1;
+    run_pass(p->plan.passes[pass_index].data(), reinterpret_cast<cplx*>(amps), rank << p->plan.n_local);
     return 0;
 }
 

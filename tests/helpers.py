@@ -83,6 +83,15 @@ def emu_lib():
         lib.qsv_plan_create.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.POINTER(F.QsvOp), C.c_size_t,
                                         C.c_uint32, C.c_uint32, C.c_int]
         lib.qsv_plan_destroy.argtypes = [C.c_void_p]
+        lib.qsv_emu_run_pass.restype = C.c_int
+        lib.qsv_emu_run_pass.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_double), C.c_uint64]
+        vp, sz, i32, u32 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32
+        lib.qsv_plan_create_ex.restype = C.c_int
+        lib.qsv_plan_create_ex.argtypes = [C.POINTER(vp), u32, u32, C.POINTER(F.QsvOp), sz, u32, u32, i32, C.POINTER(C.c_uint8), i32]
+        lib.qsv_plan_num_steps.argtypes = [vp, C.POINTER(sz)]
+        lib.qsv_plan_get_step.argtypes = [vp, sz, C.POINTER(i32), C.POINTER(u32), C.POINTER(C.c_uint8), sz]
+        lib.qsv_plan_get_layout.argtypes = [vp, i32, C.POINTER(C.c_uint8), sz]
+        lib.qsv_plan_stats.argtypes = [vp, C.POINTER(F.QsvStats)]
         lib.qsv_plan_last_error.restype = C.c_char_p
         lib.qsv_plan_serialize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         _emu = lib
@@ -235,3 +244,64 @@ def random_any_gate_circuit(C, G, n, n_gates, rng, custom=None):
             g = G.Toffoli(int(wires[1]), int(wires[2]))
         c.add_gate(g, t)
     return c
+
+
+# ---- sharded registers on the CPU: the product's plan (layouts, passes, EXCHANGE steps) driven by the emulator --------
+
+def logical_to_physical(i, layout):
+    p = 0
+    for b, pos in enumerate(layout):
+        p |= ((i >> b) & 1) << pos
+    return p
+
+
+def physical_index_table(n, layout):
+    """phys[i] = physical index of canonical index i under `layout` (vectorised)."""
+    idx = np.arange(1 << n, dtype=np.uint64)
+    phys = np.zeros_like(idx)
+    for b, pos in enumerate(layout):
+        phys |= ((idx >> np.uint64(b)) & np.uint64(1)) << np.uint64(pos)
+    return phys
+
+
+def exchange_bits_global(shards, n_local, partners):
+    """Reference semantics of an EXCHANGE step on the list of per-rank shards: rank bit j <-> local bit partners[j]."""
+    g = len(partners)
+    full = np.concatenate(shards)  # physical order: rank bits on top
+    n = n_local + g
+    idx = np.arange(1 << n, dtype=np.uint64)
+    src = idx.copy()
+    for j, p in enumerate(partners):
+        a, b = np.uint64(n_local + j), np.uint64(p)
+        ba, bb = (src >> a) & np.uint64(1), (src >> b) & np.uint64(1)
+        diff = ba ^ bb
+        src ^= (diff << a) | (diff << b)
+    out = full[src]
+    return [out[r << n_local:(r + 1) << n_local].copy() for r in range(1 << g)]
+
+
+def emu_simulate_sharded(n, enc, world, *, basis_index=0, register=None, tile_bits=0, low_bits=0):
+    """Runs a sharded plan on `world` emulated ranks in this process.  Returns the canonical-order state vector."""
+    lib = emu_lib()
+    g = world.bit_length() - 1
+    nl = n - g
+    plan = qb.Plan(n, enc, n_local=nl, tile_bits=tile_bits, low_bits=low_bits, free_layout=register is None, lib=lib)
+    lay0, lay1 = plan.layout(False), plan.layout(True)
+    full = np.zeros(1 << n, dtype=np.complex128)
+    if register is None:
+        full[logical_to_physical(basis_index, lay0)] = 1.0
+    else:
+        assert lay0 == list(range(n))
+        full[:] = register
+    shards = [full[r << nl:(r + 1) << nl].copy() for r in range(world)]
+    n_exchanges = 0
+    for kind, arg in plan.steps():
+        if kind == "pass":
+            for r in range(world):
+                assert lib.qsv_emu_run_pass(plan.handle, arg, shards[r].ctypes.data_as(C.POINTER(C.c_double)), r) == 0
+        else:
+            shards = exchange_bits_global(shards, nl, arg)
+            n_exchanges += 1
+    phys = physical_index_table(n, lay1)
+    out = np.concatenate(shards)[phys]
+    return out, plan, n_exchanges

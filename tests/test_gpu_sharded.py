@@ -1,0 +1,97 @@
+"""Two-GPU parity: a sharded register (NCCL global-qubit exchange over NVLink) against the CPU oracle.
+Skipped on boxes with fewer than two GPUs; CPU coverage of the same path is in tests/test_sharded.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import OracleCircuit, encode_gates, orc, qb, qft_circuit, qft_expected, random_any_gate_circuit
+
+pytestmark = pytest.mark.gpu
+G = qb.Gate
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, result_dir):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from quantr_b200 import _ffi as F
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = F.load_library()
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        F.check(lib.qsv_nccl_unique_id(buf, 128))
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    dist.broadcast(t, 0)
+    nccl_id = bytes(t.numpy().tobytes())
+    results = {}
+    # QFT: one remap, free initial layout
+    n, x = 16, 0xACE1
+    enc = encode_gates(qft_circuit(OracleCircuit, G, n).circuit_gates, n)
+    s = qb.DeviceState(n, rank, rank=rank, world=world, nccl_id=nccl_id)
+    s.set_option("tile_bits", 8)
+    s.init_basis(x)
+    stats = s.apply(enc)
+    allidx = np.arange(1 << n, dtype=np.uint64)
+    results["qft"] = s.gather(allidx)
+    results["qft_exchanges"] = stats["n_exchanges"]
+    results["qft_norm"] = s.norm_sqr()
+    u = np.random.default_rng(5).random(20000)
+    results["qft_samples"] = s.sample(u)
+    s.close()
+    # random circuit on an uploaded register (canonical layout, several remaps)
+    n2 = 14
+    rng = np.random.default_rng(99)
+    c = random_any_gate_circuit(OracleCircuit, G, n2, 120, rng)
+    enc2 = encode_gates(c.circuit_gates, n2)
+    reg = rng.normal(size=1 << n2) + 1j * rng.normal(size=1 << n2)
+    reg /= np.linalg.norm(reg)
+    s2 = qb.DeviceState(n2, rank, rank=rank, world=world, nccl_id=nccl_id)
+    s2.set_option("tile_bits", 7)
+    nl = n2 - (world.bit_length() - 1)
+    s2.upload(reg[rank << nl:(rank + 1) << nl], first=rank << nl)
+    st2 = s2.apply(enc2)
+    results["rand"] = s2.gather(np.arange(1 << n2, dtype=np.uint64))
+    results["rand_exchanges"] = st2["n_exchanges"]
+    s2.close()
+    if rank == 0:
+        np.savez(os.path.join(result_dir, "out.npz"), **results)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs")
+def test_two_gpu_sharded_register_matches_oracle(tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    out = np.load(tmp_path / "out.npz")
+    n, x = 16, 0xACE1
+    assert int(out["qft_exchanges"]) == 1
+    assert np.max(np.abs(out["qft"] - qft_expected(n, x))) < 1e-12
+    assert abs(float(out["qft_norm"]) - 1.0) < 1e-12
+    counts = np.bincount(out["qft_samples"].astype(np.int64), minlength=1 << n)
+    assert counts.sum() == 20000 and counts.max() <= 6  # uniform distribution over 65536 outcomes
+    n2 = 14
+    rng = np.random.default_rng(99)
+    c = random_any_gate_circuit(OracleCircuit, G, n2, 120, rng)
+    enc2 = encode_gates(c.circuit_gates, n2)
+    reg = rng.normal(size=1 << n2) + 1j * rng.normal(size=1 << n2)
+    reg /= np.linalg.norm(reg)
+    ref = orc.simulate(n2, enc2.ops, enc2.n_ops, reg, mode="dense")
+    assert int(out["rand_exchanges"]) >= 1
+    assert np.max(np.abs(out["rand"] - ref)) < 1e-12

@@ -116,8 +116,12 @@ def test_sharded_plan_rank_bits_feed_controls_and_phases():
 
 def test_plan_errors():
     enc = encode_gates(qft_circuit(OracleCircuit, G, 6).circuit_gates, 6)
+    plan = qb.Plan(6, enc, n_local=4)  # H on a rank bit: the plan inserts a global-qubit remap
+    assert any(kind == "exchange" for kind, _ in plan.steps())
+    c = OracleCircuit.new(6)
+    c.add_gate(G.Custom(lambda p: None, [0, 1, 2, 3, 4], "wide"), 5)
     with pytest.raises(F.QsvError) as e:
-        qb.Plan(6, enc, n_local=4)  # H on a rank bit needs a remap
+        qb.Plan(6, encode_gates(c.circuit_gates, 6), n_local=4)  # a 6-wire Custom gate cannot be made local on 4 bits
     assert e.value.code == 5
     bad = (F.QsvOp * 1)()
     bad[0].kind = F.GATE_CNOT
