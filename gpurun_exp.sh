@@ -1,6 +1,5 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-run() { lab=$1; shift; envs=$1; shift; echo "== $lab"; env QSV_TRACE_PASSES=1 $envs timeout 300 python bench.py --no-cpu-baseline "$@" 2>&1 | grep -E "^\[qsv\]|ms_per_step" | tail -6 | sed -E 's/.*"ms_per_step": ([0-9.]+).*max_abs_err_vs_closed_form": ([0-9.e-]+).*/ms_per_step \1 err \2/' | cut -c1-120; }
-run q33_t11_l3 "A=1" --steps 2 --warmup 1 --tile-bits 11 --low-bits 3
-run q33_t11_auto "A=1" --steps 2 --warmup 1 --tile-bits 11
-run q33_t12_l4 "A=1" --steps 2 --warmup 1 --tile-bits 12 --low-bits 4
-run q33_t12_auto "A=1" --steps 2 --warmup 1 --tile-bits 12
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --qubits 31 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_2gpu_q31.log 2>&1; tail -2 gpurun_out/bench_2gpu_q31.log | cut -c1-1800
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_2gpu_q34.log 2>&1; tail -2 gpurun_out/bench_2gpu_q34.log | cut -c1-1800

@@ -31,12 +31,16 @@ def _worker(rank, world, port, result_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lib = F.load_library()
-    buf = C.create_string_buffer(128)
-    if rank == 0:
-        F.check(lib.qsv_nccl_unique_id(buf, 128))
-    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-    dist.broadcast(t, 0)
-    nccl_id = bytes(t.numpy().tobytes())
+
+    def new_nccl_id():  # one ncclUniqueId per communicator, made on rank 0 and broadcast by the caller (here: gloo)
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            F.check(lib.qsv_nccl_unique_id(buf, 128))
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        dist.broadcast(t, 0)
+        return bytes(t.numpy().tobytes())
+
+    nccl_id = new_nccl_id()
     results = {}
     # QFT: one remap, free initial layout
     n, x = 16, 0xACE1
@@ -59,7 +63,7 @@ def _worker(rank, world, port, result_dir):
     enc2 = encode_gates(c.circuit_gates, n2)
     reg = rng.normal(size=1 << n2) + 1j * rng.normal(size=1 << n2)
     reg /= np.linalg.norm(reg)
-    s2 = qb.DeviceState(n2, rank, rank=rank, world=world, nccl_id=nccl_id)
+    s2 = qb.DeviceState(n2, rank, rank=rank, world=world, nccl_id=new_nccl_id())
     s2.set_option("tile_bits", 7)
     nl = n2 - (world.bit_length() - 1)
     s2.upload(reg[rank << nl:(rank + 1) << nl], first=rank << nl)
