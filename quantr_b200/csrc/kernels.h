@@ -14,6 +14,10 @@ cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* hos
 template <int TILE_BITS>
 cudaError_t launch_pass_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream);
 
+// defined in pass_kernel_async.cu for TILE_BITS = 11 and 12: the software-pipelined (cp.async + mbarrier) variant
+template <int TILE_BITS>
+cudaError_t launch_pass_async_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream);
+
 cudaError_t launch_set_amp(cplx* state, uint64_t index, double re, double im, cudaStream_t stream);
 cudaError_t launch_gather(const cplx* state, const uint64_t* idx, cplx* out, uint64_t count, cudaStream_t stream);
 cudaError_t launch_prob_block_sums(const cplx* state, double* sums, uint64_t n_blocks, uint32_t block_bits, int sm_count, cudaStream_t stream);

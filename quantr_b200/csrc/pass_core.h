@@ -111,7 +111,7 @@ QSV_HD void c_mul_ip(cplx& a, double fr, double fi) {
 // m = {m00.re, m00.im, m01.re, m01.im, m10.re, m10.im, m11.re, m11.im}
 
 template <int J, bool CTRL>
-QSV_HD void mat_general(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
+QSV_HD void mat_general(cplx (&a)[kSlots], const double (&m)[16], uint32_t cm) {
     if constexpr (J < kRegBits) {
     const double ar = m[0], ai = m[1], br = m[2], bi = m[3], cr = m[4], ci = m[5], dr = m[6], di = m[7];
 #pragma unroll
@@ -142,7 +142,7 @@ QSV_HD void mat_general(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
 }
 
 template <int J, bool CTRL>
-QSV_HD void mat_real(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
+QSV_HD void mat_real(cplx (&a)[kSlots], const double (&m)[16], uint32_t cm) {
     if constexpr (J < kRegBits) {
     const double ar = m[0], br = m[2], cr = m[4], dr = m[6];
 #pragma unroll
@@ -163,7 +163,7 @@ QSV_HD void mat_real(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
 }
 
 template <int J, bool CTRL>
-QSV_HD void mat_hadamard(cplx (&a)[kSlots], const double (&)[8], uint32_t cm) {
+QSV_HD void mat_hadamard(cplx (&a)[kSlots], const double (&)[16], uint32_t cm) {
     if constexpr (J < kRegBits) {
 #pragma unroll
     for (int s0 = 0; s0 < kSlots; ++s0) {
@@ -178,7 +178,7 @@ QSV_HD void mat_hadamard(cplx (&a)[kSlots], const double (&)[8], uint32_t cm) {
 }
 
 template <int J, bool CTRL>
-QSV_HD void mat_antidiag(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
+QSV_HD void mat_antidiag(cplx (&a)[kSlots], const double (&m)[16], uint32_t cm) {
     if constexpr (J < kRegBits) {
     const double br = m[2], bi = m[3], cr = m[4], ci = m[5];
 #pragma unroll
@@ -202,7 +202,7 @@ QSV_HD void mat_antidiag(cplx (&a)[kSlots], const double (&m)[8], uint32_t cm) {
 }
 
 template <int J, bool CTRL>
-QSV_HD void mat_xswap(cplx (&a)[kSlots], const double (&)[8], uint32_t cm) {
+QSV_HD void mat_xswap(cplx (&a)[kSlots], const double (&)[16], uint32_t cm) {
     if constexpr (J < kRegBits) {
 #pragma unroll
     for (int s0 = 0; s0 < kSlots; ++s0) {
@@ -217,29 +217,13 @@ QSV_HD void mat_xswap(cplx (&a)[kSlots], const double (&)[8], uint32_t cm) {
     }  // J < kRegBits
 }
 
-// Depth-first doubling over the free register bits: multiplies a[s | S] by f * prod_{k in S} r_k for every subset S of
-// the bits in FREE (a 4-bit mask), holding at most one factor per level in registers.  No table loads: the four
-// r_k = exp(i*pi*coef_k) are uniform operands from the constant bank.
-template <int FREE>
-QSV_HD void diag_dfs(cplx (&a)[kSlots], const double (&r)[8], int s, cplx f) {
-    c_mul_ip(a[s], f.x, f.y);
-    if constexpr ((FREE & 1) != 0) diag_dfs<0>(a, r, s | 1, cmul(f, cplx{r[0], r[1]}));
-    if constexpr ((FREE & 2) != 0) diag_dfs<(FREE & 1)>(a, r, s | 2, cmul(f, cplx{r[2], r[3]}));
-    if constexpr ((FREE & 4) != 0) diag_dfs<(FREE & 3)>(a, r, s | 4, cmul(f, cplx{r[4], r[5]}));
-    if constexpr ((FREE & 8) != 0 && kRegBits >= 4) diag_dfs<(FREE & 7)>(a, r, s | 8, cmul(f, cplx{r[6], r[7]}));
-}
-
-// amp[s] *= w * R[s] for the slots selected by the register-control mask, R[s] = prod_{k: bit k of s} r_k.
-// SEL = 0: all 16 slots, SEL = 1..4: the 8 slots with register bit SEL-1 set, SEL = 5: generic runtime mask.
-// tbl: the op's thread-phase table lo[32], hi[16] (shared memory for small passes, global otherwise).
-// Where a pass keeps the thread-dependent phase factors of its DIAG ops, given the shared memory one CTA may use
-// while keeping the intended number of CTAs per SM (launcher and host emulation must agree):
-//   2: per-thread phases [n_diag][threads] in shared memory, computed once per launch
-//   1: the lo/hi tables [n_diag][48] in shared memory      0: tables read from global memory
+// Which ops of a pass keep thread-dependent phases where: see choose_diag_mode() below.
 #ifndef QSV_OCC_NUM
 #define QSV_OCC_NUM 2  // CTAs per SM at T = 12 (x2 at T = 11, x4 at T = 10, /2 at T = 13); build parameter for occupancy experiments
 #endif
 QSV_HD constexpr uint32_t tile_min_blocks(uint32_t T) { return T >= 13 ? (QSV_OCC_NUM / 2 ? QSV_OCC_NUM / 2 : 1u) : T == 12 ? QSV_OCC_NUM : T == 11 ? 2u * QSV_OCC_NUM : 4u * QSV_OCC_NUM; }
+//   2: per-thread phases [n_diag][threads] in shared memory, computed once per launch
+//   1: the lo/hi tables [n_diag][kDiagTblLen] in shared memory      0: tables read from global memory
 inline size_t pass_smem_bytes(uint32_t T, uint32_t n_diag, int mode) {
     size_t b = (sizeof(cplx) << T) + sizeof(cplx) * (n_diag + 1);
     if (mode == 2) b += sizeof(cplx) * (size_t)n_diag * tile_threads(T);
@@ -272,42 +256,108 @@ struct DiagCtx {
     uint32_t threads;
 };
 
+// q-th subset (q = 0..7) of the three register bits other than bit C, as a slot mask
+template <int C>
+QSV_HD constexpr int free_subset(int q) {
+    int s = 0, k = 0;
+    for (int b = 0; b < 4; ++b) {
+        if (b == C) continue;
+        if ((q >> k) & 1) s |= 1 << b;
+        ++k;
+    }
+    return s;
+}
+
+// amp[s] *= w * R[s] on the slots selected by the register-control mask, R[s] = prod_{k: bit k of s} r_k.
+// SEL = 0: all slots, SEL = 1..4: the slots with register bit SEL-1 set, SEL = 5: generic runtime mask.
+// Two waves of independent in-place complex multiplies: first the tile/thread factor w on every selected slot, then
+// the register-bit constants (uniform operands from the constant bank, trivial entries skipped).
 template <int SEL, bool HAS_REG>
 QSV_HD void diag_apply(cplx (&a)[kSlots], const DevOp& op, const DiagCtx& ctx, uint32_t e) {
-    cplx w = ctx.ext_phase[op.diag_index];
-    if (ctx.thr_phase) {
-        if (op.flags & (DIAG_HAS_THR_LO | DIAG_HAS_THR_HI)) w = cmul(w, ctx.thr_phase[op.diag_index * ctx.threads + e]);
-    } else {
-        const cplx* tbl = ctx.thr_tbl ? ctx.thr_tbl + op.diag_index * kDiagTblLen : reinterpret_cast<const cplx*>(ctx.blob + op.tbl_off);
-        if (op.flags & DIAG_HAS_THR_LO) w = cmul(w, tbl[e & 31u]);
-        if (op.flags & DIAG_HAS_THR_HI) w = cmul(w, tbl[32u + (e >> 5)]);
-    }
     constexpr bool kSingle = SEL >= 1 && SEL <= kRegBits;
-    constexpr int kBit = kSingle ? (1 << (SEL - 1)) : 0;
+    constexpr int kCtl = kSingle ? SEL - 1 : 0;
+    constexpr int kBit = kSingle ? (1 << kCtl) : 0;
     if constexpr (SEL > kRegBits && SEL <= 4) return;  // no such register bit in this build
-    if (SEL <= 4) {
-        if (HAS_REG) {
-            diag_dfs<((kSlots - 1) & ~kBit)>(a, op.m, kBit, w);  // the control bit itself carries no linear term
+    const uint32_t cm = op.cmask_reg;
+    if (op.flags & DIAG_HAS_W) {
+        cplx w = ctx.ext_phase[op.diag_index];
+        if (ctx.thr_phase) {
+            if (op.flags & (DIAG_HAS_THR_LO | DIAG_HAS_THR_HI)) w = cmul(w, ctx.thr_phase[op.diag_index * ctx.threads + e]);
         } else {
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                if (kSingle && !(s & kBit)) continue;
-                c_mul_ip(a[s], w.x, w.y);
-            }
+            const cplx* tbl = ctx.thr_tbl ? ctx.thr_tbl + op.diag_index * kDiagTblLen : reinterpret_cast<const cplx*>(ctx.blob + op.tbl_off);
+            if (op.flags & DIAG_HAS_THR_LO) w = cmul(w, tbl[e & 31u]);
+            if (op.flags & DIAG_HAS_THR_HI) w = cmul(w, tbl[32u + (e >> 5)]);
         }
-    } else {
-        const uint32_t cm = op.cmask_reg;
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
-            if ((s & cm) != cm) continue;
-            cplx f = w;
-            if (HAS_REG) {
-                if (s & 1) f = cmul(f, cplx{op.m[0], op.m[1]});
-                if (s & 2) f = cmul(f, cplx{op.m[2], op.m[3]});
-                if (s & 4) f = cmul(f, cplx{op.m[4], op.m[5]});
-                if (s & 8) f = cmul(f, cplx{op.m[6], op.m[7]});
+            if (kSingle && !(s & kBit)) continue;
+            if (SEL == 5 && (s & cm) != cm) continue;
+            c_mul_ip(a[s], w.x, w.y);
+        }
+    }
+    if (!HAS_REG) return;
+    const uint32_t nontrivial = op.flags >> DIAG_NONTRIVIAL_SHIFT;
+    if (kSingle) {
+#pragma unroll
+        for (int q = 1; q < (1 << (kRegBits - 1)); ++q) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int s = kBit | free_subset<kCtl>(q);
+            if (s >= kSlots) continue;
+            if ((nontrivial >> (q - 1)) & 1u) c_mul_ip(a[s], op.m[2 * (q - 1)], op.m[2 * (q - 1) + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kRegBits; ++k) {
+            if (!((nontrivial >> k) & 1u)) continue;
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                if (!((s >> k) & 1)) continue;
+                if (SEL == 5 && (s & cm) != cm) continue;
+                c_mul_ip(a[s], op.m[2 * k], op.m[2 * k + 1]);
             }
-            c_mul_ip(a[s], f.x, f.y);
+        }
+    }
+}
+
+// Hadamard on register bit J fused with the DIAG op controlled by that bit: the phase factor is fetched first so its
+// latency hides behind the butterflies.
+template <int J, bool HAS_REG>
+QSV_HD void hd_apply(cplx (&a)[kSlots], const DevOp& op, const DiagCtx& ctx, uint32_t e) {
+    if constexpr (J < kRegBits) {
+        cplx w{1.0, 0.0};
+        const bool has_w = (op.flags & DIAG_HAS_W) != 0;
+        if (has_w) {
+            w = ctx.ext_phase[op.diag_index];
+            if (ctx.thr_phase) {
+                if (op.flags & (DIAG_HAS_THR_LO | DIAG_HAS_THR_HI)) w = cmul(w, ctx.thr_phase[op.diag_index * ctx.threads + e]);
+            } else {
+                const cplx* tbl = ctx.thr_tbl ? ctx.thr_tbl + op.diag_index * kDiagTblLen : reinterpret_cast<const cplx*>(ctx.blob + op.tbl_off);
+                if (op.flags & DIAG_HAS_THR_LO) w = cmul(w, tbl[e & 31u]);
+                if (op.flags & DIAG_HAS_THR_HI) w = cmul(w, tbl[32u + (e >> 5)]);
+            }
+        }
+#pragma unroll
+        for (int s0 = 0; s0 < kSlots; ++s0) {
+            if ((s0 >> J) & 1) continue;
+            cplx& x = a[s0];
+            cplx& y = a[s0 | (1 << J)];
+            f_bfly(x.x, y.x);
+            f_bfly(x.y, y.y);
+        }
+        if (has_w) {
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s)
+                if ((s >> J) & 1) c_mul_ip(a[s], w.x, w.y);
+        }
+        if (HAS_REG) {
+            const uint32_t nontrivial = op.flags >> DIAG_NONTRIVIAL_SHIFT;
+#pragma unroll
+            for (int q = 1; q < (1 << (kRegBits - 1)); ++q) {
+                const int s = (1 << J) | free_subset<J>(q);
+                if (s >= kSlots) continue;
+                if ((nontrivial >> (q - 1)) & 1u) c_mul_ip(a[s], op.m[2 * (q - 1)], op.m[2 * (q - 1) + 1]);
+            }
         }
     }
 }
@@ -342,6 +392,12 @@ inline uint32_t op_dispatch_code(const DevOp& op) {
     case kCodeMatBase + KIND * 8 + 5: FN<1, true>(a, op.m, op.cmask_reg); break;             \
     case kCodeMatBase + KIND * 8 + 6: FN<2, true>(a, op.m, op.cmask_reg); break;             \
     case kCodeMatBase + KIND * 8 + 7: FN<3, true>(a, op.m, op.cmask_reg); break;
+
+#define QSV_HD_CASES(HAS_REG)                                                                   \
+    case kCodeHdBase + (HAS_REG ? 4 : 0) + 0: hd_apply<0, HAS_REG>(a, op, ctx, e); break;       \
+    case kCodeHdBase + (HAS_REG ? 4 : 0) + 1: hd_apply<1, HAS_REG>(a, op, ctx, e); break;       \
+    case kCodeHdBase + (HAS_REG ? 4 : 0) + 2: hd_apply<2, HAS_REG>(a, op, ctx, e); break;       \
+    case kCodeHdBase + (HAS_REG ? 4 : 0) + 3: hd_apply<3, HAS_REG>(a, op, ctx, e); break;
 
 #define QSV_DIAG_CASES(HAS_REG)                                                                                                    \
     case kCodeDiagBase + (HAS_REG ? 6 : 0) + 0: diag_apply<0, HAS_REG>(a, op, ctx, e); break;           \
@@ -437,6 +493,8 @@ QSV_HD void round_ops(const DevRound& R, const DevOp* ops, const DiagCtx& ctx, c
             QSV_MAT_CASES(4, mat_antidiag)
             QSV_DIAG_CASES(false)
             QSV_DIAG_CASES(true)
+            QSV_HD_CASES(false)
+            QSV_HD_CASES(true)
             default: break;
         }
         if (!m) break;

@@ -347,7 +347,19 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
                 else d.cmask_thr |= 1u << lp;
             }
         };
-        for (size_t oi : rb.ops) {
+        for (size_t ri = 0; ri < rb.ops.size(); ++ri) {
+            size_t oi = rb.ops[ri];
+            // Peephole: an uncontrolled Hadamard followed by a diagonal op controlled by exactly the Hadamard's bit
+            // (one stage of a QFT-style ladder) becomes one fused op: emitted as the DIAG op with an HD dispatch code.
+            int fused_hadamard_slot = -1;
+            if (plan.opt.fuse && lops[oi].kind == LOp::MAT && lops[oi].mtype == OP_MAT_HADAMARD && lops[oi].cmask == 0 && ri + 1 < rb.ops.size()) {
+                const LOp& nx = lops[rb.ops[ri + 1]];
+                if (nx.kind == LOp::DIAG && nx.cmask == (1ull << lops[oi].target)) {
+                    fused_hadamard_slot = slot_of[local_of[lops[oi].target]];
+                    ++n_hadamard;
+                    oi = rb.ops[++ri];
+                }
+            }
             const LOp& lop = lops[oi];
             DevOp d;
             memset(&d, 0, sizeof(d));
@@ -386,19 +398,42 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
                 }
                 for (int b = 0; b < 5; ++b) has_lo |= thr_coef[b] != 0.0;
                 for (int b = 5; b < 10; ++b) has_hi |= thr_coef[b] != 0.0;
-                for (int j = 0; j < 4; ++j) {  // unused register slots (j >= kRegBits) stay at phase 1
-                    const cplx r = unit_phase(reg_coef[j]);
-                    d.m[2 * j] = r.x;
-                    d.m[2 * j + 1] = r.y;
-                    has_reg |= reg_coef[j] != 0.0;
+                // register-bit constants (see DevOp::m): one control bit among the register bits -> table over the
+                // subsets of the other three; otherwise one phase per register bit
+                uint32_t nontrivial = 0;
+                const bool single_ctl = d.cmask_reg && (d.cmask_reg & (d.cmask_reg - 1)) == 0;
+                if (single_ctl) {
+                    int ctl = 0;
+                    while (!((d.cmask_reg >> ctl) & 1)) ++ctl;
+                    int free_bits[3], nf = 0;
+                    for (int b = 0; b < 4; ++b) if (b != ctl) free_bits[nf++] = b;
+                    for (int q = 1; q < 8; ++q) {
+                        double ang = 0;
+                        for (int k = 0; k < 3; ++k) if ((q >> k) & 1) ang += reg_coef[free_bits[k]];
+                        const cplx r = unit_phase(ang);
+                        d.m[2 * (q - 1)] = r.x;
+                        d.m[2 * (q - 1) + 1] = r.y;
+                        if (r.x != 1.0 || r.y != 0.0) nontrivial |= 1u << (q - 1);
+                    }
+                } else {
+                    for (int j = 0; j < 4; ++j) {  // unused register slots (j >= kRegBits) stay at phase 1
+                        const cplx r = unit_phase(reg_coef[j]);
+                        d.m[2 * j] = r.x;
+                        d.m[2 * j + 1] = r.y;
+                        if (r.x != 1.0 || r.y != 0.0) nontrivial |= 1u << j;
+                    }
                 }
-                d.flags = (has_lo ? (uint32_t)DIAG_HAS_THR_LO : 0u) | (has_hi ? (uint32_t)DIAG_HAS_THR_HI : 0u) | (has_reg ? (uint32_t)DIAG_HAS_REG : 0u);
+                has_reg = nontrivial != 0;
+                const bool has_w = lop.theta0 != 0.0 || !ext.empty() || has_lo || has_hi;
+                d.flags = (has_lo ? (uint32_t)DIAG_HAS_THR_LO : 0u) | (has_hi ? (uint32_t)DIAG_HAS_THR_HI : 0u) | (has_reg ? (uint32_t)DIAG_HAS_REG : 0u) |
+                          (has_w ? (uint32_t)DIAG_HAS_W : 0u) | (nontrivial << DIAG_NONTRIVIAL_SHIFT);
                 d.n_ext = (uint32_t)ext.size();
                 if (!ext.empty()) { d.ext_off = (uint32_t)append(aux, ext.data(), ext.size()); fixes.push_back({ops.size(), 0}); }
                 d.tbl_off = (uint32_t)append(aux, tbl.data(), tbl.size());  // always present: the kernel stages it in shared memory
                 fixes.push_back({ops.size(), 1});
             }
             d.code = op_dispatch_code(d);
+            if (fused_hadamard_slot >= 0) d.code = kCodeHdBase + ((d.flags & DIAG_HAS_REG) ? 4u : 0u) + (uint32_t)fused_hadamard_slot;
             if (d.cmask_ext) hdr.ext_ctrl_mask[ops.size() >> 5] |= 1u << (ops.size() & 31);
             ops.push_back(d);
         }
@@ -576,10 +611,10 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
         close_pass();
     };
 
-    // Cost model (units: one pass streamed at the HBM roofline = 1).  Memory: measured streaming efficiency of a
-    // tile whose contiguous runs are 16 B << run_bits (tools/stream_probe.py on B200).  The arithmetic of the ops is
-    // the same for every candidate, so only the memory term and the number of passes decide.
-    auto plan_cost = [&](const std::vector<PassB>& passes) {
+    // Cost model, in units of one pass streamed at the HBM roofline.  Memory term: measured streaming efficiency of a
+    // tile whose contiguous runs are 16 B << run_bits; compute term: measured per-op and per-round costs of the pass
+    // kernel (tools/stream_probe.py, tools/diag_probe.py on B200, n = 30).  The two overlap only partly.
+    auto plan_cost = [&](const std::vector<LOp>& lops, const std::vector<PassB>& passes) {
         double total = 0;
         for (const PassB& pb : passes) {
             uint64_t tile_mask = pb.req;
@@ -587,7 +622,16 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
             int run_bits = 0;
             while (run_bits < nloc && ((tile_mask >> run_bits) & 1)) ++run_bits;
             const double eff = run_bits <= 3 ? 0.47 : run_bits == 4 ? 0.68 : run_bits == 5 ? 0.75 : run_bits == 6 ? 0.80 : run_bits == 7 ? 0.85 : 0.90;
-            total += 1.0 / eff;
+            const double mem = 1.0 / eff;
+            double compute = 0.9 + 0.145 * (pb.rounds.empty() ? 0.0 : (double)pb.rounds.size() - 1.0);
+            for (const RoundB& r : pb.rounds)
+                for (size_t oi : r.ops) {
+                    const LOp& lop = lops[oi];
+                    if (lop.kind == LOp::DENSE) compute += 0.5;
+                    else if (lop.kind == LOp::DIAG) compute += 0.06;
+                    else compute += lop.mtype == OP_MAT_GENERAL ? 0.13 : lop.mtype == OP_MAT_HADAMARD ? 0.053 : 0.08;
+                }
+            total += std::max(mem, compute) + 0.1 * std::min(mem, compute);
         }
         return total;
     };
@@ -611,7 +655,7 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
             std::vector<PassB> cand;
             for (int L = std::min(8, T - 1); L >= 3; --L) {
                 schedule(seg, L, cand);
-                const double c = plan_cost(cand);
+                const double c = plan_cost(seg, cand);
                 if (best.empty() || c < best_cost - 1e-9) { best_cost = c; chosen_L = L; best.swap(cand); }
             }
         }

@@ -67,7 +67,9 @@ enum OpType : uint32_t {
 //   MAT : 1 + kind*8 + ctrl*4 + slot, kind = 0 HADAMARD, 1 XSWAP, 2 REAL, 3 GENERAL, 4 ANTIDIAG; ctrl = has register controls
 //   DIAG: 41 + has_reg*6 + sel,        sel = 0 all slots, 1..4 slots with register bit sel-1 set, 5 runtime mask
 constexpr int kDiagTblLen = 64;  // lo[32] (thread-index bits 0-4) + hi[32] (bits 5-9)
-constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeCount = 53;
+//   HD  : 53 + has_reg*4 + slot: an uncontrolled Hadamard on register bit `slot` fused with the DIAG op that follows it
+//         and is controlled by exactly that bit (one stage of a QFT / phase-estimation ladder)
+constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeHdBase = 53, kCodeCount = 61;
 enum PassFlags : uint32_t {
     PASS_L2_PREFETCH = 1,
     PASS_DIRECT_STORE = 2  // the last round writes its registers straight to global memory (coalesced: its register bits
@@ -75,7 +77,14 @@ enum PassFlags : uint32_t {
 };
 constexpr int kMaxRoundOps = 32;  // ops per register round (one 32-bit active mask)
 
-enum DiagFlags : uint32_t { DIAG_HAS_THR_LO = 1, DIAG_HAS_THR_HI = 2, DIAG_HAS_REG = 4 };
+enum DiagFlags : uint32_t {
+    DIAG_HAS_THR_LO = 1,
+    DIAG_HAS_THR_HI = 2,
+    DIAG_HAS_REG = 4,   // some register bit carries a linear term
+    DIAG_HAS_W = 8,     // the tile/thread factor w is not identically 1
+    // bits 8..22: which entries of the register-constant table are not 1 (see DevOp::m)
+    DIAG_NONTRIVIAL_SHIFT = 8
+};
 enum RoundType : uint32_t { ROUND_REG = 0, ROUND_DENSE = 1 };
 
 struct DiagExtTerm {
@@ -84,7 +93,7 @@ struct DiagExtTerm {
     double coef;   // half-turns
 };
 
-// 128 bytes
+// 192 bytes
 struct DevOp {
     uint32_t type;
     uint32_t slot;        // MAT: register slot 0..3 of the target bit
@@ -93,7 +102,11 @@ struct DevOp {
     uint64_t cmask_ext;   // controls outside the tile (physical bit positions, rank bits included)
     uint32_t flags;       // DIAG: DiagFlags
     uint32_t diag_index;  // DIAG: slot in the per-tile external-phase array
-    double m[8];          // MAT: m00 m01 m10 m11 (re, im);  DIAG: r_0..r_3 = exp(i*pi*coef of register bit j) (re, im)
+    double m[16];         // MAT: m00 m01 m10 m11 (re, im) in m[0..8).
+                          // DIAG with one register control bit c: m[2(q-1)], m[2(q-1)+1] = exp(i*pi*sum of the coefs of the
+                          //   free register bits in q), q = 1..7 over the register bits other than c in ascending order;
+                          // DIAG otherwise: m[2k], m[2k+1] = r_k = exp(i*pi*coef of register bit k), k = 0..3.
+                          // flags bit (DIAG_NONTRIVIAL_SHIFT + q - 1) resp. (+ k): the entry differs from 1.
     uint32_t ext_off;     // DIAG: byte offset in the pass blob of DiagExtTerm[n_ext]
     uint32_t n_ext;
     uint32_t tbl_off;     // DIAG: byte offset of the thread-phase table cplx lo[32], hi[16] (kDiagTblLen entries)
@@ -102,7 +115,7 @@ struct DevOp {
     uint32_t pad;
     double theta0;        // DIAG: constant term (half-turns)
 };
-static_assert(sizeof(DevOp) == 128, "DevOp layout");
+static_assert(sizeof(DevOp) == 192, "DevOp layout");
 
 // 128 bytes
 struct DevRound {
