@@ -202,6 +202,7 @@ def main():
     # sharded: the register starts as a basis state, so the scheduler may park the last-targeted qubits in the rank id
     plan = qb.Plan(n, enc, n_local=n_local, tile_bits=args.tile_bits, low_bits=args.low_bits, free_layout=world > 1)
     pstats = plan.stats()
+    pdesc = plan.describe()
     passes = pstats["n_passes"]
     state.set_option("timing", 1)  # per-pass CUDA events inside the library -> qsv_stats.device_ms / exchange_ms
 
@@ -276,7 +277,7 @@ def main():
             e2e_step()
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.steps
-        plan_bytes = sum(p["bytes"] for p in plan.describe()["passes"])
+        plan_bytes = sum(p["bytes"] for p in pdesc["passes"])
         e2e = {"value": n_gates * 32.0 * float(1 << n) / e2e_s / 1e9, "unit": "GB/s", "ms_per_step": e2e_s * 1e3,
                "h2d_bytes_per_step": int(plan_bytes + 8 * args.shots), "d2h_bytes_per_step": int(8 * args.shots + 16 * 4096 + 8),
                "path": "qsv_init_basis + qsv_apply(host ops) + qsv_sample(host uniforms) + qsv_download(4096 amps)"}
@@ -309,7 +310,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"QFT-{n} complex f64, |x=0x{x:x}> -> {n_gates} gates (H + CRk, no final swaps)", "qubits": n,
                        "local_qubits": n_local, "state_bytes_per_gpu": 16 << n_local, "l2_policy": "state >> 126 MB L2 (no flush needed)",
-                       "tile_bits": args.tile_bits or 12, "low_bits": args.low_bits or 3, "parallelism": f"shard{world}"},
+                       "tile_bits": pdesc["tile_bits"], "low_bits": pdesc["low_bits"], "parallelism": f"shard{world}"},
             "qft_wall_time_ms": ms_per_step, "fused_passes": passes, "passes_per_gate": passes / n_gates,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int((passes + 1) * args.steps),
             "exchange": None if world == 1 else {

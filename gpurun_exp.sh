@@ -1,2 +1,5 @@
-QSV_ASYNC=1 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-timeout 600 python tools/run_configs.py 30 2>&1 | grep -v Warning | tail -8
+mkdir -p gpurun_out
+timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1; tail -1 gpurun_out/bench_default.log
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.log 2>&1; tail -1 gpurun_out/bench_reference.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r01_final.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:pass_kernel -s 4 -c 4 -o gpurun_out/prof_r01_final python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log | cut -c1-60
