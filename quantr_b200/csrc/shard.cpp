@@ -73,6 +73,9 @@ struct ShardComm {
     int rank = 0, world = 1;
     cudaStream_t stream = nullptr;
     double* d_scalar = nullptr;  // 1 + world doubles
+    // exchange pipeline: staging -> shard copies run on their own stream so they overlap the next chunk's transfer
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t recv_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
 };
 
 bool shard_unique_id(void* out, size_t out_bytes, std::string& err) {
@@ -95,12 +98,22 @@ ShardComm* shard_comm_create(int rank, int world, const void* unique_id, size_t 
     c->stream = stream;
     if (!nccl_ok(g_nccl.CommInitRank(&c->comm, world, id, rank), "ncclCommInitRank", err)) { delete c; return nullptr; }
     if (cudaMalloc(&c->d_scalar, sizeof(double) * (size_t)(1 + world)) != cudaSuccess) { err = "cudaMalloc failed"; g_nccl.CommDestroy(c->comm); delete c; return nullptr; }
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&c->recv_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming);
+    }
     return c;
 }
 
 void shard_comm_destroy(ShardComm* c) {
     if (!c) return;
     if (c->d_scalar) cudaFree(c->d_scalar);
+    for (int i = 0; i < 2; ++i) {
+        if (c->recv_done[i]) cudaEventDestroy(c->recv_done[i]);
+        if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     delete c;
 }
@@ -145,6 +158,7 @@ bool shard_exchange_bits(ShardComm* c, void* base, uint32_t n_local, const uint8
     for (uint32_t j = 0; j < g; ++j) partner_mask |= (uint64_t)1 << partner[j];
     const uint64_t n_runs = ((uint64_t)1 << n_local) >> (partner[0] + g);  // runs per peer block
     int slot = 0;
+    bool slot_used[2] = {false, false};
     // Round-robin pairing (peer = rank ^ step): every step is a perfect matching over NVSwitch.
     for (int step = 1; step < c->world; ++step) {
         const int peer = c->rank ^ step;
@@ -163,12 +177,21 @@ bool shard_exchange_bits(ShardComm* c, void* base, uint32_t n_local, const uint8
             for (uint64_t off = 0; off < bytes; off += staging_bytes) {
                 const size_t len = (size_t)(bytes - off < staging_bytes ? bytes - off : staging_bytes);
                 char* st = stage[slot];
-                slot ^= 1;
+                // the staging buffer is free again once the copy that last read it has finished
+                if (slot_used[slot] && cudaStreamWaitEvent(c->stream, c->copy_done[slot], 0) != cudaSuccess) { err = "cudaStreamWaitEvent failed"; return false; }
                 if (!nccl_ok(g_nccl.GroupStart(), "ncclGroupStart", err)) return false;
                 if (!nccl_ok(g_nccl.Send(chunk + off, len, ncclUint8, peer, c->comm, c->stream), "ncclSend", err)) return false;
                 if (!nccl_ok(g_nccl.Recv(st, len, ncclUint8, peer, c->comm, c->stream), "ncclRecv", err)) return false;
                 if (!nccl_ok(g_nccl.GroupEnd(), "ncclGroupEnd", err)) return false;
-                if (cudaMemcpyAsync(chunk + off, st, len, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { err = "staging copy failed"; return false; }
+                // staging -> shard on the copy stream: overlaps the next chunk's transfer (the send of this chunk is complete)
+                if (cudaEventRecord(c->recv_done[slot], c->stream) != cudaSuccess || cudaStreamWaitEvent(c->copy_stream, c->recv_done[slot], 0) != cudaSuccess ||
+                    cudaMemcpyAsync(chunk + off, st, len, cudaMemcpyDeviceToDevice, c->copy_stream) != cudaSuccess ||
+                    cudaEventRecord(c->copy_done[slot], c->copy_stream) != cudaSuccess) {
+                    err = "staging copy failed";
+                    return false;
+                }
+                slot_used[slot] = true;
+                slot ^= 1;
             }
         }
     }
