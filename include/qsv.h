@@ -144,6 +144,14 @@ int qsv_create_sharded(qsv_state** out, uint32_t n_qubits, int device, int rank,
                        const void* nccl_unique_id, size_t nccl_unique_id_bytes);
 int qsv_nccl_unique_id(void* out, size_t out_bytes);
 
+/* Optional, sharded handles: direct NVLink exchange.  Every rank exports an opaque 64-byte handle of its shard
+ * (qsv_peer_export), the caller all-gathers them, and every rank imports the table (qsv_peer_import: `handles` holds
+ * world x 64 bytes, entry r = rank r's export).  Afterwards global-qubit remaps swap amplitudes in place through
+ * peer-mapped memory (one kernel per peer, loads/stores over NVLink) instead of NCCL send/recv through staging. */
+#define QSV_PEER_HANDLE_BYTES 64
+int qsv_peer_export(qsv_state* s, void* out_handle, size_t out_bytes);
+int qsv_peer_import(qsv_state* s, const void* handles, size_t n_handles);
+
 int qsv_destroy(qsv_state* s);
 
 /* Thread-local message of the last failed call made with `s` (or with no

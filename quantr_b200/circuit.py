@@ -148,6 +148,17 @@ class DeviceState:
 
     __del__ = close
 
+    def peer_export(self) -> bytes:
+        """Opaque handle of this rank's shard for direct NVLink exchange (all-gather it, then `peer_import`)."""
+        buf = C.create_string_buffer(64)
+        F.check(self.lib.qsv_peer_export(self.handle, buf, 64), self.handle)
+        return buf.raw
+
+    def peer_import(self, handles: list):
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        F.check(self.lib.qsv_peer_import(self.handle, buf, len(handles)), self.handle)
+
     def set_option(self, key: str, value: int):
         F.check(self.lib.qsv_set_option(self.handle, key.encode(), value), self.handle)
 

@@ -19,6 +19,8 @@ template <int TILE_BITS>
 cudaError_t launch_pass_async_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream);
 
 cudaError_t launch_set_amp(cplx* state, uint64_t index, double re, double im, cudaStream_t stream);
+// in-place swap of this rank's block 'spelled' peer with the peer's block 'spelled' rank (peer-mapped memory, NVLink)
+cudaError_t launch_peer_swap(cplx* local, cplx* remote, uint32_t n_local, const uint8_t* partner, uint32_t g, int rank, int peer, int sm_count, cudaStream_t stream);
 cudaError_t launch_gather(const cplx* state, const uint64_t* idx, cplx* out, uint64_t count, cudaStream_t stream);
 cudaError_t launch_prob_block_sums(const cplx* state, double* sums, uint64_t n_blocks, uint32_t block_bits, int sm_count, cudaStream_t stream);
 cudaError_t launch_scan_block_sums(const double* sums, double* prefix, uint64_t n, cudaStream_t stream);

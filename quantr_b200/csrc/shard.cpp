@@ -128,6 +128,10 @@ bool shard_allreduce_sum(ShardComm* c, double* value, std::string& err) {
     return true;
 }
 
+bool shard_barrier(ShardComm* c, std::string& err) {
+    return nccl_ok(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclFloat64, ncclSum, c->comm, c->stream), "ncclAllReduce (barrier)", err);
+}
+
 bool shard_allreduce_sum_f64(ShardComm* c, double* d_buf, size_t count, std::string& err) {
     return nccl_ok(g_nccl.AllReduce(d_buf, d_buf, count, ncclFloat64, ncclSum, c->comm, c->stream), "ncclAllReduce", err);
 }

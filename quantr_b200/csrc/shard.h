@@ -18,6 +18,8 @@ bool shard_unique_id(void* out, size_t out_bytes, std::string& err);
 ShardComm* shard_comm_create(int rank, int world, const void* unique_id, size_t unique_id_bytes, cudaStream_t stream, std::string& err);
 void shard_comm_destroy(ShardComm* c);
 bool shard_allreduce_sum(ShardComm* c, double* value, std::string& err);
+// stream-ordered barrier over all ranks (a one-element all-reduce enqueued on the comm's stream)
+bool shard_barrier(ShardComm* c, std::string& err);
 // device buffers, enqueued on the comm's stream
 bool shard_allreduce_sum_f64(ShardComm* c, double* d_buf, size_t count, std::string& err);
 bool shard_allreduce_min_u64(ShardComm* c, uint64_t* d_buf, size_t count, std::string& err);

@@ -48,8 +48,9 @@ struct qsv_state {
     // its own initial layout (nothing to move) and the memset is issued just before the first pass
     bool lazy_basis = false;
     uint64_t lazy_index = 0;
-    void* d_staging = nullptr;  // exchange staging (sharded handles)
+    void* d_staging = nullptr;  // exchange staging (sharded handles, NCCL path)
     size_t staging_bytes = 0;
+    std::vector<cplx*> peer_ptr;  // peer-mapped shards (qsv_peer_import); empty = NCCL send/recv exchange
     std::string error;
 };
 
@@ -202,7 +203,7 @@ int run_exchange(qsv_state* s, const PlanStep& st, double* ms_out) {
     if (!s->comm) return set_error(s, QSV_ERR_INTERNAL, "exchange step on an unsharded handle");
     const uint32_t g = s->n_qubits - s->n_local;
     if (st.partner_bits.size() != g) return set_error(s, QSV_ERR_INTERNAL, "exchange step does not match the handle");
-    if (!s->d_staging) {
+    if (!s->d_staging && s->peer_ptr.empty()) {
         size_t want = (size_t)1 << 30;  // 1 GiB per direction, double-buffered below
         const size_t shard = sizeof(cplx) << s->n_local;
         if (want > shard / 4) want = shard / 4 ? shard / 4 : sizeof(cplx);
@@ -212,8 +213,18 @@ int run_exchange(qsv_state* s, const PlanStep& st, double* ms_out) {
     }
     if (s->timing) QSV_CUDA(s, cudaEventRecord(s->ev0, s->stream));
     std::string err;
-    if (!shard_exchange_bits(s->comm, s->d_state, s->n_local, st.partner_bits.data(), g, s->d_staging, s->staging_bytes, err))
+    if (!s->peer_ptr.empty()) {
+        // peer-memory path: barrier (every rank has finished the passes before the remap), one in-place swap kernel
+        // per peer (round-robin pairing), barrier (every peer has finished writing into this shard)
+        if (!shard_barrier(s->comm, err)) return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
+        for (int step = 1; step < s->world; ++step) {
+            const int peer = s->rank ^ step;
+            QSV_CUDA(s, launch_peer_swap(s->d_state, s->peer_ptr[peer], s->n_local, st.partner_bits.data(), g, s->rank, peer, s->sm_count, s->stream));
+        }
+        if (!shard_barrier(s->comm, err)) return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
+    } else if (!shard_exchange_bits(s->comm, s->d_state, s->n_local, st.partner_bits.data(), g, s->d_staging, s->staging_bytes, err)) {
         return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
+    }
     if (s->timing) {
         QSV_CUDA(s, cudaEventRecord(s->ev1, s->stream));
         QSV_CUDA(s, cudaEventSynchronize(s->ev1));
@@ -350,10 +361,43 @@ int qsv_nccl_unique_id(void* out, size_t out_bytes) {
     return QSV_OK;
 }
 
+int qsv_peer_export(qsv_state* s, void* out_handle, size_t out_bytes) {
+    QSV_ENTER(s);
+    if (!out_handle || out_bytes < sizeof(cudaIpcMemHandle_t)) return set_error(s, QSV_ERR_INVALID_ARG, "handle buffer must hold %zu bytes", sizeof(cudaIpcMemHandle_t));
+    cudaIpcMemHandle_t h;
+    QSV_CUDA(s, cudaIpcGetMemHandle(&h, s->d_state));
+    memcpy(out_handle, &h, sizeof(h));
+    return QSV_OK;
+}
+
+int qsv_peer_import(qsv_state* s, const void* handles, size_t n_handles) {
+    QSV_ENTER(s);
+    if (!s->comm) return set_error(s, QSV_ERR_INVALID_ARG, "peer import needs a sharded handle");
+    if (!handles || n_handles != (size_t)s->world) return set_error(s, QSV_ERR_INVALID_ARG, "expected one handle per rank");
+    std::vector<cplx*> ptrs(s->world, nullptr);
+    for (int r = 0; r < s->world; ++r) {
+        if (r == s->rank) { ptrs[r] = s->d_state; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < r; ++q) if (q != s->rank && ptrs[q]) cudaIpcCloseMemHandle(ptrs[q]);
+            return set_error(s, QSV_ERR_CUDA, "cudaIpcOpenMemHandle for rank %d: %s", r, cudaGetErrorString(e));
+        }
+        ptrs[r] = static_cast<cplx*>(p);
+    }
+    s->peer_ptr.swap(ptrs);
+    return QSV_OK;
+}
+
 int qsv_destroy(qsv_state* s) {
     if (!s) return QSV_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int r = 0; r < (int)s->peer_ptr.size(); ++r)
+        if (r != s->rank && s->peer_ptr[r]) cudaIpcCloseMemHandle(s->peer_ptr[r]);
     if (s->comm) shard_comm_destroy(s->comm);
     if (s->d_state) cudaFree(s->d_state);
     if (s->d_sums) cudaFree(s->d_sums);

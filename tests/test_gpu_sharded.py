@@ -65,6 +65,11 @@ def _worker(rank, world, port, result_dir):
     reg /= np.linalg.norm(reg)
     s2 = qb.DeviceState(n2, rank, rank=rank, world=world, nccl_id=new_nccl_id())
     s2.set_option("tile_bits", 7)
+    # this register exchanges through peer-mapped memory (NVLink loads/stores) instead of NCCL send/recv
+    mine = torch.frombuffer(bytearray(s2.peer_export()), dtype=torch.uint8).clone()
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    s2.peer_import([bytes(h.numpy().tobytes()) for h in allh])
     nl = n2 - (world.bit_length() - 1)
     s2.upload(reg[rank << nl:(rank + 1) << nl], first=rank << nl)
     st2 = s2.apply(enc2)
