@@ -10,8 +10,9 @@ QSV_REG_BITS ?= 4
 OBJ ?= build/obj$(QSV_REG_BITS)
 LIB ?= quantr_b200/libqsv.so
 QSV_OCC_NUM ?= 2
-NVCCFLAGS := -DQSV_REG_BITS=$(QSV_REG_BITS) -DQSV_OCC_NUM=$(QSV_OCC_NUM) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas -ccbin $(HOSTCXX)
-HOSTFLAGS := -DQSV_REG_BITS=$(QSV_REG_BITS) -DQSV_OCC_NUM=$(QSV_OCC_NUM) -O2 -std=c++17 -fPIC -Wall -Wextra -Wno-unknown-pragmas -pthread
+EXTRA_DEFS ?=
+NVCCFLAGS := -DQSV_REG_BITS=$(QSV_REG_BITS) -DQSV_OCC_NUM=$(QSV_OCC_NUM) $(EXTRA_DEFS) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas -ccbin $(HOSTCXX)
+HOSTFLAGS := -DQSV_REG_BITS=$(QSV_REG_BITS) -DQSV_OCC_NUM=$(QSV_OCC_NUM) $(EXTRA_DEFS) -O2 -std=c++17 -fPIC -Wall -Wextra -Wno-unknown-pragmas -pthread
 
 HOST_SRCS := $(CSRC)/plan.cpp $(CSRC)/plan_api.cpp
 HDRS := include/qsv.h $(wildcard $(CSRC)/*.h)

@@ -221,7 +221,10 @@ QSV_HD void mat_xswap(cplx (&a)[kSlots], const double (&)[16], uint32_t cm) {
 #ifndef QSV_OCC_NUM
 #define QSV_OCC_NUM 2  // CTAs per SM at T = 12 (x2 at T = 11, x4 at T = 10, /2 at T = 13); build parameter for occupancy experiments
 #endif
-QSV_HD constexpr uint32_t tile_min_blocks(uint32_t T) { return T >= 13 ? (QSV_OCC_NUM / 2 ? QSV_OCC_NUM / 2 : 1u) : T == 12 ? QSV_OCC_NUM : T == 11 ? 2u * QSV_OCC_NUM : 4u * QSV_OCC_NUM; }
+#ifndef QSV_OCC_T11
+#define QSV_OCC_T11 (2u * QSV_OCC_NUM)
+#endif
+QSV_HD constexpr uint32_t tile_min_blocks(uint32_t T) { return T >= 13 ? (QSV_OCC_NUM / 2 ? QSV_OCC_NUM / 2 : 1u) : T == 12 ? QSV_OCC_NUM : T == 11 ? QSV_OCC_T11 : 4u * QSV_OCC_NUM; }
 //   2: per-thread phases [n_diag][threads] in shared memory, computed once per launch
 //   1: the lo/hi tables [n_diag][kDiagTblLen] in shared memory      0: tables read from global memory
 inline size_t pass_smem_bytes(uint32_t T, uint32_t n_diag, int mode) {
@@ -236,6 +239,15 @@ inline int choose_diag_mode(uint32_t T, uint32_t n_diag) {
     if (pass_smem_bytes(T, n_diag, 1) <= budget) return 1;  // measured faster than mode 2 on B200 (less shared memory per CTA)
     if (pass_smem_bytes(T, n_diag, 2) <= budget) return 2;
     return 0;
+}
+
+// The uniform fast path of the pass kernel: every thread of every tile runs the whole op list (no thread-bit or tile-index controls), the pass fits
+// the small parameter class and the per-thread phase table fits next to the tile.  Launcher and emulator agree on it.
+inline bool pass_is_fast(const DevPass& hdr) {
+    if (!(hdr.flags & PASS_UNCONDITIONAL) || hdr.tile_bits < 10) return false;
+    if (hdr.n_rounds > (uint32_t)kSmallRounds || hdr.n_ops > (uint32_t)kSmallOps) return false;
+    const size_t budget = (size_t)(227 * 1024) / tile_min_blocks(hdr.tile_bits) - 1024;
+    return pass_smem_bytes(hdr.tile_bits, hdr.n_diag, 2) <= budget;
 }
 
 // Thread phase of a DIAG op: product of its lo/hi table entries for thread-group e (tile-independent).
@@ -256,6 +268,24 @@ struct DiagCtx {
     uint32_t threads;
 };
 
+// Tile/thread factor of a DIAG op for thread-group e.  FAST: external phase x precomputed thread phase, no flag tests.
+template <bool FAST>
+QSV_HD cplx diag_w(const DevOp& op, const DiagCtx& ctx, uint32_t e) {
+    cplx w = ctx.ext_phase[op.diag_index];
+    if constexpr (FAST) {
+        return cmul(w, ctx.thr_phase[op.diag_index * ctx.threads + e]);
+    } else {
+        if (ctx.thr_phase) {
+            if (op.flags & (DIAG_HAS_THR_LO | DIAG_HAS_THR_HI)) w = cmul(w, ctx.thr_phase[op.diag_index * ctx.threads + e]);
+        } else {
+            const cplx* tbl = ctx.thr_tbl ? ctx.thr_tbl + op.diag_index * kDiagTblLen : reinterpret_cast<const cplx*>(ctx.blob + op.tbl_off);
+            if (op.flags & DIAG_HAS_THR_LO) w = cmul(w, tbl[e & 31u]);
+            if (op.flags & DIAG_HAS_THR_HI) w = cmul(w, tbl[32u + (e >> 5)]);
+        }
+        return w;
+    }
+}
+
 // q-th subset (q = 0..7) of the three register bits other than bit C, as a slot mask
 template <int C>
 QSV_HD constexpr int free_subset(int q) {
@@ -272,7 +302,7 @@ QSV_HD constexpr int free_subset(int q) {
 // SEL = 0: all slots, SEL = 1..4: the slots with register bit SEL-1 set, SEL = 5: generic runtime mask.
 // Two waves of independent in-place complex multiplies: first the tile/thread factor w on every selected slot, then
 // the register-bit constants (uniform operands from the constant bank, trivial entries skipped).
-template <int SEL, bool HAS_REG>
+template <int SEL, bool HAS_REG, bool FAST>
 QSV_HD void diag_apply(cplx (&a)[kSlots], const DevOp& op, const DiagCtx& ctx, uint32_t e) {
     constexpr bool kSingle = SEL >= 1 && SEL <= kRegBits;
     constexpr int kCtl = kSingle ? SEL - 1 : 0;
@@ -280,14 +310,7 @@ QSV_HD void diag_apply(cplx (&a)[kSlots], const DevOp& op, const DiagCtx& ctx, u
     if constexpr (SEL > kRegBits && SEL <= 4) return;  // no such register bit in this build
     const uint32_t cm = op.cmask_reg;
     if (op.flags & DIAG_HAS_W) {
-        cplx w = ctx.ext_phase[op.diag_index];
-        if (ctx.thr_phase) {
-            if (op.flags & (DIAG_HAS_THR_LO | DIAG_HAS_THR_HI)) w = cmul(w, ctx.thr_phase[op.diag_index * ctx.threads + e]);
-        } else {
-            const cplx* tbl = ctx.thr_tbl ? ctx.thr_tbl + op.diag_index * kDiagTblLen : reinterpret_cast<const cplx*>(ctx.blob + op.tbl_off);
-            if (op.flags & DIAG_HAS_THR_LO) w = cmul(w, tbl[e & 31u]);
-            if (op.flags & DIAG_HAS_THR_HI) w = cmul(w, tbl[32u + (e >> 5)]);
-        }
+        const cplx w = diag_w<FAST>(op, ctx, e);
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
             if (kSingle && !(s & kBit)) continue;
@@ -322,21 +345,14 @@ QSV_HD void diag_apply(cplx (&a)[kSlots], const DevOp& op, const DiagCtx& ctx, u
 
 // Hadamard on register bit J fused with the DIAG op controlled by that bit: the phase factor is fetched first so its
 // latency hides behind the butterflies.
-template <int J, bool HAS_REG>
+template <int J, bool HAS_REG, bool FAST>
 QSV_HD void hd_apply(cplx (&a)[kSlots], const DevOp& op, const DiagCtx& ctx, uint32_t e) {
     if constexpr (J < kRegBits) {
         cplx w{1.0, 0.0};
-        const bool has_w = (op.flags & DIAG_HAS_W) != 0;
-        if (has_w) {
-            w = ctx.ext_phase[op.diag_index];
-            if (ctx.thr_phase) {
-                if (op.flags & (DIAG_HAS_THR_LO | DIAG_HAS_THR_HI)) w = cmul(w, ctx.thr_phase[op.diag_index * ctx.threads + e]);
-            } else {
-                const cplx* tbl = ctx.thr_tbl ? ctx.thr_tbl + op.diag_index * kDiagTblLen : reinterpret_cast<const cplx*>(ctx.blob + op.tbl_off);
-                if (op.flags & DIAG_HAS_THR_LO) w = cmul(w, tbl[e & 31u]);
-                if (op.flags & DIAG_HAS_THR_HI) w = cmul(w, tbl[32u + (e >> 5)]);
-            }
-        }
+        // FAST: fetched unconditionally (the tables hold 1 where the op has no tile/thread dependence) so the loads
+        // issue ahead of the butterflies
+        const bool has_w = FAST || (op.flags & DIAG_HAS_W) != 0;
+        if (has_w) w = diag_w<FAST>(op, ctx, e);
 #pragma unroll
         for (int s0 = 0; s0 < kSlots; ++s0) {
             if ((s0 >> J) & 1) continue;
@@ -394,18 +410,18 @@ inline uint32_t op_dispatch_code(const DevOp& op) {
     case kCodeMatBase + KIND * 8 + 7: FN<3, true>(a, op.m, op.cmask_reg); break;
 
 #define QSV_HD_CASES(HAS_REG)                                                                   \
-    case kCodeHdBase + (HAS_REG ? 4 : 0) + 0: hd_apply<0, HAS_REG>(a, op, ctx, e); break;       \
-    case kCodeHdBase + (HAS_REG ? 4 : 0) + 1: hd_apply<1, HAS_REG>(a, op, ctx, e); break;       \
-    case kCodeHdBase + (HAS_REG ? 4 : 0) + 2: hd_apply<2, HAS_REG>(a, op, ctx, e); break;       \
-    case kCodeHdBase + (HAS_REG ? 4 : 0) + 3: hd_apply<3, HAS_REG>(a, op, ctx, e); break;
+    case kCodeHdBase + (HAS_REG ? 4 : 0) + 0: hd_apply<0, HAS_REG, FAST>(a, op, ctx, e); break;       \
+    case kCodeHdBase + (HAS_REG ? 4 : 0) + 1: hd_apply<1, HAS_REG, FAST>(a, op, ctx, e); break;       \
+    case kCodeHdBase + (HAS_REG ? 4 : 0) + 2: hd_apply<2, HAS_REG, FAST>(a, op, ctx, e); break;       \
+    case kCodeHdBase + (HAS_REG ? 4 : 0) + 3: hd_apply<3, HAS_REG, FAST>(a, op, ctx, e); break;
 
 #define QSV_DIAG_CASES(HAS_REG)                                                                                                    \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 0: diag_apply<0, HAS_REG>(a, op, ctx, e); break;           \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 1: diag_apply<1, HAS_REG>(a, op, ctx, e); break;           \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 2: diag_apply<2, HAS_REG>(a, op, ctx, e); break;           \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 3: diag_apply<3, HAS_REG>(a, op, ctx, e); break;           \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 4: diag_apply<4, HAS_REG>(a, op, ctx, e); break;           \
-    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 5: diag_apply<5, HAS_REG>(a, op, ctx, e); break;
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 0: diag_apply<0, HAS_REG, FAST>(a, op, ctx, e); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 1: diag_apply<1, HAS_REG, FAST>(a, op, ctx, e); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 2: diag_apply<2, HAS_REG, FAST>(a, op, ctx, e); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 3: diag_apply<3, HAS_REG, FAST>(a, op, ctx, e); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 4: diag_apply<4, HAS_REG, FAST>(a, op, ctx, e); break;           \
+    case kCodeDiagBase + (HAS_REG ? 6 : 0) + 5: diag_apply<5, HAS_REG, FAST>(a, op, ctx, e); break;
 
 // Which ops of the pass act on thread-group e (controls among the thread's fixed tile-local bits).  Tile-independent:
 // the kernel evaluates it once per launch.  W words of 32 op bits.
@@ -460,10 +476,29 @@ QSV_HD void round_store_tile(const DevRound& R, uint32_t lb, cplx* tile, const c
 }
 
 //   act : bit o set = op o of the pass acts on this thread-group for this tile (W words)
-template <int W>
+//   FAST: the uniform fast path (pass_is_fast): act is ignored, every op runs
+template <int W, bool FAST = false>
 QSV_HD void round_ops(const DevRound& R, const DevOp* ops, const DiagCtx& ctx, const uint32_t (&act)[W], uint32_t e, cplx (&a)[kSlots]) {
     const uint32_t first = R.first_op, n = R.n_ops;  // n <= kMaxRoundOps
     if (n == 0) return;
+    if constexpr (FAST) {  // every op is active: a counted loop over uniform op indices
+        for (uint32_t o = first; o < first + n; ++o) {
+            const DevOp& op = ops[o];
+            switch (op.code) {
+                QSV_MAT_CASES(0, mat_hadamard)
+                QSV_MAT_CASES(1, mat_xswap)
+                QSV_MAT_CASES(2, mat_real)
+                QSV_MAT_CASES(3, mat_general)
+                QSV_MAT_CASES(4, mat_antidiag)
+                QSV_DIAG_CASES(false)
+                QSV_DIAG_CASES(true)
+                QSV_HD_CASES(false)
+                QSV_HD_CASES(true)
+                default: break;
+            }
+        }
+        return;
+    }
     // the round's slice of the active mask, bit j = op first + j
     uint32_t lo = act[0], hi = 0;
 #pragma unroll

@@ -37,7 +37,9 @@ struct TileCfg {
     static constexpr uint32_t kLoads = T_STATIC ? (uint32_t)kSlots : 8u;  // runtime T <= 9: 2^9 / 64
 };
 
-template <int T_STATIC, int NR, int NO>
+// FAST (pass_is_fast): no op has thread-bit controls, so the op walk is CTA-uniform (scalar registers, uniform branches,
+// op constants as uniform operands) and DIAG thread phases always come from the per-launch table (diag_mode 2).
+template <int T_STATIC, int NR, int NO, bool FAST>
 __global__ void __launch_bounds__(TileCfg<T_STATIC>::kThreads, TileCfg<T_STATIC>::kMinBlocks)
 pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t rank_hi, int diag_mode, const __grid_constant__ PassParams<NR, NO> P) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -61,7 +63,12 @@ pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t
 
     // ---- once per launch: thread-dependent pieces that do not depend on the tile ----------------------
     uint32_t thr_act[W];
-    thread_active_mask<W>(P.hdr, P.rounds, P.ops, tid, thr_act);
+    if constexpr (FAST) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) thr_act[w] = 0xffffffffu;
+    } else {
+        thread_active_mask<W>(P.hdr, P.rounds, P.ops, tid, thr_act);
+    }
     if (diag_mode & 3) {
         for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
             if (P.ops[o].type == OP_DIAG) {
@@ -104,7 +111,7 @@ pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t
                     const uint32_t lb = round_thread_base(P.rounds[r], tid);
                     cplx a[kSlots];
                     round_load(P.rounds[r], lb, tile, a);
-                    round_ops<W>(P.rounds[r], P.ops, ctx, act, tid, a);
+                    round_ops<W, FAST>(P.rounds[r], P.ops, ctx, act, tid, a);
                     if (direct && r + 1 == n_rounds) {
                         cplx* g = state + base + gstore_t;
 #pragma unroll
@@ -146,7 +153,7 @@ pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t
     }
 }
 
-template <int T_STATIC, int NR, int NO>
+template <int T_STATIC, int NR, int NO, bool FAST>
 static cudaError_t launch_pass_t(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream) {
     static PassParams<NR, NO> params;  // zero-initialised; only the used prefix of rounds/ops is rewritten per launch
     if (!fill_params(host_blob, params)) return cudaErrorInvalidValue;
@@ -156,31 +163,36 @@ static cudaError_t launch_pass_t(cplx* state, const uint8_t* dev_blob, const uin
     static const int mode_cap = getenv("QSV_DIAG_MODE") ? atoi(getenv("QSV_DIAG_MODE")) : 2;  // developer A/B switch
     int mode = choose_diag_mode(hdr.tile_bits, hdr.n_diag);
     if (mode > mode_cap) mode = mode_cap;
+    if (FAST) mode = hdr.n_diag ? 2 : 0;
     const size_t smem = pass_smem_bytes(hdr.tile_bits, hdr.n_diag, mode);
     static size_t smem_cfg = 0;
     if (smem_cfg == 0) {
         smem_cfg = (size_t)(227 * 1024) - 1024;  // opt-in maximum; the per-launch size decides the occupancy
-        cudaError_t err = cudaFuncSetAttribute(pass_kernel<T_STATIC, NR, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cfg);
+        cudaError_t err = cudaFuncSetAttribute(pass_kernel<T_STATIC, NR, NO, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cfg);
         if (err != cudaSuccess) return err;
     }
     if (smem > smem_cfg) return cudaErrorInvalidValue;
     static const size_t pad = getenv("QSV_SMEM_PAD") ? (size_t)atol(getenv("QSV_SMEM_PAD")) : 0;  // occupancy experiments
     const size_t smem_launch = (smem + pad <= smem_cfg) ? smem + pad : smem;
     int nb = 0;
-    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pass_kernel<T_STATIC, NR, NO>, (int)kThreads, smem_launch);
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pass_kernel<T_STATIC, NR, NO, FAST>, (int)kThreads, smem_launch);
     if (err != cudaSuccess) return err;
     uint64_t grid = (uint64_t)sm_count * (uint64_t)(nb > 0 ? nb : 1);
     if (grid > hdr.n_tiles) grid = hdr.n_tiles;
-    pass_kernel<T_STATIC, NR, NO><<<(unsigned)grid, kThreads, smem_launch, stream>>>(state, dev_blob, rank_hi, mode | (getenv("QSV_SKIP_EXT") ? 8 : 0), params);
+    pass_kernel<T_STATIC, NR, NO, FAST><<<(unsigned)grid, kThreads, smem_launch, stream>>>(state, dev_blob, rank_hi, mode | (getenv("QSV_SKIP_EXT") ? 8 : 0), params);
     return cudaGetLastError();
 }
 
 template <>
 cudaError_t launch_pass_tile<QSV_TILE_BITS>(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream) {
     const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
+#if QSV_TILE_BITS >= 10
+    static const bool no_fast = getenv("QSV_NO_FAST") != nullptr;  // developer A/B switch
+    if (!no_fast && pass_is_fast(hdr)) return launch_pass_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, true>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+#endif
     if (hdr.n_rounds <= (uint32_t)kSmallRounds && hdr.n_ops <= (uint32_t)kSmallOps)
-        return launch_pass_t<QSV_TILE_BITS, kSmallRounds, kSmallOps>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
-    return launch_pass_t<QSV_TILE_BITS, kMaxRounds, kMaxOps>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+        return launch_pass_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, false>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+    return launch_pass_t<QSV_TILE_BITS, kMaxRounds, kMaxOps, false>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
 }
 
 }  // namespace qsv

@@ -145,7 +145,7 @@ pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, ui
                 const uint32_t lb = round_thread_base(P.rounds[r], gtid);
                 cplx a[kSlots];
                 round_load(P.rounds[r], lb, tile, a);
-                round_ops<W>(P.rounds[r], P.ops, ctx, act, gtid, a);
+                round_ops<W, false>(P.rounds[r], P.ops, ctx, act, gtid, a);
                 if (direct && r + 1 == n_rounds) {
                     cplx* g = state + base + gstore_t;
 #pragma unroll

@@ -457,6 +457,9 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
             }
         }
     }
+    bool conditional = false;
+    for (const DevOp& d : ops) conditional |= d.cmask_thr != 0 || d.cmask_ext != 0;
+    if (!conditional) hdr.flags |= PASS_UNCONDITIONAL;
     hdr.n_rounds = (uint32_t)rounds.size();
     hdr.n_ops = (uint32_t)ops.size();
     hdr.n_diag = n_diag;

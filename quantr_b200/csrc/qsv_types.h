@@ -72,8 +72,10 @@ constexpr int kDiagTblLen = 64;  // lo[32] (thread-index bits 0-4) + hi[32] (bit
 constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeHdBase = 53, kCodeCount = 61;
 enum PassFlags : uint32_t {
     PASS_L2_PREFETCH = 1,
-    PASS_DIRECT_STORE = 2  // the last round writes its registers straight to global memory (coalesced: its register bits
-                           // exclude the three lowest tile bits)
+    PASS_DIRECT_STORE = 2,  // the last round writes its registers straight to global memory (coalesced: its register bits
+                            // exclude the three lowest tile bits)
+    PASS_UNCONDITIONAL = 4  // no op of the pass has a control among the thread or tile-index bits: every thread of every
+                            // tile runs the whole op list, so the kernel walks it with uniform (scalar) control flow
 };
 constexpr int kMaxRoundOps = 32;  // ops per register round (one 32-bit active mask)
 

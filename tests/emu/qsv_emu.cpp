@@ -26,14 +26,16 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
     std::vector<cplx> tile(tile_len);
     std::vector<cplx> ext_phase(kMaxOps);
     std::vector<cplx> dense_out((size_t)groups * kSlots);
+    const bool fast = pass_is_fast(P.hdr);
     std::vector<uint32_t> thr_act((size_t)groups * W);
     for (uint32_t e = 0; e < groups; ++e) {  // the kernel does this once per launch
         uint32_t act[W];
-        thread_active_mask<W>(P.hdr, P.rounds, P.ops, e, act);
+        if (fast) for (int w = 0; w < W; ++w) act[w] = 0xffffffffu;
+        else thread_active_mask<W>(P.hdr, P.rounds, P.ops, e, act);
         memcpy(&thr_act[(size_t)e * W], act, sizeof(act));
     }
     // DIAG thread phases: same placement decision as the launcher
-    const int mode = choose_diag_mode(T, P.hdr.n_diag);
+    const int mode = fast ? 2 : choose_diag_mode(T, P.hdr.n_diag);
     std::vector<cplx> thr_tbl((size_t)kMaxOps * kDiagTblLen), thr_phase((size_t)kMaxOps * threads);
     for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
         if (P.ops[o].type == OP_DIAG) {
@@ -66,7 +68,8 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
                     const uint32_t lb = round_thread_base(R, e);
                     cplx a[kSlots];
                     round_load(R, lb, tile.data(), a);
-                    round_ops<W>(R, P.ops, ctx, act, e, a);
+                    if (fast) round_ops<W, true>(R, P.ops, ctx, act, e, a);
+                    else round_ops<W, false>(R, P.ops, ctx, act, e, a);
                     if (direct && r + 1 == P.hdr.n_rounds) {
                         const uint64_t g = base + deposit(lb, P.hdr.tile_segs, P.hdr.n_tile_segs);
                         for (int s = 0; s < kSlots; ++s) {
