@@ -31,10 +31,10 @@ __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_
 cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream) {
     const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
     const uint32_t tile_bits = hdr.tile_bits;
-    // QSV_ASYNC=1: the software-pipelined kernel (one CTA per SM, tiles prefetched with cp.async while the compute
-    // groups work) for large registers.
-    static const int use_async = getenv("QSV_ASYNC") ? atoi(getenv("QSV_ASYNC")) : 0;  // measured on B200: same speed as the synchronous kernel; opt-in
-    if (use_async && hdr.n_tiles >= 16ull * (uint64_t)sm_count) {
+    // The software-pipelined kernel (one CTA per SM, tiles prefetched with cp.async while the compute groups work)
+    // serves large registers; QSV_ASYNC=0 forces the synchronous kernel, 2 the pipelined one at every size (tests).
+    static const int use_async = getenv("QSV_ASYNC") ? atoi(getenv("QSV_ASYNC")) : 1;
+    if (use_async && (use_async >= 2 || hdr.n_tiles >= 16ull * (uint64_t)sm_count)) {  // 2: always (parity tests of the async kernels)
         if (tile_bits == 12) return launch_pass_async_tile<12>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
         if (tile_bits == 11) return launch_pass_async_tile<11>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
     }

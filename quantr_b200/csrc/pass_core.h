@@ -62,14 +62,16 @@ inline bool fill_params(const uint8_t* blob, PassParams<NR, NO>& out) {
 }
 
 // External phase of a DIAG op for one tile: exp(i*pi*(theta0 + sum over bits outside the tile)).
-QSV_HD cplx diag_ext_phase(const DevOp& op, const uint8_t* blob, uint64_t base_full) {
-    double ang = op.theta0;
-    const DiagExtTerm* terms = reinterpret_cast<const DiagExtTerm*>(blob + op.ext_off);
-    for (uint32_t i = 0; i < op.n_ext; ++i)
+QSV_HD cplx diag_ext_phase_terms(double theta0, const DiagExtTerm* terms, uint32_t n_ext, uint64_t base_full) {
+    double ang = theta0;
+    for (uint32_t i = 0; i < n_ext; ++i)
         if ((base_full >> terms[i].bit) & 1ull) ang += terms[i].coef;
     cplx r;
     sincospi_hd(ang, &r.y, &r.x);
     return r;
+}
+QSV_HD cplx diag_ext_phase(const DevOp& op, const uint8_t* blob, uint64_t base_full) {
+    return diag_ext_phase_terms(op.theta0, reinterpret_cast<const DiagExtTerm*>(blob + op.ext_off), op.n_ext, base_full);
 }
 
 // ---- in-place FP64 primitives ---------------------------------------------------------------------

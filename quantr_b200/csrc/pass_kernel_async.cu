@@ -62,7 +62,7 @@ __device__ __forceinline__ void group_barrier(uint32_t group, uint32_t threads) 
 }
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
 
-template <int T, int NR, int NO>
+template <int T, int NR, int NO, bool FAST>
 __global__ void __launch_bounds__(AsyncCfg<T>::kThreads, 1)
 pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t rank_hi, int diag_mode, const __grid_constant__ PassParams<NR, NO> P) {
     using Cfg = AsyncCfg<T>;
@@ -70,13 +70,14 @@ pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, ui
     constexpr uint32_t kTileLen = 1u << T;
     constexpr int W = (NO + 31) / 32;
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: [kNB tiles][kNB mbarriers][take counter + per-group slots][per-group external phases][DIAG tables]
+    // layout: [kNB tiles][kNB mbarriers][64 bytes spare][per-group external phases][DIAG tables][external term lists]
     cplx* tiles = reinterpret_cast<cplx*>(smem);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)kNB * Cfg::kTileBytes);
-    uint32_t* ctrl = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(full_bar) + 64);  // [0] take counter, [1 + g] tile taken by group g
-    cplx* ext_all = reinterpret_cast<cplx*>(reinterpret_cast<uint8_t*>(ctrl) + 64);
+    cplx* ext_all = reinterpret_cast<cplx*>(reinterpret_cast<uint8_t*>(full_bar) + 128);
     const uint32_t n_diag = P.hdr.n_diag;
     cplx* diag_smem = ext_all + (size_t)kG * (n_diag + 1);
+    const uint32_t tbl_len = (diag_mode & 3) == 2 ? kGT : (diag_mode & 3) == 1 ? (uint32_t)kDiagTblLen : 0u;
+    DiagExtTerm* ext_terms = reinterpret_cast<DiagExtTerm*>(diag_smem + (size_t)n_diag * tbl_len);  // diag_mode & 16: [n_diag][max_ext]
 
     const uint32_t tid = threadIdx.x, group = tid / kGT, gtid = tid % kGT;
     cplx* ext_phase = ext_all + (size_t)group * (n_diag + 1);
@@ -100,7 +101,6 @@ pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, ui
 
     if (tid == 0) {
         for (uint32_t b = 0; b < kNB; ++b) mbar_init(&full_bar[b], kGT);
-        ctrl[0] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -110,29 +110,47 @@ pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, ui
 
     // ---- once per launch: thread-dependent pieces that do not depend on the tile ----------------------
     uint32_t thr_act[W];
-    thread_active_mask<W>(P.hdr, P.rounds, P.ops, gtid, thr_act);
-    if ((diag_mode & 3) == 1) {
+    if constexpr (FAST) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) thr_act[w] = 0xffffffffu;
+    } else {
+        thread_active_mask<W>(P.hdr, P.rounds, P.ops, gtid, thr_act);
+    }
+    if (diag_mode & 3) {
         for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
             if (P.ops[o].type == OP_DIAG) {
                 const cplx* src = reinterpret_cast<const cplx*>(blob + P.ops[o].tbl_off);
-                for (uint32_t i = tid; i < (uint32_t)kDiagTblLen; i += Cfg::kThreads) diag_smem[P.ops[o].diag_index * kDiagTblLen + i] = src[i];
+                if ((diag_mode & 3) == 2) {  // per-thread phases, shared by the groups
+                    for (uint32_t i = tid; i < kGT; i += Cfg::kThreads) diag_smem[P.ops[o].diag_index * kGT + i] = diag_thread_phase(P.ops[o], src, i);
+                } else {
+                    for (uint32_t i = tid; i < (uint32_t)kDiagTblLen; i += Cfg::kThreads) diag_smem[P.ops[o].diag_index * kDiagTblLen + i] = src[i];
+                }
             }
     }
-    const DiagCtx ctx{blob, ext_phase, (diag_mode & 3) == 1 ? diag_smem : nullptr, nullptr, kGT};
+    if (diag_mode & 16) {  // the term lists of the external phases, read once per tile by diag_ext_phase_terms
+        for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
+            if (P.ops[o].type == OP_DIAG) {
+                const DiagExtTerm* src = reinterpret_cast<const DiagExtTerm*>(blob + P.ops[o].ext_off);
+                for (uint32_t i = tid; i < P.ops[o].n_ext; i += Cfg::kThreads) ext_terms[P.ops[o].diag_index * P.hdr.max_ext + i] = src[i];
+            }
+    }
+    const DiagCtx ctx{blob, ext_phase, (diag_mode & 3) == 1 ? diag_smem : nullptr, (diag_mode & 3) == 2 ? diag_smem : nullptr, kGT};
     const uint64_t gstore_t = (direct && n_rounds) ? deposit(round_thread_base(P.rounds[n_rounds - 1], gtid), P.hdr.tile_segs, n_tile_segs) : 0;
     __syncthreads();
 
-    while (true) {
-        if (gtid == 0) ctrl[1 + group] = atomicAdd(&ctrl[0], 1u);
-        group_barrier(group, kGT);
-        const uint64_t k = ctrl[1 + group];
-        if (k >= n_my) break;
+    // tiles are dealt round-robin to the groups (every tile of a pass costs the same)
+    for (uint64_t k = group; k < n_my; k += kG) {
         const uint32_t slot = (uint32_t)(k % kNB);
         cplx* tile = tiles + (size_t)slot * kTileLen;
         const uint64_t base = deposit(blockIdx.x + k * gridDim.x, P.hdr.ext_segs, n_ext_segs);
         const uint64_t base_full = base | rank_hi;
-        for (uint32_t o = gtid; o < P.hdr.n_ops; o += kGT)
-            if (P.ops[o].type == OP_DIAG) ext_phase[P.ops[o].diag_index] = diag_ext_phase(P.ops[o], blob, base_full);
+        // external phases: op o on lane o / warps of warp o % warps, so no warp of the group lags behind
+        for (uint32_t o = (gtid >> 5) + (kGT >> 5) * (gtid & 31u); o < P.hdr.n_ops; o += kGT)
+            if (P.ops[o].type == OP_DIAG) {
+                const DevOp& op = P.ops[o];
+                const DiagExtTerm* terms = (diag_mode & 16) ? ext_terms + op.diag_index * P.hdr.max_ext : reinterpret_cast<const DiagExtTerm*>(blob + op.ext_off);
+                ext_phase[op.diag_index] = diag_ext_phase_terms(op.theta0, terms, op.n_ext, base_full);
+            }
         uint32_t act[W];
 #pragma unroll
         for (int w = 0; w < W; ++w) act[w] = thr_act[w];
@@ -145,7 +163,13 @@ pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, ui
                 const uint32_t lb = round_thread_base(P.rounds[r], gtid);
                 cplx a[kSlots];
                 round_load(P.rounds[r], lb, tile, a);
-                round_ops<W, false>(P.rounds[r], P.ops, ctx, act, gtid, a);
+                if (direct && r + 1 == n_rounds) {
+                    // the tile now lives in registers: hand the buffer to the tile that will use it next, a whole
+                    // round of arithmetic before this group comes back for more
+                    group_barrier(group, kGT);
+                    if (k + kNB < n_my) issue_load(k + kNB);
+                }
+                round_ops<W, FAST>(P.rounds[r], P.ops, ctx, act, gtid, a);
                 if (direct && r + 1 == n_rounds) {
                     cplx* g = state + base + gstore_t;
 #pragma unroll
@@ -167,7 +191,7 @@ pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, ui
                 group_barrier(group, kGT);
                 dense_store(gtid, tile, out);
             }
-            group_barrier(group, kGT);
+            if (!(direct && r + 1 == n_rounds)) group_barrier(group, kGT);
         }
         if (!direct) {
             cplx* gtile = state + base + goff_t;
@@ -183,12 +207,12 @@ pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, ui
             }
             group_barrier(group, kGT);  // every thread has read its part of the buffer
         }
-        // refill this buffer with the tile that will use it next
-        if (k + kNB < n_my) issue_load(k + kNB);
+        // refill this buffer with the tile that will use it next (direct-store passes did so in their last round)
+        if (!(direct && n_rounds && P.rounds[n_rounds - 1].type == ROUND_REG) && k + kNB < n_my) issue_load(k + kNB);
     }
 }
 
-template <int T, int NR, int NO>
+template <int T, int NR, int NO, bool FAST>
 static cudaError_t launch_async_t(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream) {
     using Cfg = AsyncCfg<T>;
     static PassParams<NR, NO> params;
@@ -198,27 +222,38 @@ static cudaError_t launch_async_t(cplx* state, const uint8_t* dev_blob, const ui
     const size_t fixed = (size_t)Cfg::kBuffers * Cfg::kTileBytes + 64 /* mbarriers */ + 64 /* counters */ + sizeof(cplx) * Cfg::kGroups * (hdr.n_diag + 1);
     const size_t limit = (size_t)227 * 1024 - 1024;
     int mode = (fixed + sizeof(cplx) * kDiagTblLen * hdr.n_diag <= limit) ? 1 : 0;  // DIAG tables in shared memory when they fit
+    if (FAST) mode = 2;
     if (hdr.n_diag == 0) mode = 0;
-    const size_t smem = fixed + (mode == 1 ? sizeof(cplx) * kDiagTblLen * hdr.n_diag : 0);
+    size_t smem = fixed + (mode == 1 ? sizeof(cplx) * kDiagTblLen * hdr.n_diag : mode == 2 ? sizeof(cplx) * Cfg::kGroupThreads * hdr.n_diag : 0);
+    const size_t terms_bytes = sizeof(DiagExtTerm) * (size_t)hdr.n_diag * hdr.max_ext;
+    if (terms_bytes && smem + terms_bytes <= limit) {
+        smem += terms_bytes;
+        mode |= 16;
+    }
     if (smem > limit) return cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(pass_kernel_async<T, NR, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+        cudaError_t err = cudaFuncSetAttribute(pass_kernel_async<T, NR, NO, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
         if (err != cudaSuccess) return err;
         configured = true;
     }
     uint64_t grid = (uint64_t)sm_count;
     if (grid > hdr.n_tiles) grid = hdr.n_tiles;
-    pass_kernel_async<T, NR, NO><<<(unsigned)grid, Cfg::kThreads, smem, stream>>>(state, dev_blob, rank_hi, mode | (getenv("QSV_SKIP_EXT") ? 8 : 0), params);
+    pass_kernel_async<T, NR, NO, FAST><<<(unsigned)grid, Cfg::kThreads, smem, stream>>>(state, dev_blob, rank_hi, mode | (getenv("QSV_SKIP_EXT") ? 8 : 0), params);
     return cudaGetLastError();
 }
 
 template <>
 cudaError_t launch_pass_async_tile<QSV_TILE_BITS>(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream) {
     const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
-    if (hdr.n_rounds <= (uint32_t)kSmallRounds && hdr.n_ops <= (uint32_t)kSmallOps)
-        return launch_async_t<QSV_TILE_BITS, kSmallRounds, kSmallOps>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
-    return launch_async_t<QSV_TILE_BITS, kMaxRounds, kMaxOps>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+    using Cfg = AsyncCfg<QSV_TILE_BITS>;
+    const bool small = hdr.n_rounds <= (uint32_t)kSmallRounds && hdr.n_ops <= (uint32_t)kSmallOps;
+    const size_t fast_smem = (size_t)Cfg::kBuffers * Cfg::kTileBytes + 128 + sizeof(cplx) * Cfg::kGroups * (hdr.n_diag + 1) + sizeof(cplx) * Cfg::kGroupThreads * hdr.n_diag;
+    static const bool no_fast = getenv("QSV_NO_FAST") != nullptr;  // developer A/B switch
+    if (!no_fast && small && (hdr.flags & PASS_UNCONDITIONAL) && fast_smem <= (size_t)227 * 1024 - 1024)
+        return launch_async_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, true>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+    if (small) return launch_async_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, false>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+    return launch_async_t<QSV_TILE_BITS, kMaxRounds, kMaxOps, false>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
 }
 
 }  // namespace qsv

@@ -460,6 +460,7 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
     bool conditional = false;
     for (const DevOp& d : ops) conditional |= d.cmask_thr != 0 || d.cmask_ext != 0;
     if (!conditional) hdr.flags |= PASS_UNCONDITIONAL;
+    for (const DevOp& d : ops) if (d.type == OP_DIAG && d.n_ext > hdr.max_ext) hdr.max_ext = d.n_ext;
     hdr.n_rounds = (uint32_t)rounds.size();
     hdr.n_ops = (uint32_t)ops.size();
     hdr.n_diag = n_diag;
@@ -516,7 +517,8 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
     plan.n_local = n_local;
     plan.n_alloc = std::max<uint32_t>(n_local, kMinQubits);
     plan.opt = opt_in;
-    plan.opt.tile_bits = std::max<int>(kRegBits, std::min<int>(opt_in.tile_bits, kMaxTileBits));
+    const int tile_bits_auto = plan.n_alloc >= 23 ? 11 : 12;  // measured on B200: 4 compute groups of 128 threads overlap better than 2 of 256
+    plan.opt.tile_bits = std::max<int>(kRegBits, std::min<int>(opt_in.tile_bits > 0 ? opt_in.tile_bits : tile_bits_auto, kMaxTileBits));
     plan.passes.clear();
     plan.steps.clear();
     plan.lops.clear();

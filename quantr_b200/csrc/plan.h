@@ -36,7 +36,7 @@ struct LOp {
 };
 
 struct PlanOptions {
-    int tile_bits = 12;
+    int tile_bits = 0;   // 0 = auto: 11 for registers the pipelined kernel serves (>= 2^23 local amplitudes), else 12
     int low_bits = 0;     // contiguous low index bits kept in every tile; 0 = chosen per circuit by the cost model
     int fuse = 1;
     int direct_store = 1; // last round stores registers straight to global memory when that stays coalesced

@@ -158,7 +158,7 @@ struct DevPass {
     uint32_t threads;         // CTA size = tile_threads(tile_bits)
     double final_scale;       // product of the deferred 1/sqrt2 factors of the pass's Hadamards
     uint32_t ext_ctrl_mask[3];// bit o set: op o has controls outside the tile (evaluated once per tile)
-    uint32_t pad;
+    uint32_t max_ext;         // largest DevOp::n_ext of the pass (stride of the shared-memory copy of the term lists)
     uint64_t pf_step;         // deposit(8 * threads, tile_segs): element offset between a thread's two L2-prefetch lines
     Seg tile_segs[kMaxSegs];  // tile-local index -> physical (local) offset
     Seg ext_segs[kMaxSegs];   // tile id -> physical (local) base
