@@ -38,17 +38,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// Spins on the phase with the given parity.  A wait that outlasts any legitimate tile load (about 2^22 timed-out
+// try_waits, seconds) traps, so a protocol error surfaces as a launch failure instead of a hung device.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins > (1u << 22)) __trap();
+    }
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -210,6 +217,9 @@ pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, ui
         // refill this buffer with the tile that will use it next (direct-store passes did so in their last round)
         if (!(direct && n_rounds && P.rounds[n_rounds - 1].type == ROUND_REG) && k + kNB < n_my) issue_load(k + kNB);
     }
+    // A group may run out of tiles while loads it issued for other groups are still in flight: their copies and
+    // mbarrier arrivals must not be abandoned by an exiting thread.
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 template <int T, int NR, int NO, bool FAST>

@@ -264,7 +264,7 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
         }
         if (st.kind == PlanStep::PASS) {
             QSV_CUDA(s, launch_pass(s->d_state, static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[st.pass_index], plan.passes[st.pass_index].data(),
-                                    rank_base(s), s->sm_count, s->stream));
+                                    rank_base(s), s->sm_count, s->world == 1, s->stream));
         } else {
             rc = run_exchange(s, st, &exch_ms);
             if (rc != QSV_OK) return rc;
