@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "kernels.h"
+#include "peer_swap.h"
 #include "pass_core.h"
 
 namespace qsv {
@@ -79,23 +80,6 @@ cudaError_t launch_gather(const cplx* state, const uint64_t* idx, cplx* out, uin
 // each rank of the pair moves one half of the block, reading the remote half over NVLink and writing its own
 // amplitudes back into the peer's memory with 128-bit loads/stores.
 // ---------------------------------------------------------------------------------------------
-struct SwapArgs {
-    uint64_t block_len;      // amplitudes per block: 2^(n_local - g)
-    uint64_t first, count;   // sub-range of the block handled by this rank
-    uint64_t local_spell;    // partner-bit pattern that spells the peer (in this rank's shard)
-    uint64_t remote_spell;   // partner-bit pattern that spells this rank (in the peer's shard)
-    uint32_t g;
-    uint8_t partner[8];      // ascending
-};
-
-__device__ __forceinline__ uint64_t insert_zero_bits(uint64_t j, const SwapArgs& a) {
-    for (uint32_t k = 0; k < a.g; ++k) {
-        const uint32_t p = a.partner[k];
-        j = ((j >> p) << (p + 1)) | (j & ((1ull << p) - 1ull));
-    }
-    return j;
-}
-
 __global__ void __launch_bounds__(256) peer_swap_kernel(cplx* __restrict__ local, cplx* __restrict__ remote, SwapArgs a) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j0 < a.count; j0 += 4 * stride) {
@@ -118,17 +102,7 @@ __global__ void __launch_bounds__(256) peer_swap_kernel(cplx* __restrict__ local
 }
 
 cudaError_t launch_peer_swap(cplx* local, cplx* remote, uint32_t n_local, const uint8_t* partner, uint32_t g, int rank, int peer, int sm_count, cudaStream_t stream) {
-    SwapArgs a{};
-    a.g = g;
-    a.block_len = (1ull << n_local) >> g;
-    for (uint32_t k = 0; k < g; ++k) {
-        a.partner[k] = partner[k];
-        if ((peer >> k) & 1) a.local_spell |= 1ull << partner[k];
-        if ((rank >> k) & 1) a.remote_spell |= 1ull << partner[k];
-    }
-    const uint64_t half = a.block_len / 2;  // the lower rank of the pair moves the first half, the higher rank the second
-    a.first = rank < peer ? 0 : half;
-    a.count = rank < peer ? half : a.block_len - half;
+    const SwapArgs a = make_swap_args(n_local, partner, g, rank, peer);
     if (a.count == 0) return cudaSuccess;
     uint64_t grid = (a.count + 256 * 4 - 1) / (256 * 4);
     const uint64_t cap = (uint64_t)sm_count * 8;

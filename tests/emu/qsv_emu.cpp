@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../quantr_b200/csrc/pass_core.h"
+#include "../../quantr_b200/csrc/peer_swap.h"
 #include "../../quantr_b200/csrc/plan_handle.h"
 
 using namespace qsv;
@@ -127,3 +128,23 @@ extern "C" int qsv_emu_run_pass(const qsv_plan* p, uint32_t pass_index, double* 
 }
 
 extern "C" uint32_t qsv_emu_alloc_qubits(const qsv_plan* p) { return p ? p->plan.n_alloc : 0; }
+
+// One EXCHANGE step the way the peer-memory path runs it (state_api.cu run_exchange + peer_swap_kernel): every rank,
+// for every step of the round-robin pairing, swaps its half of the pair's blocks in place.  shards[r] = rank r's amplitudes.
+extern "C" int qsv_emu_peer_exchange(double** shards, uint32_t n_local, const uint8_t* partner, uint32_t g) {
+    const int world = 1 << g;
+    for (int step = 1; step < world; ++step)
+        for (int rank = 0; rank < world; ++rank) {
+            const int peer = rank ^ step;
+            const SwapArgs a = make_swap_args(n_local, partner, g, rank, peer);
+            cplx* local = reinterpret_cast<cplx*>(shards[rank]);
+            cplx* remote = reinterpret_cast<cplx*>(shards[peer]);
+            for (uint64_t j = 0; j < a.count; ++j) {
+                const uint64_t idx = insert_zero_bits(a.first + j, a);
+                const cplx mine = local[idx | a.local_spell], theirs = remote[idx | a.remote_spell];
+                local[idx | a.local_spell] = theirs;
+                remote[idx | a.remote_spell] = mine;
+            }
+        }
+    return 0;
+}

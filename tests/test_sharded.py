@@ -153,3 +153,23 @@ def test_gloo_ranks_exchange_matches_oracle(world, n, tmp_path):
     reg[3] = 1
     ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense")
     assert np.max(np.abs(out - ref)) < 1e-12
+
+
+@pytest.mark.parametrize("g,n_local,partners", [(1, 5, [4]), (1, 6, [0]), (2, 6, [1, 4]), (2, 5, [3, 4]), (3, 7, [0, 3, 6]), (3, 6, [3, 4, 5])])
+def test_peer_memory_exchange_index_math(g, n_local, partners):
+    """The NVLink peer-memory exchange (peer_swap.h: what peer_swap_kernel runs per pair of ranks, walked here by the
+    emulation harness) against the reference semantics of an EXCHANGE step, at world sizes 2, 4 and 8."""
+    import ctypes as C
+    from helpers import emu_lib, exchange_bits_global
+    lib = emu_lib()
+    lib.qsv_emu_peer_exchange.restype = C.c_int
+    lib.qsv_emu_peer_exchange.argtypes = [C.POINTER(C.POINTER(C.c_double)), C.c_uint32, C.POINTER(C.c_uint8), C.c_uint32]
+    world = 1 << g
+    rng = np.random.default_rng(100 * g + n_local)
+    shards = [(rng.standard_normal(1 << n_local) + 1j * rng.standard_normal(1 << n_local)).astype(np.complex128) for _ in range(world)]
+    want = exchange_bits_global([s.copy() for s in shards], n_local, partners)
+    ptrs = (C.POINTER(C.c_double) * world)(*[s.ctypes.data_as(C.POINTER(C.c_double)) for s in shards])
+    part = (C.c_uint8 * g)(*partners)
+    assert lib.qsv_emu_peer_exchange(ptrs, n_local, part, g) == 0
+    for r in range(world):
+        assert np.array_equal(shards[r], want[r]), f"rank {r}"
