@@ -29,16 +29,17 @@ __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_
 // ---------------------------------------------------------------------------------------------
 // Fused pass: dispatch to the per-tile-size objects built from pass_kernel.cu.
 // ---------------------------------------------------------------------------------------------
-cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, bool pipelined_ok, cudaStream_t stream) {
+cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, bool single_process, cudaStream_t stream) {
     const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
     const uint32_t tile_bits = hdr.tile_bits;
     // The software-pipelined kernel (one CTA per SM, tiles prefetched with cp.async while the compute groups work)
     // serves large registers; QSV_ASYNC=0 forces the synchronous kernel, 2 the pipelined one at every size (tests).
     static const int use_async = getenv("QSV_ASYNC") ? atoi(getenv("QSV_ASYNC")) : 1;
-    // Measured envelope: passes of two or more rounds on single-process registers.  One-round passes
-    // hung intermittently in 2-GPU runs (an mbarrier phase that never completed; root cause open), so they and all
-    // sharded registers stay on the synchronous kernel, which reaches ~90% of HBM peak on one-round passes anyway.
-    const bool envelope = pipelined_ok && hdr.n_rounds >= 2 && hdr.n_tiles >= 16ull * (uint64_t)sm_count;
+    // Envelope: at least 16 tiles per SM.  One-round passes of sharded registers stay on the synchronous kernel: the
+    // pipelined kernel's one-round case (fixed in round 1) was re-validated on one GPU only.
+    static const int min_rounds_env = getenv("QSV_ASYNC_MIN_ROUNDS") ? atoi(getenv("QSV_ASYNC_MIN_ROUNDS")) : 0;
+    const uint32_t min_rounds = min_rounds_env > 0 ? (uint32_t)min_rounds_env : (single_process ? 1u : 2u);
+    const bool envelope = hdr.n_rounds >= min_rounds && hdr.n_tiles >= 16ull * (uint64_t)sm_count;
     if (use_async && (use_async >= 2 || envelope)) {  // 2: always (parity tests of the pipelined kernels on small registers)
         if (tile_bits == 12) return launch_pass_async_tile<12>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
         if (tile_bits == 11) return launch_pass_async_tile<11>(state, dev_blob, host_blob, rank_hi, sm_count, stream);

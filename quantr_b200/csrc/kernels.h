@@ -9,8 +9,8 @@ namespace qsv {
 
 // host_blob: the pass blob in host memory (its header/rounds/ops travel as kernel parameters);
 // dev_blob: the same blob in device memory (tables, external phase terms, Custom matrices).
-// pipelined_ok: the caller allows the software-pipelined kernel (see launch_pass in kernels.cu for when it is used)
-cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, bool pipelined_ok, cudaStream_t stream);
+// single_process: the register is not sharded (widens the envelope of the software-pipelined kernel, see kernels.cu)
+cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, bool single_process, cudaStream_t stream);
 // defined in pass_kernel.cu, one explicit specialisation per tile size (0 = runtime tile size <= 9 bits)
 template <int TILE_BITS>
 cudaError_t launch_pass_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream);

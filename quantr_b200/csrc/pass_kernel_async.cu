@@ -57,6 +57,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (spins > (1u << 22)) __trap();
     }
 }
+__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+// Spins until *p >= want (acquire); same watchdog as mbar_wait.
+__device__ __forceinline__ void wait_issued(const uint32_t* p, uint32_t want) {
+    const uint32_t addr = smem_u32(p);
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t v;
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+        if (v >= want) return;
+        if (spins > (1u << 24)) __trap();
+    }
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -77,9 +90,14 @@ pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, ui
     constexpr uint32_t kTileLen = 1u << T;
     constexpr int W = (NO + 31) / 32;
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: [kNB tiles][kNB mbarriers][64 bytes spare][per-group external phases][DIAG tables][external term lists]
+    // layout: [kNB tiles][kNB mbarriers][kNB issue counters][per-group external phases][DIAG tables][external term lists]
     cplx* tiles = reinterpret_cast<cplx*>(smem);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)kNB * Cfg::kTileBytes);
+    // issued[b] = number of tile loads issued into buffer b so far.  A consumer may only poll the buffer's mbarrier by
+    // parity once the load it waits for has been issued: a group can run two tiles ahead of the group that refills
+    // its next buffer, and a parity wait placed before that refill would be satisfied by the phase before last
+    // (same parity) - stale data, then a miscounted phase and a wait that never ends.
+    uint32_t* issued = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(full_bar) + 64);
     cplx* ext_all = reinterpret_cast<cplx*>(reinterpret_cast<uint8_t*>(full_bar) + 128);
     const uint32_t n_diag = P.hdr.n_diag;
     cplx* diag_smem = ext_all + (size_t)kG * (n_diag + 1);
@@ -104,10 +122,15 @@ pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, ui
 #pragma unroll
         for (uint32_t i = 0; i < (uint32_t)kSlots; ++i) cp_async16(tb + (soff_t ^ P.loads.soff[i]), gtile + P.loads.goff[i]);
         cp_async_arrive(&full_bar[slot]);
+        // published after the issuing group itself saw the buffer's previous phase complete (it consumed that tile)
+        if (gtid == 0) st_release_shared(&issued[slot], (uint32_t)(k / kNB) + 1u);
     };
 
     if (tid == 0) {
-        for (uint32_t b = 0; b < kNB; ++b) mbar_init(&full_bar[b], kGT);
+        for (uint32_t b = 0; b < kNB; ++b) {
+            mbar_init(&full_bar[b], kGT);
+            issued[b] = 0;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -162,7 +185,8 @@ pass_kernel_async(cplx* __restrict__ state, const uint8_t* __restrict__ blob, ui
 #pragma unroll
         for (int w = 0; w < W; ++w) act[w] = thr_act[w];
         tile_active_mask<W>(P.hdr, P.ops, base_full, act);
-        mbar_wait(&full_bar[slot], (uint32_t)((k / kNB) & 1));  // the tile has landed in shared memory
+        wait_issued(&issued[slot], (uint32_t)(k / kNB) + 1u);   // the load of this tile has been issued ...
+        mbar_wait(&full_bar[slot], (uint32_t)((k / kNB) & 1));  // ... and has landed in shared memory
         group_barrier(group, kGT);                              // ... and the external phases are written
 
         for (uint32_t r = 0; r < n_rounds; ++r) {
