@@ -517,14 +517,18 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
     plan.n_local = n_local;
     plan.n_alloc = std::max<uint32_t>(n_local, kMinQubits);
     plan.opt = opt_in;
-    const int tile_bits_auto = plan.n_alloc >= 23 ? 11 : 12;  // measured on B200: 4 compute groups of 128 threads overlap better than 2 of 256
-    plan.opt.tile_bits = std::max<int>(kRegBits, std::min<int>(opt_in.tile_bits > 0 ? opt_in.tile_bits : tile_bits_auto, kMaxTileBits));
     plan.passes.clear();
     plan.steps.clear();
     plan.lops.clear();
     plan.n_rounds = 0;
     lower_gates(n_qubits, ops, n_ops, plan.lops, &plan.n_gates);
     if (plan.opt.fuse) merge_diagonals(plan.lops);
+    // tile size: 11 for registers the pipelined kernel serves (measured on B200, DESIGN.md 6: four compute groups of
+    // 128 threads overlap better than two of 256), else 12; widened when a Custom gate needs more tile bits
+    int tile_bits_auto = plan.n_alloc >= 23 ? 11 : 12;
+    for (const LOp& lop : plan.lops)
+        if (lop.kind == LOp::DENSE) tile_bits_auto = std::max(tile_bits_auto, std::min<int>(popcnt(lop.targets()), kMaxTileBits));
+    plan.opt.tile_bits = std::max<int>(kRegBits, std::min<int>(opt_in.tile_bits > 0 ? opt_in.tile_bits : tile_bits_auto, kMaxTileBits));
 
     const int nloc = (int)plan.n_alloc;
     const int T = std::min<int>(plan.opt.tile_bits, nloc);
