@@ -201,8 +201,18 @@ def main():
         mine = torch.frombuffer(bytearray(state.peer_export()), dtype=torch.uint8).cuda()
         allh = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allh, mine)
-        state.peer_import([bytes(h.cpu().numpy().tobytes()) for h in allh])
-        exchange_path = "in-place swap kernels over peer-mapped memory (NVLink loads/stores)"
+        ok = 1
+        try:
+            state.peer_import([bytes(h.cpu().numpy().tobytes()) for h in allh])
+        except Exception as e:  # e.g. no peer access between two GPUs: every rank falls back together
+            ok = 0
+            print(f"[bench] rank {rank}: peer import failed ({e}); falling back to the NCCL transport", file=sys.stderr)
+        agree = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree.item()):
+            exchange_path = "in-place swap kernels over peer-mapped memory (NVLink loads/stores)"
+        elif ok:
+            state.peer_import([])
     if args.tile_bits:
         state.set_option("tile_bits", args.tile_bits)
     if args.low_bits:

@@ -155,6 +155,10 @@ class DeviceState:
         return buf.raw
 
     def peer_import(self, handles: list):
+        """Maps the peers' shards (entry r = rank r's `peer_export`).  An empty list drops the mappings again."""
+        if not handles:
+            F.check(self.lib.qsv_peer_import(self.handle, None, 0), self.handle)
+            return
         blob = b"".join(handles)
         buf = C.create_string_buffer(blob, len(blob))
         F.check(self.lib.qsv_peer_import(self.handle, buf, len(handles)), self.handle)

@@ -373,6 +373,14 @@ int qsv_peer_export(qsv_state* s, void* out_handle, size_t out_bytes) {
 int qsv_peer_import(qsv_state* s, const void* handles, size_t n_handles) {
     QSV_ENTER(s);
     if (!s->comm) return set_error(s, QSV_ERR_INVALID_ARG, "peer import needs a sharded handle");
+    if (n_handles == 0) {  // drop the peer mappings: remaps go through NCCL send/recv again
+        QSV_CUDA(s, cudaStreamSynchronize(s->stream));
+        for (int r = 0; r < (int)s->peer_ptr.size(); ++r)
+            if (r != s->rank && s->peer_ptr[r]) cudaIpcCloseMemHandle(s->peer_ptr[r]);
+        s->peer_ptr.clear();
+        return QSV_OK;
+    }
+    if (!s->peer_ptr.empty()) return set_error(s, QSV_ERR_INVALID_ARG, "peers already imported");
     if (!handles || n_handles != (size_t)s->world) return set_error(s, QSV_ERR_INVALID_ARG, "expected one handle per rank");
     std::vector<cplx*> ptrs(s->world, nullptr);
     for (int r = 0; r < s->world; ++r) {
