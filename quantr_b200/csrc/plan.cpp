@@ -266,8 +266,6 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
         loads.goff[i] = deposit((uint64_t)i * threads, hdr.tile_segs, hdr.n_tile_segs);
         loads.soff[i] = swz(i * threads) << 4;
     }
-    hdr.pf_step = (8ull * threads < (1ull << T)) ? deposit(8ull * threads, hdr.tile_segs, hdr.n_tile_segs) : 0;
-    if (plan.opt.l2_prefetch) hdr.flags |= PASS_L2_PREFETCH;
     uint32_t n_hadamard = 0;
 
     std::vector<DevRound> rounds;

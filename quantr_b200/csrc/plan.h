@@ -40,7 +40,6 @@ struct PlanOptions {
     int low_bits = 0;     // contiguous low index bits kept in every tile; 0 = chosen per circuit by the cost model
     int fuse = 1;
     int direct_store = 1; // last round stores registers straight to global memory when that stays coalesced
-    int l2_prefetch = 0;  // prefetch the CTA's next tile into L2 while the current one is processed
 };
 
 // One step of a plan: a fused pass over the local shard, or a global-qubit remap that swaps the index bits held in

@@ -71,7 +71,6 @@ constexpr int kDiagTblLen = 64;  // lo[32] (thread-index bits 0-4) + hi[32] (bit
 //         and is controlled by exactly that bit (one stage of a QFT / phase-estimation ladder)
 constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeHdBase = 53, kCodeCount = 61;
 enum PassFlags : uint32_t {
-    PASS_L2_PREFETCH = 1,
     PASS_DIRECT_STORE = 2,  // the last round writes its registers straight to global memory (coalesced: its register bits
                             // exclude the three lowest tile bits)
     PASS_UNCONDITIONAL = 4  // no op of the pass has a control among the thread or tile-index bits: every thread of every
@@ -159,7 +158,7 @@ struct DevPass {
     double final_scale;       // product of the deferred 1/sqrt2 factors of the pass's Hadamards
     uint32_t ext_ctrl_mask[3];// bit o set: op o has controls outside the tile (evaluated once per tile)
     uint32_t max_ext;         // largest DevOp::n_ext of the pass (stride of the shared-memory copy of the term lists)
-    uint64_t pf_step;         // deposit(8 * threads, tile_segs): element offset between a thread's two L2-prefetch lines
+    uint64_t reserved0;
     Seg tile_segs[kMaxSegs];  // tile-local index -> physical (local) offset
     Seg ext_segs[kMaxSegs];   // tile id -> physical (local) base
 };

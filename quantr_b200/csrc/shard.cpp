@@ -199,25 +199,11 @@ bool shard_exchange_bits(ShardComm* c, void* base, uint32_t n_local, const uint8
             }
         }
     }
+    // whatever follows on the comm's stream (the next pass) must see the last staging -> shard copies
+    for (int i = 0; i < 2; ++i)
+        if (slot_used[i] && cudaStreamWaitEvent(c->stream, c->copy_done[i], 0) != cudaSuccess) { err = "cudaStreamWaitEvent failed"; return false; }
     return true;
 }
 
-bool shard_exchange_slots(ShardComm* c, void* base, size_t slot_bytes, void* staging, size_t chunk_bytes, std::string& err) {
-    char* b = static_cast<char*>(base);
-    // Round-robin pairing (peer = rank ^ step) so every step is a perfect matching over NVSwitch.
-    for (int step = 1; step < c->world; ++step) {
-        const int peer = c->rank ^ step;
-        char* slot = b + (size_t)peer * slot_bytes;
-        for (size_t off = 0; off < slot_bytes; off += chunk_bytes) {
-            const size_t len = slot_bytes - off < chunk_bytes ? slot_bytes - off : chunk_bytes;
-            if (!nccl_ok(g_nccl.GroupStart(), "ncclGroupStart", err)) return false;
-            if (!nccl_ok(g_nccl.Send(slot + off, len, ncclUint8, peer, c->comm, c->stream), "ncclSend", err)) return false;
-            if (!nccl_ok(g_nccl.Recv(staging, len, ncclUint8, peer, c->comm, c->stream), "ncclRecv", err)) return false;
-            if (!nccl_ok(g_nccl.GroupEnd(), "ncclGroupEnd", err)) return false;
-            if (cudaMemcpyAsync(slot + off, staging, len, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { err = "staging copy failed"; return false; }
-        }
-    }
-    return true;
-}
 
 }  // namespace qsv

@@ -29,8 +29,5 @@ bool shard_allgather_f64(ShardComm* c, double value, double* out, std::string& e
 // (ascending).  Staged through two buffers of `staging_bytes` each.  Enqueued on the comm's stream.
 bool shard_exchange_bits(ShardComm* c, void* base, uint32_t n_local, const uint8_t* partner, uint32_t g, void* staging, size_t staging_bytes,
                          std::string& err);
-// In-place pairwise exchange: for every peer p != rank, the `slot_bytes` at `base + p*slot_bytes` are swapped with
-// the peer's slot `rank`.  Staged through `staging` (>= chunk_bytes) in chunks.  Enqueued on the comm's stream.
-bool shard_exchange_slots(ShardComm* c, void* base, size_t slot_bytes, void* staging, size_t chunk_bytes, std::string& err);
 
 }  // namespace qsv
