@@ -55,6 +55,18 @@ cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* hos
     }
 }
 
+bool pass_init_supported(const uint8_t* host_blob, int sm_count) {
+    const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
+    return (hdr.tile_bits == 11 || hdr.tile_bits == 12) && hdr.n_tiles >= (uint64_t)sm_count;
+}
+
+cudaError_t launch_pass_init(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, const PassInit& init, cudaStream_t stream) {
+    const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
+    if (hdr.tile_bits == 12) return launch_pass_init_tile<12>(state, dev_blob, host_blob, rank_hi, sm_count, init, stream);
+    if (hdr.tile_bits == 11) return launch_pass_init_tile<11>(state, dev_blob, host_blob, rank_hi, sm_count, init, stream);
+    return cudaErrorNotSupported;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K4: register access
 // ---------------------------------------------------------------------------------------------

@@ -5,6 +5,8 @@
 
 #include "qsv_types.h"
 
+namespace qsv { struct PassInit; }
+
 namespace qsv {
 
 // host_blob: the pass blob in host memory (its header/rounds/ops travel as kernel parameters);
@@ -18,6 +20,13 @@ cudaError_t launch_pass_tile(cplx* state, const uint8_t* dev_blob, const uint8_t
 // defined in pass_kernel_async.cu for TILE_BITS = 11 and 12: the software-pipelined (cp.async + mbarrier) variant
 template <int TILE_BITS>
 cudaError_t launch_pass_async_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream);
+
+// defined in pass_kernel_init.cu for TILE_BITS = 11 and 12: first pass of a plan with the basis-state initialisation fused in
+template <int TILE_BITS>
+cudaError_t launch_pass_init_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, const PassInit& init, cudaStream_t stream);
+// true when launch_pass_init serves this pass (tile size 11 or 12, at least one tile per SM)
+bool pass_init_supported(const uint8_t* host_blob, int sm_count);
+cudaError_t launch_pass_init(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, const PassInit& init, cudaStream_t stream);
 
 cudaError_t launch_set_amp(cplx* state, uint64_t index, double re, double im, cudaStream_t stream);
 // in-place swap of this rank's block 'spelled' peer with the peer's block 'spelled' rank (peer-mapped memory, NVLink)

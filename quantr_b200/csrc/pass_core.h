@@ -252,6 +252,25 @@ inline bool pass_is_fast(const DevPass& hdr) {
     return pass_smem_bytes(hdr.tile_bits, hdr.n_diag, 2) <= budget;
 }
 
+// Basis-state initialisation fused into the first pass of a plan: the pass does not read the register; every tile is
+// synthesised (all zero, except the one tile that holds the basis amplitude).
+//   mode 1: every tile is synthesised and computed;  mode 2: all-zero tiles are written as zeros without arithmetic
+//   (a linear pass maps a zero tile to a zero tile).
+struct PassInit {
+    uint64_t base_full;  // tile base (rank bits included) of the tile holding the basis amplitude
+    uint32_t local;      // its tile-local index
+    uint32_t mode;
+};
+inline PassInit make_pass_init(const DevPass& hdr, uint64_t phys_index, uint32_t n_local, uint32_t mode) {
+    const uint64_t local_mask = (1ull << n_local) - 1ull;
+    const uint64_t ext_mask = deposit(hdr.n_tiles - 1ull, hdr.ext_segs, hdr.n_ext_segs);
+    PassInit pi;
+    pi.base_full = (phys_index & local_mask & ext_mask) | (phys_index & ~local_mask);
+    pi.local = (uint32_t)extract(phys_index & local_mask, hdr.tile_segs, hdr.n_tile_segs);
+    pi.mode = mode;
+    return pi;
+}
+
 // Thread phase of a DIAG op: product of its lo/hi table entries for thread-group e (tile-independent).
 QSV_HD cplx diag_thread_phase(const DevOp& op, const cplx* tbl, uint32_t e) {
     cplx w{1.0, 0.0};

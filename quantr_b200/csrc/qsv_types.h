@@ -191,6 +191,13 @@ QSV_HD uint64_t deposit(uint64_t v, const Seg* segs, uint32_t n) {
     return r;
 }
 
+// inverse of deposit on the bits the segments cover
+QSV_HD uint64_t extract(uint64_t v, const Seg* segs, uint32_t n) {
+    uint64_t r = 0;
+    for (uint32_t i = 0; i < n; ++i) r |= ((v >> segs[i].dst_lo) & ((1ull << segs[i].width) - 1ull)) << segs[i].src_lo;
+    return r;
+}
+
 // Shared-memory swizzle of a tile-local index: XOR-folds every higher 3-bit group into the
 // 16-byte-unit bits so that any three index bits with distinct (position mod 3) spread a
 // quarter-warp's 128-bit accesses over all 32 banks.

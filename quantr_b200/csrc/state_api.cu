@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "pass_core.h"
 #include "plan.h"
 #include "plan_handle.h"
 #include "shard.h"
@@ -245,6 +246,18 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     } else if (memcmp(s->layout, plan.initial_layout.data(), s->n_qubits) != 0) {
         return set_error(s, QSV_ERR_INVALID_ARG, "the plan starts from a different qubit layout than the register is in");
     }
+    // QSV_FUSED_INIT=1|2 (opt-in, see pass_kernel_init.cu): a pending basis state is not written to HBM; the plan's first
+    // pass synthesises its tiles instead of reading the register (2: and writes all-zero tiles without arithmetic).
+    static const int fused_init_mode = getenv("QSV_FUSED_INIT") ? atoi(getenv("QSV_FUSED_INIT")) : 0;
+    bool fused_init = false;
+    PassInit pass_init{};
+    if (s->lazy_basis && fused_init_mode > 0 && !plan.steps.empty() && plan.steps[0].kind == PlanStep::PASS && s->n_alloc == s->n_local &&
+        pass_init_supported(plan.passes[plan.steps[0].pass_index].data(), s->sm_count)) {
+        const DevPass& h0 = *reinterpret_cast<const DevPass*>(plan.passes[plan.steps[0].pass_index].data());
+        pass_init = make_pass_init(h0, to_physical(s, s->lazy_index), s->n_local, fused_init_mode >= 2 ? 2u : 1u);
+        fused_init = true;
+        s->lazy_basis = false;
+    }
     int rc = materialize(s);
     if (rc != QSV_OK) return rc;
     rc = upload_plan(s, p);
@@ -262,7 +275,10 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
             cudaEventCreate(&e1);
             cudaEventRecord(e0, s->stream);
         }
-        if (st.kind == PlanStep::PASS) {
+        if (st.kind == PlanStep::PASS && i == 0 && fused_init) {
+            QSV_CUDA(s, launch_pass_init(s->d_state, static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[st.pass_index], plan.passes[st.pass_index].data(),
+                                         rank_base(s), s->sm_count, pass_init, s->stream));
+        } else if (st.kind == PlanStep::PASS) {
             QSV_CUDA(s, launch_pass(s->d_state, static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[st.pass_index], plan.passes[st.pass_index].data(),
                                     rank_base(s), s->sm_count, s->world == 1, s->stream));
         } else {

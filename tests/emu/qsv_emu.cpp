@@ -17,7 +17,7 @@
 
 using namespace qsv;
 
-static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
+static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const PassInit* init = nullptr) {
     static PassParams<kMaxRounds, kMaxOps> P;  // what the kernel receives by value
     if (!fill_params(blob, P)) return;
     constexpr int W = kMaxOps / 32;
@@ -51,11 +51,24 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi) {
     for (uint64_t t = 0; t < P.hdr.n_tiles; ++t) {
         const uint64_t base = deposit(t, P.hdr.ext_segs, P.hdr.n_ext_segs);
         const uint64_t base_full = base | rank_hi;
+        const bool holds = init && base_full == init->base_full;
+        if (init && init->mode == 2 && !holds) {  // fused initialisation, zero tile in -> zero tile out
+            for (uint32_t tid = 0; tid < threads; ++tid) {
+                const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, P.hdr.n_tile_segs);
+                for (uint32_t i = 0; i < n_loads; ++i)
+                    if (i * threads + tid < tile_len) state[base + goff_t + P.loads.goff[i]] = cplx{0.0, 0.0};
+            }
+            continue;
+        }
         for (uint32_t tid = 0; tid < threads; ++tid) {  // load phase exactly as the kernel addresses it
             const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, P.hdr.n_tile_segs);
             const uint32_t soff_t = swz(tid) << 4;
             for (uint32_t i = 0; i < n_loads; ++i)
-                if (i * threads + tid < tile_len) *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) = state[base + goff_t + P.loads.goff[i]];
+                if (i * threads + tid < tile_len) {
+                    cplx v = init ? cplx{(holds && i * threads + tid == init->local) ? 1.0 : 0.0, 0.0}  // synthesised, the register is not read
+                                  : state[base + goff_t + P.loads.goff[i]];
+                    *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) = v;
+                }
         }
         for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
             if (P.ops[o].type == OP_DIAG) ext_phase[P.ops[o].diag_index] = diag_ext_phase(P.ops[o], blob, base_full);
@@ -146,5 +159,26 @@ extern "C" int qsv_emu_peer_exchange(double** shards, uint32_t n_local, const ui
                 remote[idx | a.remote_spell] = mine;
             }
         }
+    return 0;
+}
+
+// A plan on a basis state with the initialisation fused into its first pass (state_api.cu, QSV_FUSED_INIT): `amps` is
+// never read by that pass.  phys_index = the basis index under the plan's initial layout, rank bits included.
+extern "C" int qsv_emu_run_plan_fused_init(const qsv_plan* p, double* amps, uint64_t rank, uint64_t phys_index, uint32_t mode) {
+    if (!p || !amps || p->plan.steps.empty() || p->plan.steps[0].kind != PlanStep::PASS) return 1;
+    for (const PlanStep& st : p->plan.steps)
+        if (st.kind != PlanStep::PASS) return 1;
+    const uint64_t rank_hi = rank << p->plan.n_local;
+    bool first = true;
+    for (const PlanStep& st : p->plan.steps) {
+        const uint8_t* blob = p->plan.passes[st.pass_index].data();
+        if (first) {
+            const PassInit pi = make_pass_init(*reinterpret_cast<const DevPass*>(blob), phys_index, p->plan.n_local, mode);
+            run_pass(blob, reinterpret_cast<cplx*>(amps), rank_hi, &pi);
+            first = false;
+        } else {
+            run_pass(blob, reinterpret_cast<cplx*>(amps), rank_hi);
+        }
+    }
     return 0;
 }

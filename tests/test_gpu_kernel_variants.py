@@ -22,3 +22,17 @@ def test_parity_suite_with_forced_kernel(mode, select):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k", select],
                        env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_fused_basis_initialisation(mode):
+    """Opt-in path (QSV_FUSED_INIT, pass_kernel_init.cu): written at the end of round 1 with no GPU time left, so it
+    is not part of the default suite yet - run with QSV_TEST_FUSED_INIT=1 to validate it on hardware."""
+    if os.environ.get("QSV_VARIANT_INNER"):
+        pytest.skip("inner run")
+    if not os.environ.get("QSV_TEST_FUSED_INIT"):
+        pytest.skip("opt-in: set QSV_TEST_FUSED_INIT=1")
+    env = dict(os.environ, QSV_VARIANT_INNER="1", QSV_FUSED_INIT=mode)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k", "qft_closed_form or layered or golden or random"],
+                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -135,3 +135,29 @@ def test_plan_errors():
     bad[0].kind = 99
     with pytest.raises(F.QsvError):
         qb.Plan(3, fake)
+
+
+@pytest.mark.parametrize("n,tile_bits,low_bits", [(6, 5, 2), (9, 7, 3), (13, 12, 0), (14, 11, 3), (12, 8, 0)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_basis_initialisation_fused_into_the_first_pass(n, tile_bits, low_bits, mode):
+    """Fused initialisation (pass_core.h PassInit): the first pass synthesises its tiles instead of reading the register
+    (mode 2 also writes all-zero tiles without arithmetic).  The buffer starts as NaN to prove it is never read."""
+    import ctypes as C
+    from helpers import emu_lib
+    lib = emu_lib()
+    lib.qsv_emu_run_plan_fused_init.restype = C.c_int
+    lib.qsv_emu_run_plan_fused_init.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint64, C.c_uint64, C.c_uint32]
+    rng = np.random.default_rng(n * 10 + mode)
+    for trial in range(3):
+        x = int(rng.integers(0, 1 << n))
+        c = qft_circuit(OracleCircuit, G, n) if trial == 0 else random_any_gate_circuit(OracleCircuit, G, n, 40, rng)
+        enc = encode_gates(c.circuit_gates, n)
+        reg = np.zeros(1 << n, dtype=np.complex128)
+        reg[x] = 1.0
+        ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense", threads=2)
+        plan = qb.Plan(n, enc, tile_bits=tile_bits, low_bits=low_bits, lib=lib)
+        n_alloc = lib.qsv_emu_alloc_qubits(plan.handle)
+        amps = np.full(1 << n_alloc, np.nan + 1j * np.nan, dtype=np.complex128)
+        assert lib.qsv_emu_run_plan_fused_init(plan.handle, amps.ctypes.data_as(C.POINTER(C.c_double)), 0, x, mode) == 0
+        assert np.max(np.abs(amps[:1 << n] - ref)) < 1e-12
+        plan.close()
