@@ -302,7 +302,10 @@ def main():
 
     peak, peak_src = read_peaks()
     bytes_per_pass = 32.0 * float(1 << n_local)
-    achieved = bytes_per_pass * passes * args.steps / (passes_ms * 1e-3) / 1e9
+    # QSV_FUSED_INIT (opt-in): the first pass synthesises its input instead of reading it - it moves half the bytes
+    fused_init = int(os.environ.get("QSV_FUSED_INIT", "0") or 0)
+    passes_bytes = bytes_per_pass * (passes - 0.5 if fused_init and passes else passes)
+    achieved = passes_bytes * args.steps / (passes_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -311,7 +314,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "pass_kernel (fused tile pass)", "algorithmic_bytes_per_launch": bytes_per_pass,
+                "kernel": "pass_kernel (fused tile pass)", "algorithmic_bytes_per_launch": passes_bytes / passes if passes else bytes_per_pass,
                 "avg_launch_ms": passes_ms / (passes * args.steps), "peak_source": peak_src, "per_gpu": True}
 
     if rank == 0:
@@ -327,10 +330,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"QFT-{n} complex f64, |x=0x{x:x}> -> {n_gates} gates (H + CRk, no final swaps)", "qubits": n,
-                       "local_qubits": n_local, "state_bytes_per_gpu": 16 << n_local, "l2_policy": "state >> 126 MB L2 (no flush needed)",
+                       "local_qubits": n_local, "state_bytes_per_gpu": 16 << n_local, "l2_policy": "state >> 126 MB L2 (no flush needed)", "init": ("fused into the first pass (mode %d)" % fused_init) if fused_init else "memset + set_amp before the first pass",
                        "tile_bits": pdesc["tile_bits"], "low_bits": pdesc["low_bits"], "parallelism": f"shard{world}"},
             "qft_wall_time_ms": ms_per_step, "fused_passes": passes, "passes_per_gate": passes / n_gates,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int((passes + 1) * args.steps),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int((passes + (0 if fused_init else 1) + (pstats["n_exchanges"] * (world - 1) if exchange_path.startswith("in-place") else 0)) * args.steps),
             "exchange": None if world == 1 else {
                 "remaps_per_step": pstats["n_exchanges"], "bytes_sent_per_gpu_per_step": pstats["exchange_bytes"],
                 "ms_per_step": exchange_ms / args.steps,
