@@ -139,6 +139,41 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def setup_peer_exchange(state, dist, world, rank, device):
+    """Direct NVLink exchange: all-gather the shards' IPC handles (torch is plumbing only) and map the peers.  Every
+    rank ends in the same mode: if any rank cannot export or import, all of them stay on / return to the NCCL transport.
+    Returns True when the peer-memory transport is active."""
+    import torch
+    ok = 1
+    try:
+        handle = state.peer_export()
+    except Exception as e:  # e.g. CUDA IPC unavailable in this container
+        ok, handle = 0, bytes(64)
+        print(f"[bench] rank {rank}: peer export failed ({e}); falling back to the NCCL transport", file=sys.stderr)
+    mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(device)
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    exported = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(exported, op=dist.ReduceOp.MIN)
+    imported = False
+    if int(exported.item()):
+        try:
+            state.peer_import([bytes(h.cpu().numpy().tobytes()) for h in allh])
+            imported = True
+        except Exception as e:  # e.g. no peer access between two GPUs
+            ok = 0
+            print(f"[bench] rank {rank}: peer import failed ({e}); falling back to the NCCL transport", file=sys.stderr)
+    else:
+        ok = 0
+    agree = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+    if int(agree.item()):
+        return True
+    if imported:
+        state.peer_import([])
+    return False
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,22 +232,8 @@ def main():
     state = qb.DeviceState(n, local_rank, rank=rank, world=world, nccl_id=nccl_id)
     exchange_path = "nccl send/recv through staging"
     if world > 1 and not os.environ.get("QSV_NCCL_EXCHANGE"):
-        # direct NVLink exchange: all-gather the shards' IPC handles (torch is plumbing only) and map the peers
-        mine = torch.frombuffer(bytearray(state.peer_export()), dtype=torch.uint8).cuda()
-        allh = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allh, mine)
-        ok = 1
-        try:
-            state.peer_import([bytes(h.cpu().numpy().tobytes()) for h in allh])
-        except Exception as e:  # e.g. no peer access between two GPUs: every rank falls back together
-            ok = 0
-            print(f"[bench] rank {rank}: peer import failed ({e}); falling back to the NCCL transport", file=sys.stderr)
-        agree = torch.tensor([ok], dtype=torch.int32, device="cuda")
-        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
-        if int(agree.item()):
+        if setup_peer_exchange(state, dist, world, rank, torch.device("cuda", local_rank)):
             exchange_path = "in-place swap kernels over peer-mapped memory (NVLink loads/stores)"
-        elif ok:
-            state.peer_import([])
     if args.tile_bits:
         state.set_option("tile_bits", args.tile_bits)
     if args.low_bits:
