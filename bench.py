@@ -363,6 +363,10 @@ def main():
             "clocks": clocks.summary(), "max_abs_err_vs_closed_form": max_err, "norm_sqr": norm,
         }
         print(json.dumps(line), flush=True)
+    if world > 1:
+        # importers unmap their peers before any exporter frees its shard (CUDA IPC teardown order)
+        state.peer_import([])
+        dist.barrier()
     state.close()
     if world > 1:
         dist.destroy_process_group()

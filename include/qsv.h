@@ -149,7 +149,9 @@ int qsv_nccl_unique_id(void* out, size_t out_bytes);
  * world x 64 bytes, entry r = rank r's export).  Afterwards global-qubit remaps swap amplitudes in place through
  * peer-mapped memory (one kernel per peer, loads/stores over NVLink) instead of NCCL send/recv through staging.
  * Every rank of the communicator must be in the same mode when a remap runs: if any rank's import fails, all ranks
- * call qsv_peer_import(s, NULL, 0), which drops the mappings and returns to the NCCL transport. */
+ * call qsv_peer_import(s, NULL, 0), which drops the mappings and returns to the NCCL transport.  Teardown order (CUDA
+ * IPC): every rank drops its mappings (qsv_peer_import(s, NULL, 0) or qsv_destroy) before any rank's shard is freed -
+ * drop, synchronise the ranks, then destroy. */
 #define QSV_PEER_HANDLE_BYTES 64
 int qsv_peer_export(qsv_state* s, void* out_handle, size_t out_bytes);
 int qsv_peer_import(qsv_state* s, const void* handles, size_t n_handles);

@@ -75,6 +75,8 @@ def _worker(rank, world, port, result_dir):
     st2 = s2.apply(enc2)
     results["rand"] = s2.gather(np.arange(1 << n2, dtype=np.uint64))
     results["rand_exchanges"] = st2["n_exchanges"]
+    s2.peer_import([])  # importers unmap their peers before any exporter frees its shard (CUDA IPC teardown order)
+    dist.barrier()
     s2.close()
     if rank == 0:
         np.savez(os.path.join(result_dir, "out.npz"), **results)
