@@ -329,7 +329,7 @@ def main():
     achieved = passes_bytes * args.steps / (passes_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and n_local == 33:  # the committed capture is per launch at 2^33 amplitudes per GPU
         try:
             traffic = json.load(open(tpath)).get("pass_kernel_dram_bytes_per_launch")
         except Exception:
