@@ -32,6 +32,7 @@
 #include <cstdint>
 #include <cstring>
 #include <thread>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -286,31 +287,50 @@ void apply_gate_dense(uint32_t n, const qsv_op& op, uint32_t op_index, C64* reg,
         for (size_t b = a + 1; b < sorted_bits.size(); ++b)
             if (sorted_bits[b] < sorted_bits[a]) std::swap(sorted_bits[a], sorted_bits[b]);
     const int nthreads = threads > 0 ? threads : 1;
-    auto worker = [&](int tid) {
-        std::vector<C64> in(dim), out(dim);
-        std::vector<uint8_t> seen(dim);
+    // r enumerates a group's members in ascending canonical index (by sorted bit positions); s_of_r[r] = its sub-state
+    std::vector<uint32_t> s_of_r(dim);
+    for (uint64_t r = 0; r < dim; ++r) {
+        uint64_t o = 0;
+        for (int e = 0; e < k; ++e) if ((r >> e) & 1) o |= 1ull << sorted_bits[e];
+        uint64_t s = 0;
+        for (int e = 0; e < k; ++e) s = (s << 1) | ((o >> bit[e]) & 1);
+        s_of_r[r] = (uint32_t)s;
+    }
+    // Accumulate in ascending canonical index of the inputs (the order the reference's iterator visits them).
+    // `DIM` > 0: compile-time group size for the standard 1/2/3-wire gates (same operations, fixed-size buffers).
+    auto run_groups = [&](auto dim_tag, int tid) {
+        constexpr uint64_t DIM = decltype(dim_tag)::value;
+        const uint64_t d = DIM ? DIM : dim;
+        C64 in_fix[DIM ? DIM : 1], out_fix[DIM ? DIM : 1];
+        uint8_t seen_fix[DIM ? DIM : 1];
+        std::vector<C64> in_v(DIM ? 0 : dim), out_v(DIM ? 0 : dim);
+        std::vector<uint8_t> seen_v(DIM ? 0 : dim);
+        C64* in = DIM ? in_fix : in_v.data();
+        C64* out = DIM ? out_fix : out_v.data();
+        uint8_t* seen = DIM ? seen_fix : seen_v.data();
         const uint64_t g0 = groups * (uint64_t)tid / (uint64_t)nthreads, g1 = groups * (uint64_t)(tid + 1) / (uint64_t)nthreads;
         for (uint64_t g = g0; g < g1; ++g) {
             uint64_t base = g;
             for (int b : sorted_bits) base = ((base >> b) << (b + 1)) | (base & ((1ull << b) - 1));
-            for (uint64_t s = 0; s < dim; ++s) { in[s] = reg[base | offs[s]]; seen[s] = 0; out[s] = ZERO; }
-            // Accumulate in ascending canonical index of the inputs (the order the reference's
-            // iterator visits them): r enumerates the group's members by their sorted bit positions.
-            for (uint64_t r = 0; r < dim; ++r) {
-                uint64_t o = 0;
-                for (int e = 0; e < k; ++e) if ((r >> e) & 1) o |= 1ull << sorted_bits[e];
-                uint64_t s = 0;
-                for (int e = 0; e < k; ++e) s = (s << 1) | ((o >> bit[e]) & 1);
+            for (uint64_t s = 0; s < d; ++s) { in[s] = reg[base | offs[s]]; seen[s] = 0; out[s] = ZERO; }
+            for (uint64_t r = 0; r < d; ++r) {
+                const uint64_t s = s_of_r[r];
                 if (none[s]) continue;
-                const C64* col = &cols[s * dim];
-                for (uint64_t t = 0; t < dim; ++t) {
+                const C64* col = &cols[s * d];
+                for (uint64_t t = 0; t < d; ++t) {
                     const C64 c = cmul(col[t], in[s]);
                     if (!seen[t]) { out[t] = c; seen[t] = 1; } else out[t] = cadd(out[t], c);
                 }
             }
-            for (uint64_t s = 0; s < dim; ++s) if (none[s]) out[s] = in[s];  // None-overwrite, simulation.rs:126-133
-            for (uint64_t s = 0; s < dim; ++s) reg[base | offs[s]] = out[s];
+            for (uint64_t s = 0; s < d; ++s) if (none[s]) out[s] = in[s];  // None-overwrite, simulation.rs:126-133
+            for (uint64_t s = 0; s < d; ++s) reg[base | offs[s]] = out[s];
         }
+    };
+    auto worker = [&](int tid) {
+        if (k == 1) run_groups(std::integral_constant<uint64_t, 2>(), tid);
+        else if (k == 2) run_groups(std::integral_constant<uint64_t, 4>(), tid);
+        else if (k == 3) run_groups(std::integral_constant<uint64_t, 8>(), tid);
+        else run_groups(std::integral_constant<uint64_t, 0>(), tid);
     };
     if (nthreads == 1) { worker(0); return; }
     std::vector<std::thread> pool;

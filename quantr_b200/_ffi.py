@@ -21,6 +21,7 @@ LIB_PATH = os.environ.get("QSV_LIB", os.path.join(_HERE, "libqsv.so"))  # QSV_LI
 
 ERR_NAMES = {0: "ok", 1: "invalid argument", 2: "out of memory", 3: "CUDA error", 4: "NCCL error",
              5: "unsupported", 6: "internal error"}
+(ERR_INVALID_ARG, ERR_OUT_OF_MEMORY, ERR_CUDA, ERR_NCCL, ERR_UNSUPPORTED, ERR_INTERNAL) = range(1, 7)
 UINT64_MAX = (1 << 64) - 1
 
 
@@ -136,7 +137,10 @@ def check(code, handle=None):
         raise QsvError(code, msg.decode() if msg else "")
 
 
-def check_plan(code):
+def check_plan(code, lib=None):
+    """`lib`: the library that built the plan (the host-emulation harness of the tests keeps its own error text)."""
     if code != 0:
-        msg = load_library().qsv_plan_last_error()
+        lib = lib or load_library()
+        lib.qsv_plan_last_error.restype = C.c_char_p
+        msg = lib.qsv_plan_last_error()
         raise QsvError(code, msg.decode() if msg else "")

@@ -237,7 +237,7 @@ class Plan:
         if layout is not None:
             lay = (C.c_uint8 * n_qubits)(*[int(x) for x in layout])
         F.check_plan(self.lib.qsv_plan_create_ex(C.byref(self.handle), n_qubits, self.n_local, enc.ops, enc.n_ops, tile_bits, low_bits,
-                                                 1 if fuse else 0, lay, 1 if free_layout else 0))
+                                                 1 if fuse else 0, lay, 1 if free_layout else 0), self.lib)
 
     def close(self):
         if getattr(self, "handle", None) and self.handle.value:
@@ -455,6 +455,9 @@ class SimulatedCircuit:
         return Measurement.Observable(bin_count)
 
     def measure_all_without_cache(self, shots: int) -> Measurement:  # simulated_circuit.rs:81-114
+        if shots < 1:
+            # upstream evaluates `0..shots - 1` on a usize: a panic (debug) or a wrapped, endless loop (release)
+            raise QuantrError("measure_all_without_cache needs at least one shot (shots - 1 underflows upstream, simulated_circuit.rs:91).")
         bin_count: dict = {}
         self._bin_samples(self._state.sample(_rng.random(1)), bin_count)
         if self.config_progress:

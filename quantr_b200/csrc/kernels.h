@@ -3,9 +3,28 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "qsv_types.h"
 
 namespace qsv { struct PassInit; }
+
+namespace qsv {
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: opt in once per (kernel, device).  `mask` is a
+// per-kernel static; bit d = done on device d.  Thread-safe (a lost race repeats an idempotent call).
+template <class Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<uint64_t>& mask) {
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (err != cudaSuccess) return err;
+    mask.fetch_or(bit, std::memory_order_release);
+    return cudaSuccess;
+}
+}  // namespace qsv
 
 namespace qsv {
 

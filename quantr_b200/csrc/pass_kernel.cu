@@ -155,7 +155,9 @@ pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t
 
 template <int T_STATIC, int NR, int NO, bool FAST>
 static cudaError_t launch_pass_t(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream) {
-    static PassParams<NR, NO> params;  // zero-initialised; only the used prefix of rounds/ops is rewritten per launch
+    // one staging buffer per host thread (handles may be driven from different threads, include/qsv.h); zero-initialised,
+    // only the used prefix of rounds/ops is rewritten per launch
+    static thread_local PassParams<NR, NO> params;
     if (!fill_params(host_blob, params)) return cudaErrorInvalidValue;
     const DevPass& hdr = params.hdr;
     constexpr uint32_t kThreads = TileCfg<T_STATIC>::kThreads;
@@ -165,17 +167,15 @@ static cudaError_t launch_pass_t(cplx* state, const uint8_t* dev_blob, const uin
     if (mode > mode_cap) mode = mode_cap;
     if (FAST) mode = hdr.n_diag ? 2 : 0;
     const size_t smem = pass_smem_bytes(hdr.tile_bits, hdr.n_diag, mode);
-    static size_t smem_cfg = 0;
-    if (smem_cfg == 0) {
-        smem_cfg = (size_t)(227 * 1024) - 1024;  // opt-in maximum; the per-launch size decides the occupancy
-        cudaError_t err = cudaFuncSetAttribute(pass_kernel<T_STATIC, NR, NO, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cfg);
-        if (err != cudaSuccess) return err;
-    }
+    constexpr size_t smem_cfg = (size_t)(227 * 1024) - 1024;  // opt-in maximum; the per-launch size decides the occupancy
+    static std::atomic<uint64_t> configured{0};
+    cudaError_t err = ensure_dynamic_smem(pass_kernel<T_STATIC, NR, NO, FAST>, (int)smem_cfg, configured);
+    if (err != cudaSuccess) return err;
     if (smem > smem_cfg) return cudaErrorInvalidValue;
     static const size_t pad = getenv("QSV_SMEM_PAD") ? (size_t)atol(getenv("QSV_SMEM_PAD")) : 0;  // occupancy experiments
     const size_t smem_launch = (smem + pad <= smem_cfg) ? smem + pad : smem;
     int nb = 0;
-    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pass_kernel<T_STATIC, NR, NO, FAST>, (int)kThreads, smem_launch);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pass_kernel<T_STATIC, NR, NO, FAST>, (int)kThreads, smem_launch);
     if (err != cudaSuccess) return err;
     uint64_t grid = (uint64_t)sm_count * (uint64_t)(nb > 0 ? nb : 1);
     if (grid > hdr.n_tiles) grid = hdr.n_tiles;

@@ -511,6 +511,8 @@ static LOp remap_lop(const LOp& in, const std::vector<uint8_t>& layout) {
 void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* ops, size_t n_ops, const PlanOptions& opt_in,
                 const uint8_t* initial_layout, bool free_layout) {
     if (n_local == 0 || n_local > n_qubits) fail("n_local_qubits must be in 1..n_qubits");
+    // shards below 2^kMinQubits amplitudes are padded with idle index bits, which would collide with the rank bits
+    if (n_local < n_qubits && n_local < (uint32_t)kMinQubits) fail("sharded registers need at least " + std::to_string(kMinQubits) + " qubits per rank");
     plan.n_qubits = n_qubits;
     plan.n_local = n_local;
     plan.n_alloc = std::max<uint32_t>(n_local, kMinQubits);
@@ -689,9 +691,10 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
         // needed as targets furthest in the future (Belady), preferring high positions so the exchanged chunks are large.
         std::vector<int> logical_at(n, -1);
         for (int b = 0; b < n; ++b) logical_at[layout[b]] = b;
-        const int min_partner = std::max(0, (int)n_local - 10);
+        // candidates: the top 10 local bits (large exchanged chunks); widened downwards if those do not suffice (wide
+        // Custom gates, tiny shards)
         std::vector<std::pair<size_t, int>> cand;  // (next use, physical position)
-        for (int p = min_partner; p < (int)n_local; ++p) {
+        for (int p = (int)n_local - 1; p >= 0 && (p >= (int)n_local - 10 || (int)cand.size() < g); --p) {
             const int lb = logical_at[p];
             if ((tg >> lb) & 1) continue;  // needed right now
             cand.push_back({next_target_use(lb, i), p});

@@ -44,7 +44,8 @@ int qsv_plan_create_ex(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubit
         const bool unsupported = g_plan_error.find("not supported") != std::string::npos ||
                                  g_plan_error.find("cannot bring") != std::string::npos ||
                                  g_plan_error.find("needs more qubits") != std::string::npos ||
-                                 g_plan_error.find("wider than the tile") != std::string::npos;
+                                 g_plan_error.find("wider than the tile") != std::string::npos ||
+                                 g_plan_error.find("qubits per rank") != std::string::npos;
         return unsupported ? QSV_ERR_UNSUPPORTED : QSV_ERR_INVALID_ARG;
     } catch (...) {
         g_plan_error = "unknown error";

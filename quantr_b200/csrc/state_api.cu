@@ -124,6 +124,7 @@ int create_common(qsv_state** out, uint32_t n_qubits, int device, int rank, int 
     while ((1 << g) < world) ++g;
     if (world < 1 || (1 << g) != world || rank < 0 || rank >= world) return set_error(nullptr, QSV_ERR_INVALID_ARG, "world must be a power of two and 0 <= rank < world");
     if (g >= n_qubits) return set_error(nullptr, QSV_ERR_INVALID_ARG, "more ranks than amplitudes");
+    if (g > 0 && n_qubits - g < (uint32_t)kMinQubits) return set_error(nullptr, QSV_ERR_UNSUPPORTED, "sharded registers need at least %d qubits per rank", kMinQubits);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {

@@ -287,6 +287,7 @@ def emu_simulate_sharded(n, enc, world, *, basis_index=0, register=None, tile_bi
     nl = n - g
     plan = qb.Plan(n, enc, n_local=nl, tile_bits=tile_bits, low_bits=low_bits, free_layout=register is None, lib=lib)
     lay0, lay1 = plan.layout(False), plan.layout(True)
+    assert lib.qsv_emu_alloc_qubits(plan.handle) == nl  # shards are never padded (sharded registers need >= 4 local qubits)
     full = np.zeros(1 << n, dtype=np.complex128)
     if register is None:
         full[logical_to_physical(basis_index, lay0)] = 1.0

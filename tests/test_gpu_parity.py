@@ -207,6 +207,131 @@ def test_post_select_example_and_measure_all_without_cache():
     assert set(k.to_string() for k in bins) <= {"00", "10"} and sum(bins.values()) == 40
 
 
+def _none_on_zero_closure(prod):
+    """None on |..0>, (|..0>+|..1>)/sqrt2 on |..1> of the LAST qubit of the sub-state: the untouched state |0> is also
+    part of the image of |1>, the case where the reference's overwrite rule (simulation.rs:120-133) differs from a
+    linear map."""
+    q = prod.get_qubits()
+    if q[-1] == st.Qubit.Zero:
+        return None
+    amps = np.zeros(1 << len(q), dtype=np.complex128)
+    base = 0
+    for b in q[:-1]:
+        base = (base << 1) | (1 if b == st.Qubit.One else 0)
+    amps[base << 1] = amps[(base << 1) | 1] = np.sqrt(0.5)
+    return st.SuperPosition.new_with_amplitudes_unchecked(amps)
+
+
+def test_none_overwrite_rule_on_device():
+    """App. B.4 on the GPU: input (|0>+|1>)/sqrt2 -> [0.7071, 0.5] (the additive reading would give [1.2071, 0.5])."""
+    c = Circuit.new(1)
+    c.add_gate(G.H, 0).add_gate(G.Custom(_none_on_zero_closure, [], "N"), 0)
+    sim = c.simulate()
+    assert np.max(np.abs(sim.get_state().take().get_amplitudes() - np.array([np.sqrt(0.5), 0.5]))) < 1e-15
+
+
+@pytest.mark.parametrize("tile_bits", [8, 13])
+def test_none_overwrite_rule_three_wire_custom_at_n12(tile_bits):
+    """The same closure as a 3-wire Custom (two controls) inside a 12-qubit random circuit, device vs the oracle's
+    faithful restatement of simulation.rs:120-133, for a tile smaller than and as large as the register."""
+    n = 12
+    rng = np.random.default_rng(1204)
+    c = random_any_gate_circuit(OracleCircuit, G, n, 30, rng)
+    c.add_gate(G.Custom(_none_on_zero_closure, [3, 9], "N3"), 6)
+    for w in (0, 5, 11):
+        c.add_gate(G.Ry(0.3 + w), w)
+    c.add_gate(G.Custom(_none_on_zero_closure, [11, 0], "N3b"), 4)
+    enc = encode_gates(c.circuit_gates, n)
+    reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    reg /= np.linalg.norm(reg)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="faithful")
+    assert np.max(np.abs(orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense") - ref)) < 1e-14
+    out, _ = device_run(n, enc, reg, tile_bits=tile_bits)
+    assert np.max(np.abs(out - ref)) < TOL
+
+
+def test_config3_depth100_live_oracle():
+    """BASELINE config 3's generator at its full depth (100 layers) against the live dense oracle at n = 22."""
+    import os
+    n = 22
+    c = random_layered_circuit(OracleCircuit, G, n, 100, seed=30)
+    enc = encode_gates(c.circuit_gates, n)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, None, mode="dense", threads=os.cpu_count() or 1)
+    out, stats = device_run(n, enc)
+    assert np.max(np.abs(out - ref)) < TOL
+    assert stats["n_gates"] == enc.n_ops
+
+
+@pytest.mark.parametrize("n", [26, 28])
+def test_config3_depth100_against_oracle_fixture(n):
+    """Config 3 at depth 100 and n = 26 / 28: 4,096 amplitudes + norm against the dense oracle's result, computed once
+    by tests/golden/make_config3_fixtures.py (the oracle needs ~7 / ~30 minutes at these sizes) and committed."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"config3_n{n}_d100.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"fixture {path} not generated")
+    fx = np.load(path)
+    c = random_layered_circuit(OracleCircuit, G, n, 100, seed=30)
+    enc = encode_gates(c.circuit_gates, n)
+    assert enc.n_ops == int(fx["n_gates"])
+    s = qb.DeviceState(n)
+    s.apply(enc)
+    got = s.gather(fx["indices"])
+    assert np.max(np.abs(got - fx["amps"])) < TOL
+    assert abs(s.norm_sqr() - float(fx["norm_sqr"])) < 1e-11
+    s.close()
+
+
+def test_config3_full_size_three_schedules_agree():
+    """Config 3 at its stated size (n = 30, depth 100, 4,000 gates; 16 GiB register): no CPU result can exist, so three
+    independent schedules (tile 11, tile 12, one gate per pass) must agree on 4,096 gathered amplitudes and the norm."""
+    n = 30
+    c = random_layered_circuit(OracleCircuit, G, n, 100, seed=30)
+    enc = encode_gates(c.circuit_gates, n)
+    assert enc.n_ops == 4000
+    idx = np.random.default_rng(30).integers(0, 1 << n, size=4096, dtype=np.uint64)
+    results = []
+    for opts in ({"tile_bits": 11}, {"tile_bits": 12}, {"fuse": 0}):
+        s = qb.DeviceState(n)
+        for k, v in opts.items():
+            s.set_option(k, v)
+        s.apply(enc)
+        results.append((s.gather(idx), s.norm_sqr()))
+        s.close()
+    for got, norm in results:
+        assert abs(norm - 1.0) < 1e-11
+        assert np.max(np.abs(got - results[0][0])) < TOL
+
+
+def test_two_handles_from_two_threads():
+    """include/qsv.h: different handles may be used from different threads.  Two threads each run their own
+    circuits (different tile sizes, so different kernel instantiations and launch parameters) against the oracle."""
+    import threading
+    errors = []
+
+    def work(seed, tile_bits):
+        try:
+            rng = np.random.default_rng(seed)
+            for it in range(6):
+                n = 14 + (it % 3)
+                c = random_any_gate_circuit(OracleCircuit, G, n, 120, rng)
+                enc = encode_gates(c.circuit_gates, n)
+                ref = orc.simulate(n, enc.ops, enc.n_ops, None, mode="dense")
+                out, _ = device_run(n, enc, None, tile_bits=tile_bits)
+                err = float(np.max(np.abs(out - ref)))
+                if err >= TOL:
+                    errors.append((seed, it, err))
+        except Exception as e:  # noqa: BLE001
+            errors.append((seed, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(s, t)) for s, t in ((1, 10), (2, 12), (3, 11), (4, 10))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_plan_rerun_and_range_access():
     n = 18
     c = qft_circuit(OracleCircuit, G, n)

@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import pytest
 
-from helpers import (OracleCircuit, emu_simulate_sharded, encode_gates, orc, qb, qft_circuit, qft_expected,
+from helpers import (OracleCircuit, emu_lib, emu_simulate_sharded, encode_gates, orc, qb, qft_circuit, qft_expected,
                      random_any_gate_circuit, random_layered_circuit)
 from quantr_b200 import _ffi as F
 
@@ -173,3 +173,27 @@ def test_peer_memory_exchange_index_math(g, n_local, partners):
     assert lib.qsv_emu_peer_exchange(ptrs, n_local, part, g) == 0
     for r in range(world):
         assert np.array_equal(shards[r], want[r]), f"rank {r}"
+
+
+def test_shards_below_four_qubits_are_rejected():
+    """Shards smaller than one register group (2^4 amplitudes) are padded with idle index bits that would collide with
+    the rank bits: the scheduler refuses them instead of producing wrong amplitudes."""
+    lib = emu_lib()
+    for n, world in ((4, 2), (5, 4), (6, 8)):
+        enc = encode_gates(qft_circuit(OracleCircuit, G, n).circuit_gates, n)
+        with pytest.raises(F.QsvError) as e:
+            qb.Plan(n, enc, n_local=n - (world.bit_length() - 1), lib=lib)
+        assert e.value.code == F.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_tiny_shards_find_exchange_partners(seed):
+    """n_local = 4 with up to 3 rank bits and 3-wire gates: exchange partners must be found below the top-10 window."""
+    rng = np.random.default_rng(900 + seed)
+    g = int(rng.integers(1, 4))
+    n = 4 + g
+    c = random_any_gate_circuit(OracleCircuit, G, n, 40, rng)
+    enc = encode_gates(c.circuit_gates, n)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, None, mode="dense")
+    out, _, _ = emu_simulate_sharded(n, enc, 1 << g, tile_bits=4, low_bits=1)
+    assert np.max(np.abs(out - ref)) < 1e-12
