@@ -17,7 +17,7 @@ HOSTFLAGS := -DQSV_REG_BITS=$(QSV_REG_BITS) -DQSV_OCC_NUM=$(QSV_OCC_NUM) $(EXTRA
 HOST_SRCS := $(CSRC)/plan.cpp $(CSRC)/plan_api.cpp
 HDRS := include/qsv.h $(wildcard $(CSRC)/*.h)
 TILE_BITS := 0 10 11 12 13
-PASS_OBJS := $(foreach t,$(TILE_BITS),$(OBJ)/pass_kernel_t$(t).o) $(OBJ)/pass_kernel_async_t11.o $(OBJ)/pass_kernel_async_t12.o $(OBJ)/pass_kernel_init_t11.o $(OBJ)/pass_kernel_init_t12.o
+PASS_OBJS := $(foreach t,$(TILE_BITS),$(OBJ)/pass_kernel_t$(t).o) $(OBJ)/pass_kernel_tma_t11.o $(OBJ)/pass_kernel_tma_t12.o
 LIB_OBJS := $(OBJ)/plan.o $(OBJ)/plan_api.o $(OBJ)/kernels.o $(OBJ)/state_api.o $(OBJ)/shard.o $(PASS_OBJS)
 
 all:
@@ -28,11 +28,7 @@ oracle:
 	$(MAKE) -C oracle
 emu: tests/emu/libqsv_emu.so
 
-$(OBJ)/pass_kernel_async_t%.o: $(CSRC)/pass_kernel_async.cu $(HDRS)
-	@mkdir -p $(OBJ)
-	$(NVCC) $(NVCCFLAGS) -DQSV_TILE_BITS=$* -c -o $@ $<
-
-$(OBJ)/pass_kernel_init_t%.o: $(CSRC)/pass_kernel_init.cu $(HDRS)
+$(OBJ)/pass_kernel_tma_t%.o: $(CSRC)/pass_kernel_tma.cu $(HDRS)
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVCCFLAGS) -DQSV_TILE_BITS=$* -c -o $@ $<
 

@@ -240,6 +240,11 @@ int qsv_get_layout(const qsv_state* s, uint8_t* out_layout, size_t cap);
 /* Blocks until all work queued on the handle's stream has finished. */
 int qsv_synchronize(qsv_state* s);
 
+/* Device time of every step (fused pass or exchange) of the last qsv_apply / qsv_run_plan, in plan order, in ms.
+ * Recorded only while the "timing" option is on (CUDA events around every launch; the host then waits for each step).
+ * Writes min(*n_steps, cap) entries; out_ms may be NULL to query the count. */
+int qsv_last_step_ms(const qsv_state* s, double* out_ms, size_t cap, size_t* n_steps);
+
 /* Raw device pointer / stream of the handle, for callers that time with their
  * own CUDA events or wrap the memory (no ownership transfer). */
 int qsv_device_pointer(qsv_state* s, void** dev_ptr, void** cuda_stream);

@@ -222,6 +222,14 @@ class DeviceState:
     def synchronize(self):
         F.check(self.lib.qsv_synchronize(self.handle), self.handle)
 
+    def last_step_ms(self) -> list:
+        """Device time of every step (pass or exchange) of the last plan run; needs set_option("timing", 1)."""
+        n = C.c_size_t()
+        F.check(self.lib.qsv_last_step_ms(self.handle, None, 0, C.byref(n)), self.handle)
+        buf = (C.c_double * max(1, n.value))()
+        F.check(self.lib.qsv_last_step_ms(self.handle, buf, n.value, C.byref(n)), self.handle)
+        return [buf[i] for i in range(n.value)]
+
 
 class Plan:
     """A lowered + scheduled circuit (`qsv_plan*`).  Host-only to build."""

@@ -29,21 +29,34 @@ __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_
 // ---------------------------------------------------------------------------------------------
 // Fused pass: dispatch to the per-tile-size objects built from pass_kernel.cu.
 // ---------------------------------------------------------------------------------------------
-cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, bool single_process, cudaStream_t stream) {
+// QSV_ASYNC (read once): 0 = the synchronous kernel at every size, 2 = the pipelined TMA kernel wherever the tile is
+// expressible (parity tests on small registers), default = the pipelined kernel from 16 tiles per SM upwards.
+static int async_mode() {
+    static const int mode = getenv("QSV_ASYNC") ? atoi(getenv("QSV_ASYNC")) : 1;
+    return mode;
+}
+
+bool pass_uses_tma(const uint8_t* host_blob, uint32_t n_alloc, int sm_count) {
+    const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
+    const int mode = async_mode();
+    if (mode == 0 || (mode < 2 && hdr.n_tiles < 16ull * (uint64_t)sm_count)) return false;
+    if (hdr.tile_bits == 12) return pass_tma_supported_tile<12>(host_blob, n_alloc);
+    if (hdr.tile_bits == 11) return pass_tma_supported_tile<11>(host_blob, n_alloc);
+    return false;
+}
+
+bool pass_init_supported(const uint8_t* host_blob, uint32_t n_alloc, int sm_count) { return pass_uses_tma(host_blob, n_alloc, sm_count); }
+
+cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, const cplx* ext_tbl, uint64_t rank_hi, uint32_t n_alloc, int sm_count,
+                        const PassInit* init, cudaStream_t stream) {
     const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
     const uint32_t tile_bits = hdr.tile_bits;
-    // The software-pipelined kernel (one CTA per SM, tiles prefetched with cp.async while the compute groups work)
-    // serves large registers; QSV_ASYNC=0 forces the synchronous kernel, 2 the pipelined one at every size (tests).
-    static const int use_async = getenv("QSV_ASYNC") ? atoi(getenv("QSV_ASYNC")) : 1;
-    // Envelope: at least 16 tiles per SM.  One-round passes of sharded registers stay on the synchronous kernel: the
-    // pipelined kernel's one-round case (fixed in round 1) was re-validated on one GPU only.
-    static const int min_rounds_env = getenv("QSV_ASYNC_MIN_ROUNDS") ? atoi(getenv("QSV_ASYNC_MIN_ROUNDS")) : 0;
-    const uint32_t min_rounds = min_rounds_env > 0 ? (uint32_t)min_rounds_env : (single_process ? 1u : 2u);
-    const bool envelope = hdr.n_rounds >= min_rounds && hdr.n_tiles >= 16ull * (uint64_t)sm_count;
-    if (use_async && (use_async >= 2 || envelope)) {  // 2: always (parity tests of the pipelined kernels on small registers)
-        if (tile_bits == 12) return launch_pass_async_tile<12>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
-        if (tile_bits == 11) return launch_pass_async_tile<11>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
+    if (pass_uses_tma(host_blob, n_alloc, sm_count)) {
+        const PassInit none{0, 0, 0};
+        if (tile_bits == 12) return launch_pass_tma_tile<12>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init ? *init : none, stream);
+        return launch_pass_tma_tile<11>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init ? *init : none, stream);
     }
+    if (init) return cudaErrorNotSupported;
     switch (tile_bits) {
         case 10: return launch_pass_tile<10>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
         case 11: return launch_pass_tile<11>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
@@ -55,16 +68,34 @@ cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* hos
     }
 }
 
-bool pass_init_supported(const uint8_t* host_blob, int sm_count) {
-    const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
-    return (hdr.tile_bits == 11 || hdr.tile_bits == 12) && hdr.n_tiles >= (uint64_t)sm_count;
+// External-phase tables of one pass (pipelined kernel): grid.y = table slot, grid.x strides over its 2^a + 2^b entries.
+struct ExtSlotOps {
+    uint8_t op[kMaxOps];
+};
+__global__ void __launch_bounds__(256) build_ext_tables_kernel(const uint8_t* __restrict__ blob, cplx* __restrict__ tbl, uint64_t rank_hi, uint32_t a_bits, uint64_t len_a,
+                                                             uint64_t len, ExtSlotOps slots) {
+    const DevPass& hdr = *reinterpret_cast<const DevPass*>(blob);
+    const DevOp& op = reinterpret_cast<const DevOp*>(blob + hdr.ops_off)[slots.op[blockIdx.y]];
+    const DiagExtTerm* terms = reinterpret_cast<const DiagExtTerm*>(blob + op.ext_off);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
+        const bool low = i < len_a;
+        tbl[(uint64_t)blockIdx.y * len + i] = ext_table_entry(hdr, op.theta0, terms, op.n_ext, low ? i : (i - len_a) << a_bits, rank_hi, low);
+    }
 }
 
-cudaError_t launch_pass_init(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, const PassInit& init, cudaStream_t stream) {
+cudaError_t launch_build_ext_tables(const uint8_t* dev_blob, const uint8_t* host_blob, cplx* tbl, uint64_t rank_hi, cudaStream_t stream) {
     const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
-    if (hdr.tile_bits == 12) return launch_pass_init_tile<12>(state, dev_blob, host_blob, rank_hi, sm_count, init, stream);
-    if (hdr.tile_bits == 11) return launch_pass_init_tile<11>(state, dev_blob, host_blob, rank_hi, sm_count, init, stream);
-    return cudaErrorNotSupported;
+    if (hdr.n_ext_ops == 0) return cudaSuccess;
+    const DevOp* ops = reinterpret_cast<const DevOp*>(host_blob + hdr.ops_off);
+    ExtSlotOps slots{};
+    for (uint32_t o = 0; o < hdr.n_ops; ++o)
+        if (ops[o].type == OP_DIAG && ops[o].ext_slot != kNoExtSlot) slots.op[ops[o].ext_slot] = (uint8_t)o;
+    const uint32_t a_bits = ext_table_low_bits(hdr.n_tiles);
+    const uint64_t len = ext_table_len(hdr.n_tiles);
+    uint64_t gx = (len + 255) / 256;
+    if (gx > 64) gx = 64;
+    build_ext_tables_kernel<<<dim3((unsigned)gx, hdr.n_ext_ops), 256, 0, stream>>>(dev_blob, tbl, rank_hi, a_bits, 1ull << a_bits, len, slots);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -251,9 +282,69 @@ cudaError_t launch_prob_block_sums(const cplx* state, double* sums, uint64_t n_b
     return cudaGetLastError();
 }
 
+// Large registers (2^21 block sums at 33 qubits): three short launches instead of one CTA walking the whole array.
+//   chunk_scan   one CTA per chunk of 4096 sums: exclusive scan inside the chunk, chunk total to `chunk_tot`
+//   (the single-CTA kernel above scans the <= 1024 chunk totals in place; its total is prefix[n])
+//   chunk_add    prefix[i] += offset of i's chunk
+constexpr uint32_t kScanChunk = 4096;
+__global__ void __launch_bounds__(1024) chunk_scan_kernel(const double* __restrict__ sums, double* __restrict__ prefix, double* __restrict__ chunk_tot, uint64_t n) {
+    __shared__ double warp_tot[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t i0 = (uint64_t)blockIdx.x * kScanChunk + 4ull * threadIdx.x;
+    double v[4], run = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        v[j] = i0 + j < n ? sums[i0 + j] : 0.0;
+        run += v[j];
+    }
+    double inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += y;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        double w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= (uint32_t)o) w += y;
+        }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    double before = (warp ? warp_tot[warp - 1] : 0.0) + (inc - run);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (i0 + j < n) prefix[i0 + j] = before;
+        before += v[j];
+    }
+    if (threadIdx.x == 1023) chunk_tot[blockIdx.x] = warp_tot[31];
+}
+__global__ void __launch_bounds__(1024) chunk_add_kernel(double* __restrict__ prefix, const double* __restrict__ chunk_off, uint64_t n) {
+    const double off = chunk_off[blockIdx.x];
+    const uint64_t i0 = (uint64_t)blockIdx.x * kScanChunk + 4ull * threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (i0 + j < n) prefix[i0 + j] += off;
+}
+
+// prefix must have room for n + 2 + 2 * kScanMaxChunks doubles: prefix[n] = total, the rest is chunk scratch
 cudaError_t launch_scan_block_sums(const double* sums, double* prefix, uint64_t n, cudaStream_t stream) {
-    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(sums, prefix, n);
-    return cudaGetLastError();
+    const uint64_t chunks = (n + kScanChunk - 1) / kScanChunk;
+    if (chunks <= 2 || chunks > (uint64_t)kScanMaxChunks) {
+        scan_block_sums_kernel<<<1, 1024, 0, stream>>>(sums, prefix, n);
+        return cudaGetLastError();
+    }
+    double* chunk_tot = prefix + n + 1;
+    double* chunk_off = chunk_tot + kScanMaxChunks;  // exclusive scan of the chunk totals; chunk_off[chunks] = total
+    chunk_scan_kernel<<<(unsigned)chunks, 1024, 0, stream>>>(sums, prefix, chunk_tot, n);
+    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(chunk_tot, chunk_off, chunks);
+    chunk_add_kernel<<<(unsigned)chunks, 1024, 0, stream>>>(prefix, chunk_off, n);
+    cudaError_t e = cudaMemcpyAsync(prefix + n, chunk_off + chunks, sizeof(double), cudaMemcpyDeviceToDevice, stream);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_sample_shots(const cplx* state, const double* prefix, uint64_t n_blocks, uint32_t block_bits, const double* uniforms,

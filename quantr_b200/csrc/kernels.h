@@ -29,29 +29,36 @@ inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<uin
 namespace qsv {
 
 // host_blob: the pass blob in host memory (its header/rounds/ops travel as kernel parameters);
-// dev_blob: the same blob in device memory (tables, external phase terms, Custom matrices).
-// single_process: the register is not sharded (widens the envelope of the software-pipelined kernel, see kernels.cu)
-cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, bool single_process, cudaStream_t stream);
-// defined in pass_kernel.cu, one explicit specialisation per tile size (0 = runtime tile size <= 9 bits)
+// dev_blob: the same blob in device memory (tables, external phase terms, Custom matrices);
+// ext_tbl: the pass's external-phase tables in device memory (launch_build_ext_tables), may be null for passes without;
+// init: null, or the basis state whose initialisation is fused into this pass (the register is not read).
+cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, const cplx* ext_tbl, uint64_t rank_hi, uint32_t n_alloc, int sm_count,
+                        const PassInit* init, cudaStream_t stream);
+// true when launch_pass sends this pass to the pipelined TMA kernel (large registers whose tile is a tensor-map box)
+bool pass_uses_tma(const uint8_t* host_blob, uint32_t n_alloc, int sm_count);
+// true when launch_pass accepts `init` for this pass
+bool pass_init_supported(const uint8_t* host_blob, uint32_t n_alloc, int sm_count);
+// fills the pass's external-phase tables: hdr.n_ext_ops x ext_table_len(hdr.n_tiles) entries (pass_core.h ext_table_entry)
+cudaError_t launch_build_ext_tables(const uint8_t* dev_blob, const uint8_t* host_blob, cplx* tbl, uint64_t rank_hi, cudaStream_t stream);
+
+// defined in pass_kernel.cu, one explicit specialisation per tile size (0 = runtime tile size <= 9 bits): the synchronous kernel
 template <int TILE_BITS>
 cudaError_t launch_pass_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream);
 
-// defined in pass_kernel_async.cu for TILE_BITS = 11 and 12: the software-pipelined (cp.async + mbarrier) variant
+// defined in pass_kernel_tma.cu for TILE_BITS = 11 and 12: the software-pipelined TMA kernel
 template <int TILE_BITS>
-cudaError_t launch_pass_async_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, cudaStream_t stream);
-
-// defined in pass_kernel_init.cu for TILE_BITS = 11 and 12: first pass of a plan with the basis-state initialisation fused in
+cudaError_t launch_pass_tma_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, const cplx* ext_tbl, uint64_t rank_hi, uint32_t n_alloc, int sm_count,
+                                 const PassInit& init, cudaStream_t stream);
 template <int TILE_BITS>
-cudaError_t launch_pass_init_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, const PassInit& init, cudaStream_t stream);
-// true when launch_pass_init serves this pass (tile size 11 or 12, at least one tile per SM)
-bool pass_init_supported(const uint8_t* host_blob, int sm_count);
-cudaError_t launch_pass_init(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, uint64_t rank_hi, int sm_count, const PassInit& init, cudaStream_t stream);
+bool pass_tma_supported_tile(const uint8_t* host_blob, uint32_t n_alloc);
 
 cudaError_t launch_set_amp(cplx* state, uint64_t index, double re, double im, cudaStream_t stream);
 // in-place swap of this rank's block 'spelled' peer with the peer's block 'spelled' rank (peer-mapped memory, NVLink)
 cudaError_t launch_peer_swap(cplx* local, cplx* remote, uint32_t n_local, const uint8_t* partner, uint32_t g, int rank, int peer, int sm_count, cudaStream_t stream);
 cudaError_t launch_gather(const cplx* state, const uint64_t* idx, cplx* out, uint64_t count, cudaStream_t stream);
 cudaError_t launch_prob_block_sums(const cplx* state, double* sums, uint64_t n_blocks, uint32_t block_bits, int sm_count, cudaStream_t stream);
+// `prefix` must hold n + 2 + 2 * kScanMaxChunks doubles (prefix[n] = total, the rest is scratch of the chunked scan)
+constexpr int kScanMaxChunks = 1024;
 cudaError_t launch_scan_block_sums(const double* sums, double* prefix, uint64_t n, cudaStream_t stream);
 cudaError_t launch_sample_shots(const cplx* state, const double* prefix, uint64_t n_blocks, uint32_t block_bits, const double* uniforms,
                                 uint64_t shots, uint64_t index_or, uint64_t* out, int sm_count, cudaStream_t stream);

@@ -74,6 +74,26 @@ QSV_HD cplx diag_ext_phase(const DevOp& op, const uint8_t* blob, uint64_t base_f
     return diag_ext_phase_terms(op.theta0, reinterpret_cast<const DiagExtTerm*>(blob + op.ext_off), op.n_ext, base_full);
 }
 
+// External-phase tables of the pipelined kernel: the tile id t is split into its low `a` bits and the rest, and
+//   exp(i*pi*(theta0 + sum over set bits outside the tile)) = A[t & (2^a - 1)] * B[t >> a]
+// with A carrying theta0 and the rank bits.  One entry (built once per plan upload, on the device):
+//   part   = the tile-id bits of this half, in place (low half: i, high half: i << a)
+//   is_low = the entry belongs to table A
+QSV_HD cplx ext_table_entry(const DevPass& hdr, double theta0, const DiagExtTerm* terms, uint32_t n_ext, uint64_t part, uint64_t rank_hi, bool is_low) {
+    const uint64_t base = deposit(part, hdr.ext_segs, hdr.n_ext_segs) | (is_low ? rank_hi : 0ull);
+    return diag_ext_phase_terms(is_low ? theta0 : 0.0, terms, n_ext, base);
+}
+QSV_HD uint32_t ext_table_low_bits(uint64_t n_tiles) {
+    uint32_t nt = 0;
+    while ((1ull << nt) < n_tiles) ++nt;
+    return (nt + 1) / 2;
+}
+// entries of table A + table B for a pass with n_tiles tiles
+QSV_HD uint64_t ext_table_len(uint64_t n_tiles) {
+    const uint32_t a = ext_table_low_bits(n_tiles);
+    return (1ull << a) + ((n_tiles + (1ull << a) - 1) >> a);
+}
+
 // ---- in-place FP64 primitives ---------------------------------------------------------------------
 // Every op below updates the thread's 16 amplitudes strictly in place: the device versions are single
 // PTX instructions with tied ("+d") operands so the 64 data registers keep one home through the op
@@ -494,6 +514,14 @@ QSV_HD void round_store_tile(const DevRound& R, uint32_t lb, cplx* tile, const c
     char* tb = reinterpret_cast<char*>(tile);
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) *reinterpret_cast<cplx*>(tb + (sb ^ R.xoff[s])) = a[s];
+}
+
+// last round of a pass that leaves through the tile buffer (TMA store): the deferred 1/sqrt2 factors are applied here
+QSV_HD void round_store_tile_scaled(const DevRound& R, uint32_t lb, cplx* tile, const cplx (&a)[kSlots], double scale) {
+    const uint32_t sb = swz(lb) << 4;
+    char* tb = reinterpret_cast<char*>(tile);
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) *reinterpret_cast<cplx*>(tb + (sb ^ R.xoff[s])) = cplx{a[s].x * scale, a[s].y * scale};
 }
 
 //   act : bit o set = op o of the pass acts on this thread-group for this tile (W words)

@@ -219,6 +219,9 @@ std::vector<Seg> runs_to_segs(const std::vector<int>& phys_sorted) {
     return segs;
 }
 
+// same for a list that is not ascending (thread index bit i -> tile-local bit list[i]): runs of consecutive positions
+std::vector<Seg> runs_to_segs_ordered(const std::vector<int>& list) { return runs_to_segs(list); }
+
 template <class T>
 size_t append(std::vector<uint8_t>& blob, const T* data, size_t count) {
     while (blob.size() % 16) blob.push_back(0);
@@ -274,7 +277,7 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
     struct Fix { size_t op; int field; };  // field: 0 ext_off, 1 tbl_off, 2 dense_off
     std::vector<Fix> fixes;
     std::vector<std::pair<size_t, std::vector<size_t>>> dense_fix;  // aux offset of DevDense -> needs internal fix
-    uint32_t n_diag = 0;
+    uint32_t n_diag = 0, n_ext_ops = 0;
 
     for (const RoundB& rb : pb.rounds) {
         DevRound dr;
@@ -287,6 +290,7 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
             DevOp dop;
             memset(&dop, 0, sizeof(dop));
             dop.type = OP_DENSE;
+            dop.ext_slot = kNoExtSlot;
             DevDense dd;
             memset(&dd, 0, sizeof(dd));
             dd.k = (uint32_t)lop.bits.size();
@@ -325,8 +329,26 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
         std::vector<int> slot_of(16, -1), thr_local, thr_index(16, -1);
         for (int j = 0; j < kRegBits; ++j) { dr.reg_pos[j] = (uint8_t)reg_local[j]; slot_of[reg_local[j]] = j; }
         for (int lp = 0; lp < T; ++lp)
-            if (slot_of[lp] < 0) { thr_index[lp] = (int)thr_local.size(); thr_local.push_back(lp); }
-        auto thsegs = runs_to_segs(thr_local);
+            if (slot_of[lp] < 0) thr_local.push_back(lp);
+        // Thread bits 0-2 (the lanes of a quarter-warp) should address all eight 16-byte units of the swizzled rows
+        // (qsv_types.h swz()): three non-register bits below 6 with distinct positions mod 3, lowest first.  When the
+        // register bits leave tile bits 0-2 to the threads this is the identity order (and global stores coalesce).
+        {
+            std::vector<int> low;
+            for (int lp : thr_local) if (lp < 6) low.push_back(lp);
+            int pick[3] = {-1, -1, -1};
+            for (size_t x = 0; x < low.size() && pick[0] < 0; ++x)
+                for (size_t y = x + 1; y < low.size() && pick[0] < 0; ++y)
+                    for (size_t z = y + 1; z < low.size() && pick[0] < 0; ++z)
+                        if (low[x] % 3 != low[y] % 3 && low[x] % 3 != low[z] % 3 && low[y] % 3 != low[z] % 3) { pick[0] = low[x]; pick[1] = low[y]; pick[2] = low[z]; }
+            if (pick[0] >= 0) {
+                std::vector<int> ordered(pick, pick + 3);
+                for (int lp : thr_local) if (lp != pick[0] && lp != pick[1] && lp != pick[2]) ordered.push_back(lp);
+                if (runs_to_segs_ordered(ordered).size() <= (size_t)kMaxThrSegs) thr_local.swap(ordered);
+            }
+        }
+        for (size_t i = 0; i < thr_local.size(); ++i) thr_index[thr_local[i]] = (int)i;
+        auto thsegs = runs_to_segs_ordered(thr_local);
         if (thsegs.size() > (size_t)kMaxThrSegs) fail("internal: too many thread segments");
         dr.n_thr_segs = (uint32_t)thsegs.size();
         for (size_t i = 0; i < thsegs.size(); ++i) dr.thr_segs[i] = thsegs[i];
@@ -361,6 +383,7 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
             const LOp& lop = lops[oi];
             DevOp d;
             memset(&d, 0, sizeof(d));
+            d.ext_slot = kNoExtSlot;
             split_cmask(lop.cmask, d);
             if (lop.kind == LOp::MAT) {
                 d.type = lop.mtype;
@@ -426,6 +449,7 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
                 d.flags = (has_lo ? (uint32_t)DIAG_HAS_THR_LO : 0u) | (has_hi ? (uint32_t)DIAG_HAS_THR_HI : 0u) | (has_reg ? (uint32_t)DIAG_HAS_REG : 0u) |
                           (has_w ? (uint32_t)DIAG_HAS_W : 0u) | (nontrivial << DIAG_NONTRIVIAL_SHIFT);
                 d.n_ext = (uint32_t)ext.size();
+                d.ext_slot = ext.empty() ? kNoExtSlot : n_ext_ops++;
                 if (!ext.empty()) { d.ext_off = (uint32_t)append(aux, ext.data(), ext.size()); fixes.push_back({ops.size(), 0}); }
                 d.tbl_off = (uint32_t)append(aux, tbl.data(), tbl.size());  // always present: the kernel stages it in shared memory
                 fixes.push_back({ops.size(), 1});
@@ -462,6 +486,7 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
     hdr.n_rounds = (uint32_t)rounds.size();
     hdr.n_ops = (uint32_t)ops.size();
     hdr.n_diag = n_diag;
+    hdr.n_ext_ops = n_ext_ops;
     hdr.final_scale = ldexp((n_hadamard & 1) ? 0.70710678118654752440 : 1.0, -(int)(n_hadamard / 2));
     hdr.rounds_off = (uint32_t)(sizeof(DevPass) + sizeof(DevLoads));
     hdr.ops_off = hdr.rounds_off + (uint32_t)(rounds.size() * sizeof(DevRound));

@@ -65,7 +65,9 @@ struct Plan {
     // device residency (owned by the state API)
     void* dev_blob = nullptr;
     std::vector<size_t> dev_offsets;
+    std::vector<size_t> dev_tbl_offsets;  // external-phase tables of pass i inside dev_blob (SIZE_MAX: the pass has none)
     int dev_device = -1;
+    int dev_rank = -1;                     // the tables carry the rank bits of the handle that uploaded the plan
 };
 
 // Throws std::runtime_error with a message on invalid input / unsupported circuits.

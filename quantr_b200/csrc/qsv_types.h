@@ -41,7 +41,8 @@ constexpr int kSmallTileThreads = 64; // CTA size for tiles below 2^10 amplitude
 
 // CTA size for a tile of 2^T amplitudes: one thread per register group of 16 amplitudes.
 QSV_HD constexpr uint32_t tile_threads(uint32_t T) { return T >= 10 ? (1u << (T - kRegBits)) : (uint32_t)kSmallTileThreads; }
-constexpr uint32_t kPassMagic = 0x51535631u;  // "QSV1"
+constexpr uint32_t kPassMagic = 0x51535632u;  // "QSV2"
+constexpr uint32_t kNoExtSlot = 0xffffffffu;
 
 struct alignas(16) cplx {
     double x, y;
@@ -113,7 +114,7 @@ struct DevOp {
     uint32_t tbl_off;     // DIAG: byte offset of the thread-phase table cplx lo[32], hi[16] (kDiagTblLen entries)
     uint32_t dense_off;   // DENSE: byte offset of DevDense
     uint32_t code;        // dispatch code (see kCode*)
-    uint32_t pad;
+    uint32_t ext_slot;    // DIAG with n_ext > 0: index of its pair of external-phase tables (ext_tables.h); else kNoExtSlot
     double theta0;        // DIAG: constant term (half-turns)
 };
 static_assert(sizeof(DevOp) == 192, "DevOp layout");
@@ -158,7 +159,8 @@ struct DevPass {
     double final_scale;       // product of the deferred 1/sqrt2 factors of the pass's Hadamards
     uint32_t ext_ctrl_mask[3];// bit o set: op o has controls outside the tile (evaluated once per tile)
     uint32_t max_ext;         // largest DevOp::n_ext of the pass (stride of the shared-memory copy of the term lists)
-    uint64_t reserved0;
+    uint32_t n_ext_ops;       // DIAG ops whose phase depends on bits outside the tile (DevOp::ext_slot = 0..n_ext_ops-1)
+    uint32_t reserved0;
     Seg tile_segs[kMaxSegs];  // tile-local index -> physical (local) offset
     Seg ext_segs[kMaxSegs];   // tile id -> physical (local) base
 };
@@ -198,13 +200,13 @@ QSV_HD uint64_t extract(uint64_t v, const Seg* segs, uint32_t n) {
     return r;
 }
 
-// Shared-memory swizzle of a tile-local index: XOR-folds every higher 3-bit group into the
-// 16-byte-unit bits so that any three index bits with distinct (position mod 3) spread a
-// quarter-warp's 128-bit accesses over all 32 banks.
-QSV_HD uint32_t swz(uint32_t l) {
-    const uint32_t x = l >> 3;
-    return l ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7u);
-}
+// Shared-memory swizzle of a tile-local index.  It is the layout the TMA unit writes for a tensor map with
+// CU_TENSOR_MAP_SWIZZLE_128B and a 128-byte inner box (8 amplitudes): the 16-byte unit inside each 128-byte row is
+// XORed with the row number mod 8 (byte-address bits 4-6 ^= bits 7-9).  A quarter-warp's 128-bit accesses hit all 32
+// banks when its three varying tile-local bits lie below bit 6 with distinct (position mod 3); the scheduler orders the
+// thread bits of every round accordingly (emit_pass).  Every kernel - TMA or not - and the host emulation use this one
+// layout.
+QSV_HD uint32_t swz(uint32_t l) { return l ^ ((l >> 3) & 7u); }
 
 QSV_HD cplx cmul(cplx a, cplx b) { return cplx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 

@@ -51,6 +51,20 @@ struct qsv_state {
     uint64_t lazy_index = 0;
     void* d_staging = nullptr;  // exchange staging (sharded handles, NCCL path)
     size_t staging_bytes = 0;
+    // scratch for qsv_sample / qsv_gather (uniforms, indices, results): grown on demand, never per call
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    bool total_valid = false;  // total_prob has been read back since the prefix was rebuilt
+    // plans of recent qsv_apply calls, keyed by the serialised gate list + options + layout: re-running a circuit
+    // (measure_all_without_cache, repeated simulate) skips lowering, scheduling and the schedule upload
+    struct CachedPlan {
+        std::vector<uint8_t> key;
+        qsv_plan* plan = nullptr;
+        uint64_t stamp = 0;
+    };
+    std::vector<CachedPlan> plan_cache;
+    uint64_t plan_stamp = 0;
+    std::vector<double> last_step_ms;  // "timing" option: device time of every step of the last plan run
     std::vector<cplx*> peer_ptr;  // peer-mapped shards (qsv_peer_import); empty = NCCL send/recv exchange
     std::string error;
 };
@@ -116,6 +130,22 @@ int materialize(qsv_state* s) {
     return QSV_OK;
 }
 
+// Device scratch of at least `bytes` (256-byte aligned sub-ranges are carved by the callers).
+int ensure_scratch(qsv_state* s, size_t bytes) {
+    if (bytes <= s->scratch_bytes) return QSV_OK;
+    if (s->d_scratch) {
+        QSV_CUDA(s, cudaStreamSynchronize(s->stream));
+        cudaFree(s->d_scratch);
+        s->d_scratch = nullptr;
+        s->scratch_bytes = 0;
+    }
+    size_t want = 1 << 16;
+    while (want < bytes) want <<= 1;
+    QSV_CUDA(s, cudaMalloc(&s->d_scratch, want));
+    s->scratch_bytes = want;
+    return QSV_OK;
+}
+
 int create_common(qsv_state** out, uint32_t n_qubits, int device, int rank, int world) {
     if (!out) return set_error(nullptr, QSV_ERR_INVALID_ARG, "out is NULL");
     *out = nullptr;
@@ -153,7 +183,7 @@ int create_common(qsv_state** out, uint32_t n_qubits, int device, int rank, int 
     }
     s->block_bits = s->n_alloc < 12 ? s->n_alloc : 12;
     s->n_blocks = 1ull << (s->n_alloc - s->block_bits);
-    if ((e = cudaMalloc(&s->d_sums, sizeof(double) * s->n_blocks)) != cudaSuccess || (e = cudaMalloc(&s->d_prefix, sizeof(double) * (s->n_blocks + 1))) != cudaSuccess) {
+    if ((e = cudaMalloc(&s->d_sums, sizeof(double) * s->n_blocks)) != cudaSuccess || (e = cudaMalloc(&s->d_prefix, sizeof(double) * (s->n_blocks + 2 + 2 * kScanMaxChunks))) != cudaSuccess) {
         cudaGetLastError();
         return fail(set_error(nullptr, QSV_ERR_OUT_OF_MEMORY, "cudaMalloc of the measurement scratch: %s", cudaGetErrorString(e)));
     }
@@ -179,21 +209,39 @@ void release_plan_device(qsv_plan* p) {
 
 int upload_plan(qsv_state* s, qsv_plan* p) {
     Plan& plan = p->plan;
-    if (plan.dev_blob && plan.dev_device == s->device) return QSV_OK;
+    if (plan.dev_blob && plan.dev_device == s->device && plan.dev_rank == s->rank) return QSV_OK;
     if (plan.dev_blob) release_plan_device(p);
     size_t total = 0;
     plan.dev_offsets.clear();
+    plan.dev_tbl_offsets.clear();
     for (auto& b : plan.passes) {
         plan.dev_offsets.push_back(total);
         total += (b.size() + 255) & ~size_t(255);
     }
     if (total == 0) return QSV_OK;
-    std::vector<uint8_t> host(total, 0);
+    const size_t blob_bytes = total;
+    // external-phase tables of the passes the pipelined kernel will run (two half-index tables per DIAG op whose phase
+    // depends on bits outside the tile; filled on the device below)
+    for (auto& b : plan.passes) {
+        const DevPass& hdr = *reinterpret_cast<const DevPass*>(b.data());
+        if (hdr.n_ext_ops && pass_uses_tma(b.data(), s->n_alloc, s->sm_count)) {
+            plan.dev_tbl_offsets.push_back(total);
+            total += (sizeof(cplx) * hdr.n_ext_ops * ext_table_len(hdr.n_tiles) + 255) & ~size_t(255);
+        } else {
+            plan.dev_tbl_offsets.push_back(SIZE_MAX);
+        }
+    }
+    std::vector<uint8_t> host(blob_bytes, 0);
     for (size_t i = 0; i < plan.passes.size(); ++i) memcpy(host.data() + plan.dev_offsets[i], plan.passes[i].data(), plan.passes[i].size());
     QSV_CUDA(s, cudaMalloc(&plan.dev_blob, total));
     plan.dev_device = s->device;
+    plan.dev_rank = s->rank;
     p->release_device = release_plan_device;
-    QSV_CUDA(s, cudaMemcpyAsync(plan.dev_blob, host.data(), total, cudaMemcpyHostToDevice, s->stream));
+    QSV_CUDA(s, cudaMemcpyAsync(plan.dev_blob, host.data(), blob_bytes, cudaMemcpyHostToDevice, s->stream));
+    for (size_t i = 0; i < plan.passes.size(); ++i)
+        if (plan.dev_tbl_offsets[i] != SIZE_MAX)
+            QSV_CUDA(s, launch_build_ext_tables(static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[i], plan.passes[i].data(),
+                                                reinterpret_cast<cplx*>(static_cast<uint8_t*>(plan.dev_blob) + plan.dev_tbl_offsets[i]), rank_base(s), s->stream));
     QSV_CUDA(s, cudaStreamSynchronize(s->stream));  // `host` goes out of scope
     return QSV_OK;
 }
@@ -247,13 +295,14 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     } else if (memcmp(s->layout, plan.initial_layout.data(), s->n_qubits) != 0) {
         return set_error(s, QSV_ERR_INVALID_ARG, "the plan starts from a different qubit layout than the register is in");
     }
-    // QSV_FUSED_INIT=1|2 (opt-in, see pass_kernel_init.cu): a pending basis state is not written to HBM; the plan's first
-    // pass synthesises its tiles instead of reading the register (2: and writes all-zero tiles without arithmetic).
-    static const int fused_init_mode = getenv("QSV_FUSED_INIT") ? atoi(getenv("QSV_FUSED_INIT")) : 0;
+    // Fused initialisation (pass_kernel_tma.cu): a pending basis state is not written to HBM when the plan's first step is
+    // a pass the pipelined kernel runs; that pass synthesises the one tile holding the amplitude and writes every other
+    // tile as zeros (mode 2).  QSV_FUSED_INIT=0 turns it off (memset + ordinary first pass), 1 computes every tile.
+    static const int fused_init_mode = getenv("QSV_FUSED_INIT") ? atoi(getenv("QSV_FUSED_INIT")) : 2;
     bool fused_init = false;
     PassInit pass_init{};
     if (s->lazy_basis && fused_init_mode > 0 && !plan.steps.empty() && plan.steps[0].kind == PlanStep::PASS && s->n_alloc == s->n_local &&
-        pass_init_supported(plan.passes[plan.steps[0].pass_index].data(), s->sm_count)) {
+        pass_init_supported(plan.passes[plan.steps[0].pass_index].data(), s->n_alloc, s->sm_count)) {
         const DevPass& h0 = *reinterpret_cast<const DevPass*>(plan.passes[plan.steps[0].pass_index].data());
         pass_init = make_pass_init(h0, to_physical(s, s->lazy_index), s->n_local, fused_init_mode >= 2 ? 2u : 1u);
         fused_init = true;
@@ -267,6 +316,7 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     static const bool trace_passes = getenv("QSV_TRACE_PASSES") != nullptr;  // developer aid: per-step device times on stderr
     double pass_ms = 0.0, exch_ms = 0.0;
     uint64_t n_exch = 0;
+    s->last_step_ms.clear();
     for (size_t i = 0; i < plan.steps.size(); ++i) {
         const PlanStep& st = plan.steps[i];
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -276,16 +326,19 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
             cudaEventCreate(&e1);
             cudaEventRecord(e0, s->stream);
         }
-        if (st.kind == PlanStep::PASS && i == 0 && fused_init) {
-            QSV_CUDA(s, launch_pass_init(s->d_state, static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[st.pass_index], plan.passes[st.pass_index].data(),
-                                         rank_base(s), s->sm_count, pass_init, s->stream));
-        } else if (st.kind == PlanStep::PASS) {
-            QSV_CUDA(s, launch_pass(s->d_state, static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[st.pass_index], plan.passes[st.pass_index].data(),
-                                    rank_base(s), s->sm_count, s->world == 1, s->stream));
+        if (st.kind == PlanStep::PASS) {
+            const uint8_t* dev_pass = static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[st.pass_index];
+            const cplx* ext_tbl = plan.dev_tbl_offsets[st.pass_index] == SIZE_MAX
+                                      ? nullptr
+                                      : reinterpret_cast<const cplx*>(static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_tbl_offsets[st.pass_index]);
+            QSV_CUDA(s, launch_pass(s->d_state, dev_pass, plan.passes[st.pass_index].data(), ext_tbl, rank_base(s), s->n_alloc, s->sm_count,
+                                    (i == 0 && fused_init) ? &pass_init : nullptr, s->stream));
         } else {
+            const double before = exch_ms;
             rc = run_exchange(s, st, &exch_ms);
             if (rc != QSV_OK) return rc;
             ++n_exch;
+            if (s->timing) s->last_step_ms.push_back(exch_ms - before);
         }
         if (timed) {
             cudaEventRecord(e1, s->stream);
@@ -293,6 +346,7 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, e0, e1);
             pass_ms += ms;
+            if (s->timing) s->last_step_ms.push_back(ms);
             if (trace_passes) {
                 const DevPass& h = *reinterpret_cast<const DevPass*>(plan.passes[st.pass_index].data());
                 int run_bits = 0;
@@ -325,10 +379,50 @@ int ensure_prefix(qsv_state* s) {
     if (s->prefix_valid) return QSV_OK;
     QSV_CUDA(s, launch_prob_block_sums(s->d_state, s->d_sums, s->n_blocks, s->block_bits, s->sm_count, s->stream));
     QSV_CUDA(s, launch_scan_block_sums(s->d_sums, s->d_prefix, s->n_blocks, s->stream));
+    s->prefix_valid = true;
+    s->total_valid = false;
+    return QSV_OK;
+}
+
+// total probability of this rank's shard on the host (one 8-byte read-back per rebuilt prefix)
+int ensure_total(qsv_state* s) {
+    int rc = ensure_prefix(s);
+    if (rc != QSV_OK || s->total_valid) return rc;
     QSV_CUDA(s, cudaMemcpyAsync(&s->total_prob, s->d_prefix + s->n_blocks, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     QSV_CUDA(s, cudaStreamSynchronize(s->stream));
-    s->prefix_valid = true;
+    s->total_valid = true;
     return QSV_OK;
+}
+
+// Serialises everything a plan depends on (qsv_apply's cache key).  Returns false when the key would be too large to be
+// worth keeping (huge Custom matrices).
+bool plan_cache_key(const qsv_state* s, const qsv_op* ops, size_t n_ops, bool free_layout, std::vector<uint8_t>& key) {
+    constexpr size_t kMaxKey = 8u << 20;
+    key.clear();
+    auto put = [&](const void* p, size_t n) { const uint8_t* b = static_cast<const uint8_t*>(p); key.insert(key.end(), b, b + n); };
+    const uint32_t head[6] = {s->n_qubits, s->n_local, (uint32_t)s->opt.tile_bits, (uint32_t)s->opt.low_bits, (uint32_t)s->opt.fuse, free_layout ? 1u : 0u};
+    put(head, sizeof(head));
+    if (!free_layout) put(s->layout, s->n_qubits);
+    for (size_t g = 0; g < n_ops; ++g) {
+        const qsv_op& op = ops[g];
+        const uint32_t f[3] = {op.kind, op.target, op.n_controls};
+        put(f, sizeof(f));
+        put(&op.param, sizeof(op.param));
+        put(&op.iparam, sizeof(op.iparam));
+        if (op.n_controls > 20 || (op.n_controls && !op.controls)) return false;  // invalid: let the scheduler report it
+        if (op.n_controls) put(op.controls, sizeof(uint32_t) * op.n_controls);
+        if (op.kind == QSV_GATE_CUSTOM) {
+            if (!op.matrix) return false;
+            const size_t dim = (size_t)1 << (op.n_controls + 1);
+            if (key.size() + dim * dim * 16 + dim > kMaxKey) return false;
+            put(op.matrix, dim * dim * 16);
+            const uint8_t has_none = op.none_mask ? 1 : 0;
+            put(&has_none, 1);
+            if (op.none_mask) put(op.none_mask, dim);
+        }
+        if (key.size() > kMaxKey) return false;
+    }
+    return true;
 }
 
 }  // namespace
@@ -428,6 +522,8 @@ int qsv_destroy(qsv_state* s) {
     if (s->d_sums) cudaFree(s->d_sums);
     if (s->d_prefix) cudaFree(s->d_prefix);
     if (s->d_staging) cudaFree(s->d_staging);
+    if (s->d_scratch) cudaFree(s->d_scratch);
+    for (auto& e : s->plan_cache) qsv_plan_destroy(e.plan);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -523,12 +619,12 @@ int qsv_gather(qsv_state* s, const uint64_t* indices, uint64_t count, double* ho
             if (!mine[i] && !s->comm) return set_error(s, QSV_ERR_INVALID_ARG, "index %llu is outside this rank's shard", (unsigned long long)indices[i]);
             local[i] = mine[i] ? (phys & (local_len(s) - 1)) : 0;
         }
-        uint64_t* d_idx = nullptr;
-        cplx* d_out = nullptr;
-        QSV_CUDA(s, cudaMalloc(&d_idx, sizeof(uint64_t) * count));
-        cudaError_t e = cudaMalloc(&d_out, sizeof(cplx) * count);
-        if (e != cudaSuccess) { cudaFree(d_idx); return set_error(s, QSV_ERR_OUT_OF_MEMORY, "cudaMalloc: %s", cudaGetErrorString(e)); }
-        int rc = QSV_OK;
+        const size_t idx_bytes = (sizeof(uint64_t) * count + 255) & ~size_t(255);
+        int rc = ensure_scratch(s, idx_bytes + sizeof(cplx) * count);
+        if (rc != QSV_OK) return rc;
+        uint64_t* d_idx = static_cast<uint64_t*>(s->d_scratch);
+        cplx* d_out = reinterpret_cast<cplx*>(static_cast<uint8_t*>(s->d_scratch) + idx_bytes);
+        cudaError_t e;
         if ((e = cudaMemcpyAsync(d_idx, local.data(), sizeof(uint64_t) * count, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess ||
             (e = launch_gather(s->d_state, d_idx, d_out, count, s->stream)) != cudaSuccess ||
             (e = cudaMemcpyAsync(host_amps, d_out, sizeof(cplx) * count, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess ||
@@ -544,8 +640,6 @@ int qsv_gather(qsv_state* s, const uint64_t* indices, uint64_t count, double* ho
                 (e = cudaStreamSynchronize(s->stream)) != cudaSuccess)
                 rc = set_error(s, QSV_ERR_NCCL, "gather across ranks: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
         }
-        cudaFree(d_idx);
-        cudaFree(d_out);
         return rc;
     } catch (const std::bad_alloc&) {
         return set_error(s, QSV_ERR_OUT_OF_MEMORY, "host allocation failed");
@@ -554,24 +648,59 @@ int qsv_gather(qsv_state* s, const uint64_t* indices, uint64_t count, double* ho
 
 int qsv_apply(qsv_state* s, const qsv_op* ops, size_t n_ops, qsv_stats* stats) {
     QSV_ENTER(s);
-    qsv_plan* p = nullptr;
-    // a pending basis state has no data to move, so the scheduler may choose the initial layout of a sharded register
-    int rc = qsv_plan_create_ex(&p, s->n_qubits, s->n_local, ops, n_ops, (uint32_t)s->opt.tile_bits, (uint32_t)s->opt.low_bits, s->opt.fuse,
-                                s->lazy_basis ? nullptr : s->layout, s->lazy_basis && s->world > 1);
-    if (rc != QSV_OK) return set_error(s, rc, "%s", qsv_plan_last_error());
     try {
-        rc = run_plan_impl(s, p, stats);
-        if (rc == QSV_OK) {
-            cudaError_t e = cudaStreamSynchronize(s->stream);  // the plan's device copy is freed below
-            if (e != cudaSuccess) rc = set_error(s, QSV_ERR_CUDA, "fused pass failed: %s", cudaGetErrorString(e));
+        // a pending basis state has no data to move, so the scheduler may choose the initial layout of a sharded register
+        const bool free_layout = s->lazy_basis && s->world > 1;
+        std::vector<uint8_t> key;
+        const bool cacheable = plan_cache_key(s, ops, n_ops, free_layout, key);
+        qsv_plan* p = nullptr;
+        if (cacheable)
+            for (auto& e : s->plan_cache)
+                if (e.key == key) {
+                    e.stamp = ++s->plan_stamp;
+                    p = e.plan;
+                    break;
+                }
+        bool owned = false;
+        if (!p) {
+            int rc = qsv_plan_create_ex(&p, s->n_qubits, s->n_local, ops, n_ops, (uint32_t)s->opt.tile_bits, (uint32_t)s->opt.low_bits, s->opt.fuse,
+                                        s->lazy_basis ? nullptr : s->layout, free_layout);
+            if (rc != QSV_OK) return set_error(s, rc, "%s", qsv_plan_last_error());
+            if (cacheable) {
+                constexpr size_t kCacheSlots = 4;
+                if (s->plan_cache.size() >= kCacheSlots) {  // evict the least recently used plan (its device copy may still be in use)
+                    size_t lru = 0;
+                    for (size_t i = 1; i < s->plan_cache.size(); ++i)
+                        if (s->plan_cache[i].stamp < s->plan_cache[lru].stamp) lru = i;
+                    cudaStreamSynchronize(s->stream);
+                    qsv_plan_destroy(s->plan_cache[lru].plan);
+                    s->plan_cache.erase(s->plan_cache.begin() + (long)lru);
+                }
+                qsv_state::CachedPlan e;
+                e.key.swap(key);
+                e.plan = p;
+                e.stamp = ++s->plan_stamp;
+                s->plan_cache.push_back(std::move(e));
+            } else {
+                owned = true;
+            }
         }
+        int rc = run_plan_impl(s, p, stats);
+        if (owned) {
+            if (rc == QSV_OK) {
+                cudaError_t e = cudaStreamSynchronize(s->stream);  // the plan's device copy is freed below
+                if (e != cudaSuccess) rc = set_error(s, QSV_ERR_CUDA, "fused pass failed: %s", cudaGetErrorString(e));
+            }
+            qsv_plan_destroy(p);
+        }
+        return rc;
+    } catch (const std::bad_alloc&) {
+        return set_error(s, QSV_ERR_OUT_OF_MEMORY, "host allocation failed");
     } catch (const std::exception& e) {
-        rc = set_error(s, QSV_ERR_INTERNAL, "%s", e.what());
+        return set_error(s, QSV_ERR_INTERNAL, "%s", e.what());
     } catch (...) {
-        rc = set_error(s, QSV_ERR_INTERNAL, "unexpected exception in qsv_apply");
+        return set_error(s, QSV_ERR_INTERNAL, "unexpected exception in qsv_apply");
     }
-    qsv_plan_destroy(p);
-    return rc;
 }
 
 int qsv_run_plan(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
@@ -591,7 +720,7 @@ int qsv_sample(qsv_state* s, const double* uniforms, uint64_t shots, uint64_t* o
     if (shots == 0) return QSV_OK;
     if (!uniforms || !out_indices) return set_error(s, QSV_ERR_INVALID_ARG, "NULL argument");
     { int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
-    int rc = ensure_prefix(s);
+    int rc = s->comm ? ensure_total(s) : ensure_prefix(s);
     if (rc != QSV_OK) return rc;
     // Sharded: the cumulative sums run over the physical order (rank 0's shard first); every rank receives the same
     // uniforms, answers the shots that fall into its interval and the minimum over ranks assembles the result.
@@ -602,11 +731,11 @@ int qsv_sample(qsv_state* s, const double* uniforms, uint64_t shots, uint64_t* o
         if (!shard_allgather_f64(s->comm, s->total_prob, totals.data(), err)) return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
         for (int r = 0; r < s->rank; ++r) offset += totals[r];
     }
-    double* d_u = nullptr;
-    uint64_t* d_out = nullptr;
-    QSV_CUDA(s, cudaMalloc(&d_u, sizeof(double) * shots));
-    cudaError_t e = cudaMalloc(&d_out, sizeof(uint64_t) * shots);
-    if (e != cudaSuccess) { cudaFree(d_u); return set_error(s, QSV_ERR_OUT_OF_MEMORY, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    const size_t u_bytes = (sizeof(double) * shots + 255) & ~size_t(255);
+    rc = ensure_scratch(s, u_bytes + sizeof(uint64_t) * shots);
+    if (rc != QSV_OK) return rc;
+    double* d_u = static_cast<double*>(s->d_scratch);
+    uint64_t* d_out = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(s->d_scratch) + u_bytes);
     std::vector<double> shifted;
     const double* src = uniforms;
     if (s->comm) {  // shots below this rank's interval get a negative uniform (-> not mine), shots above fall off the end
@@ -615,14 +744,13 @@ int qsv_sample(qsv_state* s, const double* uniforms, uint64_t shots, uint64_t* o
         src = shifted.data();
     }
     std::string err;
+    cudaError_t e;
     if ((e = cudaMemcpyAsync(d_u, src, sizeof(double) * shots, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess ||
         (e = launch_sample_shots(s->d_state, s->d_prefix, s->n_blocks, s->block_bits, d_u, shots, rank_base(s), d_out, s->sm_count, s->stream)) != cudaSuccess ||
         (s->comm && !shard_allreduce_min_u64(s->comm, d_out, shots, err)) ||
         (e = cudaMemcpyAsync(out_indices, d_out, sizeof(uint64_t) * shots, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(s->stream)) != cudaSuccess)
         rc = set_error(s, err.empty() ? QSV_ERR_CUDA : QSV_ERR_NCCL, "sample: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
-    cudaFree(d_u);
-    cudaFree(d_out);
     if (rc == QSV_OK && !s->layout_identity)
         for (uint64_t i = 0; i < shots; ++i)
             if (out_indices[i] != UINT64_MAX) out_indices[i] = to_logical(s, out_indices[i]);
@@ -633,7 +761,7 @@ int qsv_norm_sqr(qsv_state* s, double* out) {
     QSV_ENTER(s);
     if (!out) return set_error(s, QSV_ERR_INVALID_ARG, "out is NULL");
     { int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
-    int rc = ensure_prefix(s);
+    int rc = ensure_total(s);
     if (rc != QSV_OK) return rc;
     double total = s->total_prob;
     if (s->comm) {
@@ -647,6 +775,14 @@ int qsv_norm_sqr(qsv_state* s, double* out) {
 int qsv_get_layout(const qsv_state* s, uint8_t* out_layout, size_t cap) {
     if (!s || !out_layout || cap < s->n_qubits) return set_error(nullptr, QSV_ERR_INVALID_ARG, "bad argument");
     memcpy(out_layout, s->layout, s->n_qubits);
+    return QSV_OK;
+}
+
+int qsv_last_step_ms(const qsv_state* s, double* out_ms, size_t cap, size_t* n_steps) {
+    if (!s || !n_steps) return set_error(nullptr, QSV_ERR_INVALID_ARG, "NULL argument");
+    *n_steps = s->last_step_ms.size();
+    if (out_ms)
+        for (size_t i = 0; i < s->last_step_ms.size() && i < cap; ++i) out_ms[i] = s->last_step_ms[i];
     return QSV_OK;
 }
 

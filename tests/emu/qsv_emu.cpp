@@ -14,10 +14,21 @@
 #include "../../quantr_b200/csrc/pass_core.h"
 #include "../../quantr_b200/csrc/peer_swap.h"
 #include "../../quantr_b200/csrc/plan_handle.h"
+#include "../../quantr_b200/csrc/tma_tile.h"
 
 using namespace qsv;
 
-static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const PassInit* init = nullptr) {
+// 1: passes whose tile is a tensor-map box are walked the way pass_kernel_tma.cu moves them (box copies through the
+// software TMA model of tma_tile.h, tile phases from the two half-index tables, scaled last round + box store);
+// 0: the way the synchronous kernel does (per-thread loads, term-loop phases).
+static int g_tma_mode = 0;
+extern "C" void qsv_emu_set_tma_mode(int on) { g_tma_mode = on; }
+// number of passes the last qsv_emu_run_* call walked in TMA mode, and the largest number of boxes per tile among them
+static uint32_t g_tma_passes = 0, g_tma_max_boxes = 0;
+extern "C" uint32_t qsv_emu_tma_passes(void) { return g_tma_passes; }
+extern "C" uint32_t qsv_emu_tma_max_boxes(void) { return g_tma_max_boxes; }
+
+static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const PassInit* init = nullptr, uint32_t n_alloc = 0) {
     static PassParams<kMaxRounds, kMaxOps> P;  // what the kernel receives by value
     if (!fill_params(blob, P)) return;
     constexpr int W = kMaxOps / 32;
@@ -48,10 +59,47 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
     const bool direct = (P.hdr.flags & PASS_DIRECT_STORE) != 0;
     const double sc = P.hdr.final_scale;
     char* tb = reinterpret_cast<char*>(tile.data());
+    // TMA mode: tensor-map description of the tile + the external-phase tables exactly as the device builds them
+    TmaTileDesc desc;
+    const bool tma = g_tma_mode && n_alloc && T >= 6 && make_tma_tile(P.hdr, n_alloc, desc);
+    const uint32_t a_bits = ext_table_low_bits(P.hdr.n_tiles);
+    const uint64_t tbl_len = ext_table_len(P.hdr.n_tiles);
+    std::vector<cplx> ext_tbl;
+    if (tma) {
+        ++g_tma_passes;
+        if (desc.tile.n_boxes > g_tma_max_boxes) g_tma_max_boxes = desc.tile.n_boxes;
+        ext_tbl.resize((size_t)P.hdr.n_ext_ops * tbl_len);
+        for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
+            if (P.ops[o].type == OP_DIAG && P.ops[o].ext_slot != kNoExtSlot) {
+                const DiagExtTerm* terms = reinterpret_cast<const DiagExtTerm*>(blob + P.ops[o].ext_off);
+                for (uint64_t i = 0; i < tbl_len; ++i) {
+                    const bool low = i < (1ull << a_bits);
+                    ext_tbl[(size_t)P.ops[o].ext_slot * tbl_len + i] =
+                        ext_table_entry(P.hdr, P.ops[o].theta0, terms, P.ops[o].n_ext, low ? i : (i - (1ull << a_bits)) << a_bits, rank_hi, low);
+                }
+            }
+    }
+    auto tma_move = [&](uint64_t tile_id, bool store) {  // every box of tile `tile_id`, coordinates as the kernel computes them
+        double* gd = reinterpret_cast<double*>(state);
+        for (uint32_t j = 0; j < desc.tile.n_boxes; ++j) {
+            int32_t c[kTmaRank];
+            tma_tile_coords(desc.tile, (uint32_t)tile_id, j, c);
+            char* sb = tb + (size_t)j * desc.tile.box_bytes;
+            tma_box_walk(desc, c, [&](uint64_t goff, uint64_t soff) {
+                if (store) gd[goff] = *reinterpret_cast<double*>(sb + soff);
+                else *reinterpret_cast<double*>(sb + soff) = gd[goff];
+            });
+        }
+    };
     for (uint64_t t = 0; t < P.hdr.n_tiles; ++t) {
         const uint64_t base = deposit(t, P.hdr.ext_segs, P.hdr.n_ext_segs);
         const uint64_t base_full = base | rank_hi;
         const bool holds = init && base_full == init->base_full;
+        if (init && init->mode == 2 && !holds && tma) {  // bulk store from the zeroed buffer
+            memset(tile.data(), 0, sizeof(cplx) * tile_len);
+            tma_move(t, true);
+            continue;
+        }
         if (init && init->mode == 2 && !holds) {  // fused initialisation, zero tile in -> zero tile out
             for (uint32_t tid = 0; tid < threads; ++tid) {
                 const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, P.hdr.n_tile_segs);
@@ -60,6 +108,8 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
             }
             continue;
         }
+        if (tma && !init) tma_move(t, false);
+        else
         for (uint32_t tid = 0; tid < threads; ++tid) {  // load phase exactly as the kernel addresses it
             const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, P.hdr.n_tile_segs);
             const uint32_t soff_t = swz(tid) << 4;
@@ -71,7 +121,16 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
                 }
         }
         for (uint32_t o = 0; o < P.hdr.n_ops; ++o)
-            if (P.ops[o].type == OP_DIAG) ext_phase[P.ops[o].diag_index] = diag_ext_phase(P.ops[o], blob, base_full);
+            if (P.ops[o].type == OP_DIAG) {
+                if (tma && !init && P.ops[o].ext_slot != kNoExtSlot) {
+                    const cplx* tbl = &ext_tbl[(size_t)P.ops[o].ext_slot * tbl_len];
+                    ext_phase[P.ops[o].diag_index] = cmul(tbl[t & ((1ull << a_bits) - 1)], tbl[(1ull << a_bits) + (t >> a_bits)]);
+                } else if (tma && !init) {
+                    ext_phase[P.ops[o].diag_index] = diag_ext_phase_terms(P.ops[o].theta0, nullptr, 0, 0);
+                } else {
+                    ext_phase[P.ops[o].diag_index] = diag_ext_phase(P.ops[o], blob, base_full);
+                }
+            }
         for (uint32_t r = 0; r < P.hdr.n_rounds; ++r) {
             const DevRound& R = P.rounds[r];
             if (R.type == ROUND_REG) {
@@ -91,6 +150,8 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
                             if (sc != 1.0) { v.x *= sc; v.y *= sc; }
                             state[g + P.loads.store_goff[s]] = v;
                         }
+                    } else if (tma && r + 1 == P.hdr.n_rounds) {
+                        round_store_tile_scaled(R, lb, tile.data(), a, sc);
                     } else {
                         round_store_tile(R, lb, tile.data(), a);
                     }
@@ -105,11 +166,14 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
                 for (uint32_t e = 0; e < groups; ++e) {
                     cplx out[kSlots];
                     memcpy(out, &dense_out[(size_t)e * kSlots], sizeof(out));
+                    if (tma && r + 1 == P.hdr.n_rounds)
+                        for (int sl = 0; sl < kSlots; ++sl) { out[sl].x *= sc; out[sl].y *= sc; }
                     dense_store(e, tile.data(), out);
                 }
             }
         }
         if (direct) continue;
+        if (tma) { tma_move(t, true); continue; }
         for (uint32_t tid = 0; tid < threads; ++tid) {
             const uint64_t goff_t = deposit(tid, P.hdr.tile_segs, P.hdr.n_tile_segs);
             const uint32_t soff_t = swz(tid) << 4;
@@ -126,17 +190,18 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
 // Runs every PASS step in order on one rank's shard (plans without EXCHANGE steps).
 extern "C" int qsv_emu_run_plan(const qsv_plan* p, double* amps, uint64_t rank) {
     if (!p || !amps) return 1;
+    g_tma_passes = g_tma_max_boxes = 0;
     const uint64_t rank_hi = rank << p->plan.n_local;
     for (const auto& st : p->plan.steps) {
         if (st.kind != PlanStep::PASS) return 2;  // the caller must drive exchanges (qsv_emu_run_pass per step)
-        run_pass(p->plan.passes[st.pass_index].data(), reinterpret_cast<cplx*>(amps), rank_hi);
+        run_pass(p->plan.passes[st.pass_index].data(), reinterpret_cast<cplx*>(amps), rank_hi, nullptr, p->plan.n_alloc);
     }
     return 0;
 }
 
 extern "C" int qsv_emu_run_pass(const qsv_plan* p, uint32_t pass_index, double* amps, uint64_t rank) {
     if (!p || !amps || pass_index >= p->plan.passes.size()) return 1;
-    run_pass(p->plan.passes[pass_index].data(), reinterpret_cast<cplx*>(amps), rank << p->plan.n_local);
+    run_pass(p->plan.passes[pass_index].data(), reinterpret_cast<cplx*>(amps), rank << p->plan.n_local, nullptr, p->plan.n_alloc);
     return 0;
 }
 
@@ -174,10 +239,10 @@ extern "C" int qsv_emu_run_plan_fused_init(const qsv_plan* p, double* amps, uint
         const uint8_t* blob = p->plan.passes[st.pass_index].data();
         if (first) {
             const PassInit pi = make_pass_init(*reinterpret_cast<const DevPass*>(blob), phys_index, p->plan.n_local, mode);
-            run_pass(blob, reinterpret_cast<cplx*>(amps), rank_hi, &pi);
+            run_pass(blob, reinterpret_cast<cplx*>(amps), rank_hi, &pi, p->plan.n_alloc);
             first = false;
         } else {
-            run_pass(blob, reinterpret_cast<cplx*>(amps), rank_hi);
+            run_pass(blob, reinterpret_cast<cplx*>(amps), rank_hi, nullptr, p->plan.n_alloc);
         }
     }
     return 0;

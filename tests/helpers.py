@@ -94,6 +94,9 @@ def emu_lib():
         lib.qsv_plan_stats.argtypes = [vp, C.POINTER(F.QsvStats)]
         lib.qsv_plan_last_error.restype = C.c_char_p
         lib.qsv_plan_serialize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        lib.qsv_emu_set_tma_mode.argtypes = [C.c_int]
+        lib.qsv_emu_tma_passes.restype = C.c_uint32
+        lib.qsv_emu_tma_max_boxes.restype = C.c_uint32
         _emu = lib
     return _emu
 

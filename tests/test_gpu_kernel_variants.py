@@ -1,7 +1,8 @@
-"""The pass kernel exists in two builds: the pipelined one (large registers) and the synchronous one (small registers).
-The launcher picks by register size; these tests force each build onto the sizes the other one normally serves, so
-both are checked against the oracle over the whole parity suite.  The switch (QSV_ASYNC) is read once per process,
-hence the subprocesses."""
+"""The pass kernel exists in two builds: the pipelined TMA kernel (large registers, pass_kernel_tma.cu) and the
+synchronous one (small registers, pass_kernel.cu).  The launcher picks by register size; these tests force each build
+onto the sizes the other one normally serves, so both are checked against the oracle over the whole parity suite - and
+the fused basis initialisation of the pipelined kernel in each of its modes.  The switches (QSV_ASYNC, QSV_FUSED_INIT)
+are read once per process, hence the subprocesses."""
 import os
 import subprocess
 import sys
@@ -12,27 +13,27 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode,select", [("2", "golden or random or qft16 or x3sudoko or layered or rerun"), ("0", "layered or qft_closed_form"), ("2-nofast", "golden or qft16 or random")])
-def test_parity_suite_with_forced_kernel(mode, select):
+def run_inner(env_extra, select):
     if os.environ.get("QSV_VARIANT_INNER"):
         pytest.skip("inner run")
-    env = dict(os.environ, QSV_VARIANT_INNER="1", QSV_ASYNC=mode.split("-")[0])
-    if mode.endswith("nofast"):
-        env["QSV_NO_FAST"] = "1"
+    env = dict(os.environ, QSV_VARIANT_INNER="1", **env_extra)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k", select],
                        env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_fused_basis_initialisation(mode):
-    """Opt-in path (QSV_FUSED_INIT, pass_kernel_init.cu): written at the end of round 1 with no GPU time left, so it
-    is not part of the default suite yet - run with QSV_TEST_FUSED_INIT=1 to validate it on hardware."""
-    if os.environ.get("QSV_VARIANT_INNER"):
-        pytest.skip("inner run")
-    if not os.environ.get("QSV_TEST_FUSED_INIT"):
-        pytest.skip("opt-in: set QSV_TEST_FUSED_INIT=1")
-    env = dict(os.environ, QSV_VARIANT_INNER="1", QSV_FUSED_INIT=mode)
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k", "qft_closed_form or layered or golden or random"],
-                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+@pytest.mark.parametrize("mode,select", [("2", "golden or random or qft16 or x3sudoko or layered or rerun or none_overwrite"),
+                                         ("0", "layered or qft_closed_form"),
+                                         ("2-nofast", "golden or qft16 or random")])
+def test_parity_suite_with_forced_kernel(mode, select):
+    env = {"QSV_ASYNC": mode.split("-")[0]}
+    if mode.endswith("nofast"):
+        env["QSV_NO_FAST"] = "1"
+    run_inner(env, select)
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_fused_basis_initialisation_modes(mode):
+    """0: memset + ordinary first pass; 1: every tile synthesised and computed; 2 (default): zero tiles written by bulk
+    stores.  Forced onto small registers as well (QSV_ASYNC=2) so the golden vectors and random circuits run through it."""
+    run_inner({"QSV_FUSED_INIT": mode, "QSV_ASYNC": "2"}, "qft_closed_form or layered or golden or rerun or config3_depth100_live")

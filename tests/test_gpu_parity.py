@@ -177,6 +177,23 @@ def test_measure_all_chi_square_and_exact_inverse_cdf(n):
     s.close()
 
 
+def test_sampling_large_register_chunked_scan():
+    """n = 27: 2^15 block sums, scanned by the chunked (multi-CTA) scan.  After H on every wire |amp|^2 = 2^-n exactly,
+    so the sample for u is floor(u * 2^n) up to the rounding of the cumulative sums; the total must be 1."""
+    n = 27
+    c = OracleCircuit.new(n)
+    for w in range(n):
+        c.add_gate(G.H, w)
+    s = qb.DeviceState(n)
+    s.apply(encode_gates(c.circuit_gates, n))
+    u = np.random.default_rng(27).random(20000)
+    u[:4] = [0.0, 0.5, 0.999999999, 1.0 - 2.0 ** -40]
+    got = s.sample(u).astype(np.float64)
+    assert np.max(np.abs(got - np.floor(u * float(1 << n)))) <= 2.0
+    assert abs(s.norm_sqr() - 1.0) < 1e-12
+    s.close()
+
+
 def test_failed_collapse_and_strictness_on_device():
     """Non-unitary register (total probability 0.25): shots with u >= total return UINT64_MAX."""
     s = qb.DeviceState(2)
@@ -330,6 +347,25 @@ def test_two_handles_from_two_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("n,iterations", [(16, 3), (24, 2)])
+def test_grover_from_native_gates(n, iterations):
+    """The Grover workload of bench.py --workload grover (tests/workloads.py) on one GPU: the oracle at n = 16, the closed
+    form on the (marked, unmarked) plane at both sizes."""
+    from workloads import grover_circuit, grover_expected_amplitudes
+    c, info = grover_circuit(OracleCircuit, G, n, iterations=iterations)
+    enc = encode_gates(c.circuit_gates, n)
+    s = qb.DeviceState(n)
+    s.apply(enc)
+    am, ao, probe = grover_expected_amplitudes(info, iterations)
+    got = s.gather(np.array(probe["indices"], dtype=np.uint64))
+    assert np.max(np.abs(got - np.array(probe["expect"]))) < TOL
+    assert abs(s.norm_sqr() - 1.0) < 1e-12
+    if n <= 16:
+        ref = orc.simulate(n, enc.ops, enc.n_ops, None, mode="dense", threads=4)
+        assert np.max(np.abs(s.download() - ref)) < TOL
+    s.close()
 
 
 def test_plan_rerun_and_range_access():

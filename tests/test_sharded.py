@@ -197,3 +197,18 @@ def test_tiny_shards_find_exchange_partners(seed):
     ref = orc.simulate(n, enc.ops, enc.n_ops, None, mode="dense")
     out, _, _ = emu_simulate_sharded(n, enc, 1 << g, tile_bits=4, low_bits=1)
     assert np.max(np.abs(out - ref)) < 1e-12
+
+
+@pytest.mark.parametrize("n,world,iterations", [(10, 2, 2), (12, 4, 1), (13, 8, 1)])
+def test_grover_from_native_gates_sharded(n, world, iterations):
+    """BASELINE configs[4]'s Grover workload (tests/workloads.py: Toffoli V-chain + CZ, no Custom gate) on emulated ranks:
+    closed-form amplitudes, the oracle, several remaps per circuit and Toffoli controls held in the rank id."""
+    from workloads import grover_circuit, grover_expected_amplitudes
+    c, info = grover_circuit(OracleCircuit, G, n, iterations=iterations)
+    enc = encode_gates(c.circuit_gates, n)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, None, mode="dense")
+    _, _, probe = grover_expected_amplitudes(info, iterations, n_probe=256)
+    assert np.max(np.abs(ref[np.array(probe["indices"])] - np.array(probe["expect"]))) < 1e-13
+    out, plan, n_exchanges = emu_simulate_sharded(n, enc, world, tile_bits=6, low_bits=3)
+    assert np.max(np.abs(out - ref)) < 1e-12
+    assert n_exchanges >= 2
