@@ -364,7 +364,7 @@ def main():
     if args.low_bits:
         state.set_option("low_bits", args.low_bits)
     # sharded: the register starts as a basis state, so the scheduler may park the last-targeted qubits in the rank id
-    plan = qb.Plan(n, enc, n_local=n_local, tile_bits=args.tile_bits, low_bits=args.low_bits, free_layout=world > 1)
+    plan = qb.Plan(n, enc, n_local=n_local, tile_bits=args.tile_bits, low_bits=args.low_bits, free_layout=True)  # every step starts from qsv_init_basis
     pstats = plan.stats()
     pdesc = plan.describe()
     passes = pstats["n_passes"]

@@ -199,7 +199,9 @@ int qsv_plan_create(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubits,
  * amplitude index; positions >= n_local_qubits live in the rank id); NULL = identity.  With `free_layout` != 0 the
  * scheduler chooses the initial layout itself (valid when the register is a basis state, which has no data to move):
  * it parks the qubits that are targeted last in the rank id.  Gates that target a qubit held in the rank id make the
- * plan insert a global-qubit remap (QSV_STEP_EXCHANGE) before them. */
+ * plan insert a global-qubit remap (QSV_STEP_EXCHANGE) before them.  `free_layout` also tells the scheduler that the
+ * plan will start from a basis state that has not been written to HBM yet (qsv_init_basis is lazy), so its first pass is
+ * write-only (the initialisation is fused into it) and is sized accordingly; qsv_apply passes it whenever that holds. */
 int qsv_plan_create_ex(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubits, const qsv_op* ops, size_t n_ops,
                        uint32_t tile_bits, uint32_t low_bits, int fuse, const uint8_t* layout, int free_layout);
 int qsv_plan_destroy(qsv_plan* p);

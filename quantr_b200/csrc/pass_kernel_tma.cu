@@ -11,8 +11,8 @@
 //                   ride along with the tile as cp.async.bulk copies (UBLKCP) on the same mbarrier.
 //   initialisation  On a register that is a basis state not yet written to HBM (qsv_init_basis is lazy) the first pass
 //                   of a plan does not read it: the one tile holding the amplitude is synthesised in shared memory and
-//                   every other tile - all zero in, all zero out, the pass is linear - is written by a bulk tensor store
-//                   from a zeroed buffer (init.mode 2), or synthesised and computed like any other (mode 1, tests).
+//                   every other tile - all zero in, all zero out, the pass is linear - is covered by one contiguous stream
+//                   of zero stores over the shard (init.mode 2), or synthesised and computed like any other (mode 1, tests).
 //
 // Ring protocol: tile k of the CTA lives in buffer k mod NB and is worked on by group k mod G; the group that has moved
 // tile k into registers (or out through a bulk store) refills that buffer with tile k + NB.  A consumer polls the
@@ -83,6 +83,7 @@ __device__ __forceinline__ void wait_issued(const uint32_t* p, uint32_t want) {
         uint32_t v;
         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
         if (v >= want) return;
+        __nanosleep(64);  // the refill is issued by another group of the CTA: leave it the issue slots
         if (spins > (1u << 24)) __trap();
     }
 }
@@ -149,9 +150,17 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
     const bool last_is_reg = n_rounds && P.rounds[n_rounds - 1].type == ROUND_REG;
     const bool direct = (P.hdr.flags & PASS_DIRECT_STORE) != 0 && !(diag_mode & 4) && last_is_reg;
     const bool need_base = direct || (P.hdr.ext_ctrl_mask[0] | P.hdr.ext_ctrl_mask[1] | P.hdr.ext_ctrl_mask[2]) != 0 || init.mode != 0;
-    // tiles of this CTA: t_k = blockIdx.x + k * gridDim.x, k < n_my (tile ids and per-CTA counts fit 32 bits)
+    // Tiles of this CTA (tile ids and per-CTA counts fit 32 bits): the k-th tile it works on is
+    //   t_k = ((blockIdx.x + (k >> ilog) * gridDim.x) << ilog) | (k & (2^ilog - 1)),   k < n_my.
+    // With ilog = log2(kG) the kG groups of the CTA work on kG tiles with consecutive ids at the same time: tile ids count
+    // the index bits right above the tile's 128-byte rows, so the CTA's loads and stores cover kG adjacent rows (512
+    // contiguous bytes) at every row position instead of one - measured, DRAM streams 128-byte runs at ~58 % of the
+    // copy peak and 256-byte runs at ~90 % (profiles/r02_stream_probe.txt).
     const uint32_t n_tiles = (uint32_t)P.hdr.n_tiles;
-    const uint32_t n_my = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t ilog = ((uint32_t)diag_mode >> 8) & 7u, imask = (1u << ilog) - 1u;
+    const uint32_t n_super = n_tiles >> ilog;
+    const uint32_t n_my = (n_super > blockIdx.x ? (n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0) << ilog;
+    auto tile_of = [&](uint32_t k) { return ((blockIdx.x + (k >> ilog) * gridDim.x) << ilog) | (k & imask); };
     const uint32_t tbl_a_mask = (1u << tt.tbl_a_bits) - 1u;
     const uint32_t tbl_stride = (tbl_a_mask + 1u) + ((n_tiles + tbl_a_mask) >> tt.tbl_a_bits);  // entries per op: table A then table B
 
@@ -194,16 +203,25 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    cplx* zero_tile = tiles + (size_t)kG * kTileLen;  // init mode: buffers 0..kG-1 belong to the groups, buffer kG stays zero
-    if (init.mode) {
-        for (uint32_t i = tid; i < kTileLen; i += Cfg::kThreads) zero_tile[i] = cplx{0.0, 0.0};
-        fence_proxy_async();
+    // init mode 2: every tile but one is all zero in, all zero out.  The zeros are written here as one contiguous,
+    // coalesced stream over the shard - independent of the pass's tile shape, which would cost short-run write efficiency
+    // for nothing - skipping the 128-byte rows of the one tile that holds the amplitude; that tile is then synthesised
+    // and computed by the group it falls to in the loop below.
+    if (init.mode == 2) {
+        const uint64_t n_rows = 1ull << (init.n_alloc - 3);
+        const uint64_t row_mask = init.ext_mask >> 3, row_hold = (init.base_full & init.ext_mask & ((1ull << init.n_alloc) - 1ull)) >> 3;
+        const bool here = (init.base_full >> init.n_alloc) == (rank_hi >> init.n_alloc);
+        const uint64_t rows_per_cta = (n_rows + gridDim.x - 1) / gridDim.x;
+        const uint64_t r0 = rows_per_cta * blockIdx.x, r1 = r0 + rows_per_cta < n_rows ? r0 + rows_per_cta : n_rows;
+        const uint32_t sub = tid & 7u;  // amplitude within the row
+        for (uint64_t r = r0 + (tid >> 3); r < r1; r += Cfg::kThreads >> 3)
+            if (!(here && (r & row_mask) == row_hold)) st_stream(state + (r << 3) + sub, cplx{0.0, 0.0});
     }
     __syncthreads();
     // prologue: the first kNB tiles, spread over the groups
     if (!init.mode && gtid < 32u)
         for (uint32_t k = group; k < kNB; k += kG)
-            if (k < n_my) issue_load(blockIdx.x + k * gridDim.x, k, 0u);
+            if (k < n_my) issue_load(tile_of(k), k, 0u);
 
     // ---- once per launch: thread-dependent pieces that do not depend on the tile ----------------------
     uint32_t thr_act[W];
@@ -237,21 +255,18 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
 
     // tiles are dealt round-robin to the groups (every tile of a pass costs the same); buffer and use number of the
     // group's current tile are carried along instead of recomputed (k mod kNB, k / kNB)
-    uint32_t slot = group % kNB, use = group / kNB, t_id = blockIdx.x + group * gridDim.x, parity = 0;
-    const uint32_t t_step = kG * gridDim.x, t_ahead = kNB * gridDim.x;
-    for (uint32_t k = group; k < n_my; k += kG, t_id += t_step, parity ^= 1u) {
+    uint32_t slot = group % kNB, use = group / kNB, parity = 0;
+    for (uint32_t k = group; k < n_my; k += kG, parity ^= 1u) {
+        const uint32_t t_id = tile_of(k);
         uint64_t base = 0;
-        if (need_base) base = deposit(t_id, P.hdr.ext_segs, n_ext_segs);
+        if (need_base) base = tma_tile_base(tt, t_id);
         const uint64_t base_full = base | rank_hi;
         cplx* ext_phase = ext_phase2 + (size_t)parity * (n_diag + 1);
         const DiagCtx ctx{blob, ext_phase, (diag_mode & 3) == 1 ? diag_smem : nullptr, (diag_mode & 3) == 2 ? diag_smem : nullptr, kGT};
         cplx* tile;
         if (init.mode) {
             const bool holds = base_full == init.base_full;  // uniform over the group
-            if (init.mode == 2 && !holds) {  // zero tile in, zero tile out
-                if (gtid == 0) store_tile(zero_tile, t_id);
-                continue;
-            }
+            if (init.mode == 2 && !holds) continue;  // zero tile in, zero tile out: written by the stream above
             tile = tiles + (size_t)group * kTileLen;
             if (gtid == 0 && refill_pending) {
                 bulk_wait_read_all();
@@ -296,7 +311,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
                     // the tile now lives in registers: hand the buffer to the tile that will use it next, a whole
                     // round of arithmetic before this group comes back for more
                     group_barrier(group, kGT);
-                    if (gtid < 32u && k + kNB < n_my) issue_load(t_id + t_ahead, slot, use + 1u);
+                    if (gtid < 32u && k + kNB < n_my) issue_load(tile_of(k + kNB), slot, use + 1u);
                 }
                 round_ops<W, FAST>(P.rounds[r], P.ops, ctx, act, gtid, a);
                 if (direct && last) {
@@ -341,7 +356,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
                 refill_pending = true;  // init mode: only the wait before the group's buffer is synthesised again
             } else if (k + kNB < n_my) {
                 refill_pending = true;
-                refill_t = t_id + t_ahead;
+                refill_t = tile_of(k + kNB);
                 refill_slot = slot;
                 refill_use = use + 1u;
             }
@@ -436,10 +451,15 @@ static cudaError_t launch_tma_t(cplx* state, const uint8_t* dev_blob, const uint
     static std::atomic<uint64_t> configured{0};
     err = ensure_dynamic_smem(pass_kernel_tma<T, NR, NO, FAST>, (int)kSmemLimit, configured);
     if (err != cudaSuccess) return err;
+    // tile interleave (see the kernel): the groups of a CTA take tiles with consecutive ids; QSV_TILE_INTERLEAVE=0 turns it off
+    static const int interleave = getenv("QSV_TILE_INTERLEAVE") ? atoi(getenv("QSV_TILE_INTERLEAVE")) : 1;
+    uint32_t ilog = 0;
+    if (interleave)
+        while ((1u << (ilog + 1)) <= Cfg::kGroups && (hdr.n_tiles >> (ilog + 1)) >= 1) ++ilog;
     uint64_t grid = (uint64_t)sm_count;
-    if (grid > hdr.n_tiles) grid = hdr.n_tiles;
+    if (grid > (hdr.n_tiles >> ilog)) grid = hdr.n_tiles >> ilog;
     static const int tma_store = getenv("QSV_TMA_STORE") ? atoi(getenv("QSV_TMA_STORE")) : 0;  // developer A/B switch: 1 = no register->global stores
-    pass_kernel_tma<T, NR, NO, FAST><<<(unsigned)grid, Cfg::kThreads, smem, stream>>>(map, state, dev_blob, ext_tbl, rank_hi, mode | (tma_store ? 4 : 0), init, desc.tile, params);
+    pass_kernel_tma<T, NR, NO, FAST><<<(unsigned)grid, Cfg::kThreads, smem, stream>>>(map, state, dev_blob, ext_tbl, rank_hi, mode | (tma_store ? 4 : 0) | (int)(ilog << 8), init, desc.tile, params);
     return cudaGetLastError();
 }
 

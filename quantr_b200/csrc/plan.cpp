@@ -200,6 +200,7 @@ struct RoundB {
 struct PassB {
     uint64_t req = 0;          // physical bits that must be tile bits
     bool relaxed_low = false;  // a wide Custom gate took the low passenger bits
+    bool big = false;          // all required bits lie in the contiguous low block: the pass uses the larger tile (kBigTileBits)
     std::vector<RoundB> rounds;
     size_t n_ops = 0;
     bool empty() const { return rounds.empty(); }
@@ -237,8 +238,10 @@ cplx unit_phase(double half_turns) {
     return r;
 }
 
+constexpr int kBigTileBits = 12;  // tile of a pass over the contiguous low index bits (no short runs to pay for)
+
 void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
-    const int T = std::min<int>(plan.opt.tile_bits, (int)plan.n_alloc);
+    const int T = pb.big ? kBigTileBits : std::min<int>(plan.opt.tile_bits, (int)plan.n_alloc);
     const int nloc = (int)plan.n_alloc;
     // tile bits = required bits + lowest free bits
     uint64_t tile_mask = pb.req;
@@ -367,8 +370,51 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
                 else d.cmask_thr |= 1u << lp;
             }
         };
+        // A whole round of a QFT / phase-estimation ladder (kCodeQft4): H + ladder on four physically adjacent register
+        // bits, highest first, the ladders' register-bit phases being pi/2^(distance); the lowest stage may be a bare H.
+        // Emitted as one macro-op followed - outside the round's op range - by the stages' DIAG ops, which keep supplying
+        // the tile/thread factors.
+        uint32_t qft4_diags = 0;
+        bool qft4 = false;
+        const int n_st = (int)rb.reg.size();  // stages = register bits that are targets (3: the fourth, highest, bit is a passenger)
+        if (plan.opt.fuse && plan.opt.qft4 && kRegBits == 4 && (n_st == 4 || n_st == 3) &&
+            (rb.ops.size() == (size_t)(2 * n_st) || rb.ops.size() == (size_t)(2 * n_st - 1))) {
+            bool ok = true;
+            for (int j = 0; j + 1 < n_st; ++j) ok &= tile_phys[reg_local[j + 1]] == tile_phys[reg_local[j]] + 1;
+            for (int st = 0; st < n_st && ok; ++st) {  // stage st works on slot n_st - 1 - st
+                const int j = n_st - 1 - st;
+                const LOp& h = lops[rb.ops[2 * st]];
+                ok &= h.kind == LOp::MAT && h.mtype == OP_MAT_HADAMARD && h.cmask == 0 && slot_of[local_of[h.target]] == j;
+                if (!ok || (size_t)(2 * st + 1) >= rb.ops.size()) break;  // bare H as the last stage
+                const LOp& d = lops[rb.ops[2 * st + 1]];
+                ok &= d.kind == LOp::DIAG && d.cmask == (1ull << h.target);
+                if (!ok) break;
+                double want[4] = {0, 0, 0, 0};
+                for (int i = 0; i < j; ++i) want[i] = ldexp(1.0, -(j - i));
+                double have[4] = {0, 0, 0, 0};
+                for (auto& t : d.lin) {
+                    const int lp = t.first < nloc ? local_of[t.first] : -1;
+                    if (lp >= 0 && slot_of[lp] >= 0) have[slot_of[lp]] += t.second;
+                }
+                for (int i = 0; i < 4; ++i) ok &= have[i] == want[i];
+            }
+            if (ok) {
+                qft4 = true;
+                qft4_diags = (uint32_t)rb.ops.size() / 2;  // one per stage, or one less with a bare H at the end
+                DevOp mo;
+                memset(&mo, 0, sizeof(mo));
+                mo.type = OP_QFT4;
+                mo.code = kCodeQft4;
+                mo.slot = qft4_diags;
+                mo.cmask_reg = (uint32_t)n_st;
+                mo.ext_slot = kNoExtSlot;
+                ops.push_back(mo);
+                n_hadamard += (uint32_t)n_st;
+            }
+        }
         for (size_t ri = 0; ri < rb.ops.size(); ++ri) {
             size_t oi = rb.ops[ri];
+            if (qft4 && lops[oi].kind == LOp::MAT) continue;  // the macro-op's Hadamards
             // Peephole: an uncontrolled Hadamard followed by a diagonal op controlled by exactly the Hadamard's bit
             // (one stage of a QFT-style ladder) becomes one fused op: emitted as the DIAG op with an HD dispatch code.
             int fused_hadamard_slot = -1;
@@ -456,10 +502,11 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
             }
             d.code = op_dispatch_code(d);
             if (fused_hadamard_slot >= 0) d.code = kCodeHdBase + ((d.flags & DIAG_HAS_REG) ? 4u : 0u) + (uint32_t)fused_hadamard_slot;
+            if (qft4) d.code = kCodeNop;  // applied by the macro-op in front of it
             if (d.cmask_ext) hdr.ext_ctrl_mask[ops.size() >> 5] |= 1u << (ops.size() & 31);
             ops.push_back(d);
         }
-        dr.n_ops = (uint32_t)ops.size() - dr.first_op;
+        dr.n_ops = qft4 ? 1u : (uint32_t)ops.size() - dr.first_op;  // the macro-op's DIAG ops sit outside the range
         rounds.push_back(dr);
     }
     if (rounds.size() > (size_t)kMaxRounds || ops.size() > (size_t)kMaxOps) fail("internal: pass exceeds round/op caps");
@@ -599,12 +646,18 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
     plan.initial_layout.assign(layout.begin(), layout.begin() + n);
 
     // Greedy in-order grouping of (physical-space) ops into passes for a given number of low passenger bits.
-    auto schedule = [&](const std::vector<LOp>& lops, int L, std::vector<PassB>& out) {
+    // L_first: passenger bits of the segment's first pass (it may differ: on a basis state the plan's first pass is
+    // write-only, its run length does not matter, so it can hold one more target)
+    auto schedule = [&](const std::vector<LOp>& lops, int L_first, int L, std::vector<PassB>& out) {
         out.clear();
-        const uint64_t low_mask = (T == nloc) ? 0 : ((1ull << L) - 1);  // single-tile states: every bit is a tile bit
+        uint64_t low_mask = (T == nloc) ? 0 : ((1ull << L_first) - 1);  // single-tile states: every bit is a tile bit
+        const bool allow_big = plan.opt.fuse && T == 11 && nloc >= 23 && plan.opt.big_low_pass;
         PassB cur;
         auto close_pass = [&]() {
-            if (!cur.empty()) out.push_back(std::move(cur));
+            if (!cur.empty()) {
+                out.push_back(std::move(cur));
+                low_mask = (T == nloc) ? 0 : ((1ull << L) - 1);
+            }
             cur = PassB();
         };
         for (size_t i = 0; i < lops.size(); ++i) {
@@ -613,12 +666,18 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
             if (!plan.opt.fuse) close_pass();
             // Can the op join the open pass?  Its targets must fit next to the pass's tile bits and the
             // low passenger bits, and the pass must stay within the kernel's round/op caps.
-            const bool can_join = !cur.relaxed_low && popcnt(cur.req | tg | low_mask) <= T &&
-                                  cur.n_ops + 1 <= (size_t)kMaxOps && cur.rounds.size() + 2 <= (size_t)kMaxRounds;
+            const bool caps_ok = cur.n_ops + 1 <= (size_t)kMaxOps && cur.rounds.size() + 2 <= (size_t)kMaxRounds;
+            const bool fits = !cur.big && popcnt(cur.req | tg | low_mask) <= T;
+            // a pass whose targets all lie in the lowest kBigTileBits index bits streams contiguous 64 KiB tiles whatever
+            // its size, so it may hold more targets than the strided passes (large registers only)
+            const bool fits_big = allow_big && ((cur.req | tg) >> kBigTileBits) == 0;
+            const bool can_join = !cur.relaxed_low && (fits || fits_big) && caps_ok;
             if (!can_join) close_pass();
+            const bool now_big = allow_big && ((cur.req | tg) >> kBigTileBits) == 0 && popcnt(cur.req | tg | low_mask) > T;
             // A Custom gate wider than T - low_bits gets a pass of its own without passenger bits.
-            const bool relaxed = popcnt(cur.req | tg | low_mask) > T;
+            const bool relaxed = !now_big && !cur.big && popcnt(cur.req | tg | low_mask) > T;
             cur.req |= tg;
+            cur.big |= now_big;
             cur.relaxed_low |= relaxed;
             if (lop.kind == LOp::DENSE) {
                 RoundB r;
@@ -648,24 +707,38 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
     // Cost model, in units of one pass streamed at the HBM roofline.  Memory term: measured streaming efficiency of a
     // tile whose contiguous runs are 16 B << run_bits; compute term: measured per-op and per-round costs of the pass
     // kernel (tools/stream_probe.py, tools/diag_probe.py on B200, n = 30).  The two overlap only partly.
-    auto plan_cost = [&](const std::vector<LOp>& lops, const std::vector<PassB>& passes) {
+    // write_only_first: the first pass of the plan runs on a basis state that was never written to HBM (fused
+    // initialisation): zeros are streamed contiguously whatever the tile shape, one tile is computed
+    auto plan_cost = [&](const std::vector<LOp>& lops, const std::vector<PassB>& passes, bool write_only_first) {
         double total = 0;
+        bool first = true;
         for (const PassB& pb : passes) {
+            if (first && write_only_first) {
+                first = false;
+                total += 0.55;
+                continue;
+            }
+            first = false;
+            const int Tp = pb.big ? kBigTileBits : T;
             uint64_t tile_mask = pb.req;
-            for (int b = 0; b < nloc && popcnt(tile_mask) < T; ++b) tile_mask |= 1ull << b;
+            for (int b = 0; b < nloc && popcnt(tile_mask) < Tp; ++b) tile_mask |= 1ull << b;
             int run_bits = 0;
             while (run_bits < nloc && ((tile_mask >> run_bits) & 1)) ++run_bits;
-            const double eff = run_bits <= 3 ? 0.47 : run_bits == 4 ? 0.68 : run_bits == 5 ? 0.75 : run_bits == 6 ? 0.80 : run_bits == 7 ? 0.85 : 0.90;
+            // measured with the pipelined TMA kernel (profiles/r02_stream_probe.txt, r02_qft33_tile_configs.txt): tiles whose
+            // rows are one 128-byte line stream at ~60 % of the copy peak, two lines at ~88 %
+            const double eff = run_bits <= 3 ? 0.60 : run_bits == 4 ? 0.88 : run_bits == 5 ? 0.90 : 0.93;
             const double mem = 1.0 / eff;
-            double compute = 0.9 + 0.145 * (pb.rounds.empty() ? 0.0 : (double)pb.rounds.size() - 1.0);
+            double compute = 0.6 + 0.12 * (pb.rounds.empty() ? 0.0 : (double)pb.rounds.size() - 1.0);
             for (const RoundB& r : pb.rounds)
                 for (size_t oi : r.ops) {
                     const LOp& lop = lops[oi];
                     if (lop.kind == LOp::DENSE) compute += 0.5;
-                    else if (lop.kind == LOp::DIAG) compute += 0.06;
-                    else compute += lop.mtype == OP_MAT_GENERAL ? 0.13 : lop.mtype == OP_MAT_HADAMARD ? 0.053 : 0.08;
+                    else if (lop.kind == LOp::DIAG) compute += 0.035;
+                    else compute += lop.mtype == OP_MAT_GENERAL ? 0.09 : lop.mtype == OP_MAT_HADAMARD ? 0.035 : 0.05;
                 }
-            total += std::max(mem, compute) + 0.1 * std::min(mem, compute);
+            // the 2^12-tile kernel keeps one tile in flight per SM (three 64 KiB buffers, two compute groups): measured
+            // ~1.3x slower than the 2^11-tile kernel on the same work
+            total += (std::max(mem, compute) + 0.1 * std::min(mem, compute)) * (Tp == 12 && T == 11 ? 1.3 : 1.0);
         }
         return total;
     };
@@ -678,20 +751,23 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
         seg.reserve(i1 - i0);
         for (size_t i = i0; i < i1; ++i) seg.push_back(remap_lop(plan.lops[i], layout));
         std::vector<PassB> best;
+        const bool write_only_first = free_layout && i0 == 0 && plan.passes.empty() && nloc >= 23;  // fused initialisation will apply
         if (plan.opt.low_bits > 0 || T == nloc || !plan.opt.fuse) {
             const int L = std::max(0, std::min<int>(plan.opt.low_bits > 0 ? plan.opt.low_bits : 3, T - 1));
             chosen_L = L;
-            schedule(seg, L, best);
+            schedule(seg, L, L, best);
         } else {
             // low_bits = 0: pick the number of passenger bits that minimises the modelled cost (longer runs stream
-            // better, fewer passenger bits fuse more gates per pass); ties go to the longer runs.
+            // better, fewer passenger bits fuse more gates per pass); ties go to the longer runs.  A write-only first
+            // pass chooses its own.
             double best_cost = 0;
             std::vector<PassB> cand;
-            for (int L = std::min(8, T - 1); L >= 3; --L) {
-                schedule(seg, L, cand);
-                const double c = plan_cost(seg, cand);
-                if (best.empty() || c < best_cost - 1e-9) { best_cost = c; chosen_L = L; best.swap(cand); }
-            }
+            for (int L = std::min(8, T - 1); L >= 3; --L)
+                for (int Lf = write_only_first ? 3 : L; Lf <= (write_only_first ? std::min(8, T - 1) : L); ++Lf) {
+                    schedule(seg, Lf, L, cand);
+                    const double c = plan_cost(seg, cand, write_only_first);
+                    if (best.empty() || c < best_cost - 1e-9) { best_cost = c; chosen_L = L; best.swap(cand); }
+                }
         }
         for (const PassB& pb : best) {
             emit_pass(plan, pb, seg);

@@ -40,6 +40,8 @@ struct PlanOptions {
     int low_bits = 0;     // contiguous low index bits kept in every tile; 0 = chosen per circuit by the cost model
     int fuse = 1;
     int direct_store = 1; // last round stores registers straight to global memory when that stays coalesced
+    int qft4 = 1;         // whole QFT-ladder rounds become one radix-16 macro-op (pass_core.h qft4_apply)
+    int big_low_pass = 1; // a pass over the contiguous low index bits may use a 2^12 tile next to 2^11 strided passes
 };
 
 // One step of a plan: a fused pass over the local shard, or a global-qubit remap that swaps the index bits held in

@@ -28,6 +28,8 @@ int qsv_plan_create_ex(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubit
         if (low_bits) opt.low_bits = (int)low_bits;
         opt.fuse = fuse;
         if (const char* env = getenv("QSV_DIRECT_STORE")) opt.direct_store = atoi(env) != 0;
+        if (const char* env = getenv("QSV_QFT4")) opt.qft4 = atoi(env) != 0;  // developer A/B switch
+        if (const char* env = getenv("QSV_BIG_LOW_PASS")) opt.big_low_pass = atoi(env) != 0;  // developer A/B switch
         try {
             qsv::build_plan(p->plan, n_qubits, n_local_qubits, ops, n_ops, opt, layout, free_layout != 0);
         } catch (...) {

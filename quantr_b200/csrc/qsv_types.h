@@ -62,6 +62,8 @@ enum OpType : uint32_t {
     OP_DENSE = 5,         // k-qubit Custom matrix (dense round)
     OP_MAT_HADAMARD = 6   // unnormalised butterfly a0' = a0+a1, a1' = a0-a1; the 1/sqrt2 factors of a pass are
                           // collected in DevPass::final_scale and applied once when the tile is stored
+    ,
+    OP_QFT4 = 7           // macro-op, see kCodeQft4
 };
 
 // Fully resolved dispatch code of an op inside a register round (one jump-table entry per routine):
@@ -70,7 +72,11 @@ enum OpType : uint32_t {
 constexpr int kDiagTblLen = 64;  // lo[32] (thread-index bits 0-4) + hi[32] (bits 5-9)
 //   HD  : 53 + has_reg*4 + slot: an uncontrolled Hadamard on register bit `slot` fused with the DIAG op that follows it
 //         and is controlled by exactly that bit (one stage of a QFT / phase-estimation ladder)
-constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeHdBase = 53, kCodeCount = 61;
+//   QFT4: 61: a whole register round of a QFT / phase-estimation ladder as one op - four HD stages on four physically
+//         adjacent register bits, highest first, whose register-bit phases are the QFT ones (pi/2, pi/4, pi/8).  The
+//         DevOp carries no constants; the DIAG ops of the (3 or 4, DevOp::slot) stages follow it in the op array outside
+//         the round's op range and supply the tile/thread factors (pass_core.h qft4_apply).
+constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeHdBase = 53, kCodeQft4 = 61, kCodeCount = 62;
 enum PassFlags : uint32_t {
     PASS_DIRECT_STORE = 2,  // the last round writes its registers straight to global memory (coalesced: its register bits
                             // exclude the three lowest tile bits)

@@ -650,7 +650,7 @@ int qsv_apply(qsv_state* s, const qsv_op* ops, size_t n_ops, qsv_stats* stats) {
     QSV_ENTER(s);
     try {
         // a pending basis state has no data to move, so the scheduler may choose the initial layout of a sharded register
-        const bool free_layout = s->lazy_basis && s->world > 1;
+        const bool free_layout = s->lazy_basis;  // also tells the scheduler that the plan's first pass will be write-only
         std::vector<uint8_t> key;
         const bool cacheable = plan_cache_key(s, ops, n_ops, free_layout, key);
         qsv_plan* p = nullptr;

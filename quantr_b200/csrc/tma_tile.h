@@ -32,6 +32,8 @@ struct TmaTile {
     uint32_t tshift[kTmaRank];     // first tile-id bit of dimension i's coordinate field
     uint32_t tmask[kTmaRank];      // width mask of that field (0 for unused dimensions)
     uint32_t cshift[kTmaRank];     // log2 of the box extent of dimension i (coordinates are box-aligned); dimension 0 counts doubles
+    uint32_t bshift[kTmaRank];     // index bit where dimension i's coordinate field starts (tile base = fields shifted back in place)
+    uint32_t last_lo;              // index bit where the last dimension starts
     uint32_t last_dim;             // dimension that absorbs the enumerated tile bits of boxes 1..n_boxes-1
     uint32_t n_ext_ops;            // DIAG ops with external-phase tables
     uint32_t tbl_a_bits;           // table A is indexed by the low tbl_a_bits bits of the tile id, table B by the rest
@@ -121,6 +123,7 @@ inline bool make_tma_tile(const DevPass& hdr, uint32_t n_alloc, TmaTileDesc& out
             if (i + 1 < rank && field_bits != hi - field_lo) return false;  // (cannot happen: a tile bit inside would have started a dimension)
             t.tmask[i] = field_bits >= 32 ? 0xffffffffu : ((1u << field_bits) - 1u);
             t.cshift[i] = w[i] + (i == 0 ? 1u : 0u);
+            t.bshift[i] = field_lo;
             out.dim[i] = (1ull << span) * (i == 0 ? 2ull : 1ull);
             out.box[i] = (1u << w[i]) * (i == 0 ? 2u : 1u);
             out.stride_bytes[i] = (uint64_t)sizeof(cplx) << lo[i];
@@ -128,6 +131,7 @@ inline bool make_tma_tile(const DevPass& hdr, uint32_t n_alloc, TmaTileDesc& out
             t.tshift[i] = 0;
             t.tmask[i] = 0;  // coordinate 0
             t.cshift[i] = 0;
+            t.bshift[i] = 0;
             out.dim[i] = 1;
             out.box[i] = 1;
             out.stride_bytes[i] = (uint64_t)sizeof(cplx) << n_alloc;
@@ -147,6 +151,7 @@ inline bool make_tma_tile(const DevPass& hdr, uint32_t n_alloc, TmaTileDesc& out
         t.last_segs[t.n_last_segs++] = Seg{(uint8_t)(e.src_lo + (start - e_lo)), (uint8_t)(e_hi - start), (uint8_t)(start - lo[rank - 1]), 0};
     }
     t.tmask[rank - 1] = 0;  // handled by last_segs
+    t.last_lo = lo[rank - 1];
     return true;
 }
 
@@ -160,6 +165,16 @@ QSV_HD void tma_tile_coords(const TmaTile& t, uint32_t tile_id, uint32_t j, int3
 #pragma unroll
     for (int i = 0; i < kTmaRank; ++i)
         if ((uint32_t)i == t.last_dim) c[i] = last;
+}
+
+// Element offset of tile t in the register (= deposit(t, ext_segs)), from the same fields.
+QSV_HD uint64_t tma_tile_base(const TmaTile& t, uint32_t tile_id) {
+    uint64_t base = 0;
+#pragma unroll
+    for (int i = 0; i < kTmaRank; ++i) base |= (uint64_t)((tile_id >> t.tshift[i]) & t.tmask[i]) << t.bshift[i];
+    for (uint32_t sgi = 0; sgi < t.n_last_segs; ++sgi)
+        base |= (uint64_t)((tile_id >> t.last_segs[sgi].src_lo) & ((1u << t.last_segs[sgi].width) - 1u)) << (t.last_segs[sgi].dst_lo + t.last_lo);
+    return base;
 }
 
 // Software model of one tiled-mode box copy with CU_TENSOR_MAP_SWIZZLE_128B (host emulation and unit tests):

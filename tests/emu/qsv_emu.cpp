@@ -93,6 +93,7 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
     };
     for (uint64_t t = 0; t < P.hdr.n_tiles; ++t) {
         const uint64_t base = deposit(t, P.hdr.ext_segs, P.hdr.n_ext_segs);
+        if (tma && tma_tile_base(desc.tile, (uint32_t)t) != base) __builtin_trap();  // the kernel derives the tile base from the tile id fields
         const uint64_t base_full = base | rank_hi;
         const bool holds = init && base_full == init->base_full;
         if (init && init->mode == 2 && !holds && tma) {  // bulk store from the zeroed buffer
