@@ -115,8 +115,9 @@ def grover_workload(n, iterations):
     c, info = grover_circuit(qb.Circuit, qb.Gate, n, iterations=iterations)
     gates = c.get_gates()
     n_gates = sum(1 for g in gates if g.kind != 0)
-    return {"name": f"Grover-{n}: {info['search']} search + {info['ancilla']} V-chain ancilla + 1 kick-back wire, marked item 0x{info['marked']:x}, "
-                    f"{iterations} iteration(s) of oracle + diffusion from native H/X/CNot/Toffoli ({n_gates} gates)",
+    return {"name": f"Grover-{n}: {info['search']} search + {info['ancilla']} V-chain ancilla wires" + (f" + {info['idle']} idle" if info['idle'] else "") +
+                    f", marked item 0x{info['marked']:x}, {iterations} iteration(s) of oracle + diffusion from native H/X/Toffoli/CZ ({n_gates} gates; "
+                    f"the optimal count would be ~{int(0.785 * 2 ** (info['search'] / 2))})",
             "gates": gates, "basis": 0, "n_gates": n_gates, "check": "grover", "info": info}
 
 
@@ -333,16 +334,19 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: quantr_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    nccl_id = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def new_nccl_id():  # one ncclUniqueId per communicator (= per sharded handle): made on rank 0, broadcast by torch
         lib = F.load_library()
         buf = C.create_string_buffer(128)
         if rank == 0:
             F.check(lib.qsv_nccl_unique_id(buf, 128))
         t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
         dist.broadcast(t, 0)
-        nccl_id = bytes(t.cpu().numpy().tobytes())
+        return bytes(t.cpu().numpy().tobytes())
+
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        nccl_id = new_nccl_id()
 
     n = args.qubits
     n_local = n - g
@@ -353,7 +357,7 @@ def main():
     use_peers = world > 1 and not os.environ.get("QSV_NCCL_EXCHANGE")
     parity_err = parity_remaps = None
     if world > 1 and not args.no_extras:
-        parity_err, parity_remaps = sharded_parity(qb, F, dist, torch, rank, world, local_rank, nccl_id, use_peers)
+        parity_err, parity_remaps = sharded_parity(qb, F, dist, torch, rank, world, local_rank, new_nccl_id(), use_peers)
 
     state = qb.DeviceState(n, local_rank, rank=rank, world=world, nccl_id=nccl_id)
     exchange_path = "nccl send/recv through staging"
@@ -480,6 +484,25 @@ def main():
     sampling = {"shots": args.shots, "k6_ms": k6_ms, "k6_GBps": (16.0 * (1 << n_local) / (k6_ms * 1e-3) / 1e9) if k6_ms > 0 else None,
                 "k7_ms": t_second * 1e3, "note": "K6 = prob_block_sums + scan (one read of the shard, cached until the register changes); K7 = sample_shots incl. H2D/D2H of the shots"}
 
+    # ---- the global-qubit remap in isolation (N > 1): H on wire 0, a qubit held in the rank id, on the finished register ----
+    exchange_probe = None
+    if world > 1 and args.workload == "qft":
+        probe = qb.Circuit.new(n)
+        probe.add_gate(qb.Gate.H, 0)
+        penc = encode_gates(probe.get_gates(), n)
+        state.init_basis(x)
+        state.run_plan(plan)
+        state.set_option("timing", 1)
+        st = state.apply(penc)
+        state.set_option("timing", 0)
+        t = torch.tensor([st["exchange_ms"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ex_ms = float(t[0])
+        exchange_probe = {"circuit": "H on wire 0 (held in the rank id) applied to the QFT result: one remap + one pass",
+                          "remaps": st["n_exchanges"], "bytes_sent_per_gpu": st["exchange_bytes"], "ms": ex_ms,
+                          "achieved_GBps_per_direction": (st["exchange_bytes"] / (ex_ms * 1e-3) / 1e9) if ex_ms > 0 else None,
+                          "nvlink_peak_GBps_per_direction": NVLINK_PEAK, "frac_of_peak": (st["exchange_bytes"] / (ex_ms * 1e-3) / 1e9 / NVLINK_PEAK) if ex_ms > 0 else None}
+
     peak, peak_src = read_peaks()
     bytes_per_pass = 32.0 * float(1 << n_local)
     # fused initialisation (default; QSV_FUSED_INIT=0 turns it off): the first pass does not read the register
@@ -544,6 +567,7 @@ def main():
                 "ms_per_step": exchange_ms, "exposed_ms": max(0.0, ms_per_step - sum(pass_ms)),
                 "achieved_GBps_per_direction": (pstats["exchange_bytes"] / (exchange_ms * 1e-3) / 1e9) if exchange_ms > 0 else None,
                 "path": exchange_path, "nvlink_peak_GBps_per_direction": NVLINK_PEAK, "peak_source": "B200_PROFILING.md measured peer copy"},
+            "exchange_probe": exchange_probe, "prefix_ops_folded_into_initial_state": pdesc.get("prefix_ops", 0),
             "sharded_parity_max_abs_err": parity_err, "sharded_parity_remaps": parity_remaps,
             "clocks": clocks.summary(), "norm_sqr": norm,
         }

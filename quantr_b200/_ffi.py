@@ -102,6 +102,7 @@ def load_library():
         "qsv_plan_get_layout": [vp, i32, C.POINTER(C.c_uint8), sz],
         "qsv_get_layout": [vp, C.POINTER(C.c_uint8), sz],
         "qsv_plan_stats": [vp, C.POINTER(QsvStats)],
+        "qsv_plan_initial_amplitudes": [vp, u64, dp, sz],
         "qsv_plan_serialize": [vp, vp, sz, C.POINTER(sz)],
         "qsv_run_plan": [vp, vp, C.POINTER(QsvStats)],
         "qsv_sample": [vp, dp, u64, C.POINTER(u64)],
@@ -126,7 +127,7 @@ EXPORTED_SYMBOLS = [
     "qsv_create", "qsv_create_sharded", "qsv_nccl_unique_id", "qsv_peer_export", "qsv_peer_import", "qsv_destroy", "qsv_last_error", "qsv_set_option",
     "qsv_get_info", "qsv_init_basis", "qsv_upload", "qsv_download", "qsv_gather", "qsv_apply", "qsv_plan_create",
     "qsv_plan_create_ex", "qsv_plan_num_steps", "qsv_plan_get_step", "qsv_plan_get_layout", "qsv_get_layout",
-    "qsv_plan_destroy", "qsv_plan_stats", "qsv_plan_serialize", "qsv_plan_last_error", "qsv_run_plan", "qsv_sample",
+    "qsv_plan_destroy", "qsv_plan_initial_amplitudes", "qsv_plan_stats", "qsv_plan_serialize", "qsv_plan_last_error", "qsv_run_plan", "qsv_sample",
     "qsv_norm_sqr", "qsv_synchronize", "qsv_last_step_ms", "qsv_device_pointer",
 ]
 

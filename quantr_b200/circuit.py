@@ -272,6 +272,14 @@ class Plan:
             out.append(("pass", pidx.value) if kind.value == 0 else ("exchange", [partners[j] for j in range(g)]))
         return out
 
+    def initial_amplitudes(self, basis_index: int) -> np.ndarray:
+        """Amplitude of every rank when the plan starts from the basis state `basis_index` (see qsv_plan_initial_amplitudes)."""
+        world = 1 << (self.n_qubits - self.n_local)
+        out = np.zeros(world, dtype=np.complex128)
+        self.lib.qsv_plan_initial_amplitudes.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_double), C.c_size_t]
+        F.check_plan(self.lib.qsv_plan_initial_amplitudes(self.handle, basis_index, out.ctypes.data_as(C.POINTER(C.c_double)), world), self.lib)
+        return out
+
     def layout(self, final: bool = False) -> list:
         """layout[b] = physical position of logical index bit b, before the first / after the last step."""
         buf = (C.c_uint8 * self.n_qubits)()

@@ -52,7 +52,7 @@ cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* hos
     const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
     const uint32_t tile_bits = hdr.tile_bits;
     if (pass_uses_tma(host_blob, n_alloc, sm_count)) {
-        const PassInit none{0, 0, 0, 0, 0, 0};
+        const PassInit none{0, 0, 0, 0, 0, 0, 1.0, 0.0};
         if (tile_bits == 12) return launch_pass_tma_tile<12>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init ? *init : none, stream);
         return launch_pass_tma_tile<11>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init ? *init : none, stream);
     }

@@ -283,6 +283,7 @@ struct PassInit {
     uint64_t ext_mask;   // index bits (of the local shard) that belong to the tile id; base_full & ext_mask identifies the tile's rows
     uint32_t holds_here; // the tile lies in this rank's shard
     uint32_t n_alloc;    // log2 of the shard length
+    double amp_re, amp_im;  // the amplitude (1 unless a sharded plan folded leading gates into the initial state, plan.h Plan::prefix)
 };
 inline PassInit make_pass_init(const DevPass& hdr, uint64_t phys_index, uint32_t n_local, uint32_t mode) {
     const uint64_t local_mask = (1ull << n_local) - 1ull;
@@ -294,6 +295,8 @@ inline PassInit make_pass_init(const DevPass& hdr, uint64_t phys_index, uint32_t
     pi.ext_mask = ext_mask;
     pi.holds_here = 1;  // the launcher compares the rank bits (launch_pass knows rank_hi)
     pi.n_alloc = n_local;
+    pi.amp_re = 1.0;
+    pi.amp_im = 0.0;
     return pi;
 }
 

@@ -277,7 +277,8 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
             char* tb = reinterpret_cast<char*>(tile);
 #pragma unroll
             for (uint32_t i = 0; i < (uint32_t)kSlots; ++i)
-                *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) = cplx{(holds && i * kGT + gtid == init.local) ? 1.0 : 0.0, 0.0};
+                *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) =
+                    (holds && i * kGT + gtid == init.local) ? cplx{init.amp_re, init.amp_im} : cplx{0.0, 0.0};
             for (uint32_t o = gtid; o < P.hdr.n_ops; o += kGT)
                 if (P.ops[o].type == OP_DIAG) ext_phase[P.ops[o].diag_index] = diag_ext_phase(P.ops[o], blob, base_full);
         } else {

@@ -609,7 +609,7 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
         if (lop.kind == LOp::DENSE && popcnt(lop.targets()) > T) fail("Custom gate is wider than the tile (" + std::to_string(T) + " bits)");
 
     // ---- layout: physical position of every logical index bit ------------------------------------------------
-    const size_t n_lops = plan.lops.size();
+    size_t n_lops = plan.lops.size();
     auto next_target_use = [&](int bit, size_t from) {  // first op >= from that needs `bit` as a tile bit
         for (size_t i = from; i < n_lops; ++i)
             if ((plan.lops[i].targets() >> bit) & 1) return i;
@@ -643,7 +643,31 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
             seen |= 1ull << layout[b];
         }
     }
+    // Prefix folding (sharded basis states): with the canonical layout the rank id holds the top g logical bits (wires
+    // 0..g-1, the first ones a QFT touches).  Leading ops whose targets are all rank bits - diagonal ops included - see a
+    // product state, so the host applies them to the 2^g rank amplitudes at run time; if that prefix contains a
+    // non-diagonal gate the canonical layout is kept and the prefix leaves the schedule.  QFT-n on 2^g ranks then needs
+    // no remap at all (its first g stages are the prefix, every later stage is local).
+    plan.prefix.clear();
+    if (plan.free_initial_layout && g > 0 && plan.opt.fold_prefix && plan.opt.fuse) {
+        const uint64_t rank_mask = (((1ull << g) - 1ull) << n_local);
+        size_t len = 0;
+        bool has_mat = false;
+        while (len < plan.lops.size()) {
+            const LOp& lop = plan.lops[len];
+            if (lop.kind == LOp::DENSE || (lop.targets() & ~rank_mask)) break;
+            has_mat |= lop.kind == LOp::MAT;
+            ++len;
+        }
+        while (len > 0 && plan.lops[len - 1].kind == LOp::DIAG) --len;  // trailing diagonals stay in the schedule (they fuse for free)
+        if (has_mat && len > 0) {
+            plan.prefix.assign(plan.lops.begin(), plan.lops.begin() + (long)len);
+            plan.lops.erase(plan.lops.begin(), plan.lops.begin() + (long)len);
+            for (int b = 0; b < 64; ++b) layout[b] = (uint8_t)b;  // canonical layout
+        }
+    }
     plan.initial_layout.assign(layout.begin(), layout.begin() + n);
+    n_lops = plan.lops.size();
 
     // Greedy in-order grouping of (physical-space) ops into passes for a given number of low passenger bits.
     // L_first: passenger bits of the segment's first pass (it may differ: on a basis state the plan's first pass is
@@ -824,11 +848,47 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
     plan.final_layout.assign(layout.begin(), layout.begin() + n);
 }
 
+void prefix_amplitudes(const Plan& plan, uint64_t basis_index, std::vector<cplx>& out) {
+    const uint32_t n = plan.n_qubits, nl = plan.n_local, g = n - nl;
+    const uint64_t P = 1ull << g;
+    out.assign(P, cplx{0.0, 0.0});
+    // physical index of the basis state under the initial layout
+    uint64_t phys = 0;
+    for (uint32_t b = 0; b < n; ++b) phys |= ((basis_index >> b) & 1ull) << plan.initial_layout[b];
+    out[phys >> nl] = cplx{1.0, 0.0};
+    if (plan.prefix.empty()) return;
+    // the prefix exists only under the canonical layout: logical bit = physical bit; local bits are constants
+    const uint64_t local = phys & ((1ull << nl) - 1ull), rank_mask = (P - 1ull) << nl;
+    for (const LOp& op : plan.prefix) {
+        if (op.kind == LOp::MAT) {
+            if ((local & op.cmask & ~rank_mask) != (op.cmask & ~rank_mask)) continue;  // a control on a local bit that is 0
+            const uint64_t cm = (op.cmask & rank_mask) >> nl, tb = 1ull << (op.target - (int)nl);
+            const cplx m00{op.m[0], op.m[1]}, m01{op.m[2], op.m[3]}, m10{op.m[4], op.m[5]}, m11{op.m[6], op.m[7]};
+            for (uint64_t r = 0; r < P; ++r) {
+                if ((r & tb) || (r & cm) != cm) continue;
+                const cplx a0 = out[r], a1 = out[r | tb];
+                const cplx p00 = cmul(m00, a0), p01 = cmul(m01, a1), p10 = cmul(m10, a0), p11 = cmul(m11, a1);
+                out[r] = cplx{p00.x + p01.x, p00.y + p01.y};
+                out[r | tb] = cplx{p10.x + p11.x, p10.y + p11.y};
+            }
+        } else if (op.kind == LOp::DIAG) {
+            for (uint64_t r = 0; r < P; ++r) {
+                const uint64_t idx = (r << nl) | local;
+                if ((idx & op.cmask) != op.cmask) continue;
+                double ang = op.theta0;
+                for (auto& t : op.lin)
+                    if ((idx >> t.first) & 1ull) ang += t.second;
+                out[r] = cmul(out[r], unit_phase(ang));
+            }
+        }
+    }
+}
+
 std::string describe_plan(const Plan& plan) {
     std::ostringstream os;
     os << "{\"n_qubits\":" << plan.n_qubits << ",\"n_local\":" << plan.n_local << ",\"n_alloc\":" << plan.n_alloc
        << ",\"tile_bits\":" << std::min<int>(plan.opt.tile_bits, (int)plan.n_alloc) << ",\"low_bits\":" << plan.opt.low_bits
-       << ",\"n_gates\":" << plan.n_gates << ",\"n_lowered_ops\":" << plan.lops.size() << ",\"passes\":[";
+       << ",\"n_gates\":" << plan.n_gates << ",\"n_lowered_ops\":" << plan.lops.size() << ",\"prefix_ops\":" << plan.prefix.size() << ",\"passes\":[";
     for (size_t p = 0; p < plan.passes.size(); ++p) {
         const uint8_t* blob = plan.passes[p].data();
         const DevPass* h = reinterpret_cast<const DevPass*>(blob);

@@ -42,6 +42,7 @@ struct PlanOptions {
     int direct_store = 1; // last round stores registers straight to global memory when that stays coalesced
     int qft4 = 1;         // whole QFT-ladder rounds become one radix-16 macro-op (pass_core.h qft4_apply)
     int big_low_pass = 1; // a pass over the contiguous low index bits may use a 2^12 tile next to 2^11 strided passes
+    int fold_prefix = 1;  // sharded basis states: leading gates on the qubits held in the rank id are applied on the host (build_plan)
 };
 
 // One step of a plan: a fused pass over the local shard, or a global-qubit remap that swaps the index bits held in
@@ -63,6 +64,11 @@ struct Plan {
     // layout[b] = physical position of logical index bit b (positions >= n_local live in the rank id)
     std::vector<uint8_t> initial_layout, final_layout;
     bool free_initial_layout = false;             // the scheduler chose initial_layout (register must be a basis state)
+    // Sharded plans on a basis state: the leading lowered ops whose targets all lie in the rank id act on a product
+    // state (one amplitude per rank, all at the same local index), so they are applied on the host to the 2^g-vector
+    // of rank amplitudes when the plan runs (prefix_amplitudes) instead of forcing a global-qubit remap.  Logical bit
+    // space; empty = none.  A plan with a prefix needs a register that is a basis state.
+    std::vector<LOp> prefix;
     uint64_t n_gates = 0, n_rounds = 0;
     // device residency (owned by the state API)
     void* dev_blob = nullptr;
@@ -79,6 +85,10 @@ void merge_diagonals(std::vector<LOp>& lops);
 void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* ops, size_t n_ops, const PlanOptions& opt,
                 const uint8_t* initial_layout = nullptr, bool free_layout = false);
 std::string describe_plan(const Plan& plan);
+// Amplitude of every rank (2^g complex values, index = rank id under the plan's initial layout) after the plan's prefix
+// has been applied to the basis state `basis_index` (canonical index); all amplitudes sit at the same local index.
+// Without a prefix: 1 on the rank that holds the basis state.
+void prefix_amplitudes(const Plan& plan, uint64_t basis_index, std::vector<cplx>& out);
 
 void host_sincospi(double x, double* s, double* c);
 

@@ -30,6 +30,7 @@ int qsv_plan_create_ex(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubit
         if (const char* env = getenv("QSV_DIRECT_STORE")) opt.direct_store = atoi(env) != 0;
         if (const char* env = getenv("QSV_QFT4")) opt.qft4 = atoi(env) != 0;  // developer A/B switch
         if (const char* env = getenv("QSV_BIG_LOW_PASS")) opt.big_low_pass = atoi(env) != 0;  // developer A/B switch
+        if (const char* env = getenv("QSV_FOLD_PREFIX")) opt.fold_prefix = atoi(env) != 0;    // developer A/B switch
         try {
             qsv::build_plan(p->plan, n_qubits, n_local_qubits, ops, n_ops, opt, layout, free_layout != 0);
         } catch (...) {
@@ -82,6 +83,21 @@ int qsv_plan_get_layout(const qsv_plan* p, int which, uint8_t* out_layout, size_
     if (cap < l.size()) { g_plan_error = "layout buffer too small"; return QSV_ERR_INVALID_ARG; }
     memcpy(out_layout, l.data(), l.size());
     return QSV_OK;
+}
+
+int qsv_plan_initial_amplitudes(const qsv_plan* p, uint64_t basis_index, double* out, size_t cap) {
+    if (!p || !out) { g_plan_error = "NULL argument"; return QSV_ERR_INVALID_ARG; }
+    if (basis_index >> p->plan.n_qubits) { g_plan_error = "basis index out of range"; return QSV_ERR_INVALID_ARG; }
+    try {
+        std::vector<qsv::cplx> amps;
+        qsv::prefix_amplitudes(p->plan, basis_index, amps);
+        if (cap < amps.size()) { g_plan_error = "amplitude buffer too small"; return QSV_ERR_INVALID_ARG; }
+        for (size_t r = 0; r < amps.size(); ++r) { out[2 * r] = amps[r].x; out[2 * r + 1] = amps[r].y; }
+        return QSV_OK;
+    } catch (const std::exception& e) {
+        g_plan_error = e.what();
+        return QSV_ERR_INTERNAL;
+    }
 }
 
 int qsv_plan_destroy(qsv_plan* p) {

@@ -119,13 +119,18 @@ void set_layout(qsv_state* s, const uint8_t* layout) {
 }
 
 // Writes a pending basis state to HBM (under the current layout).
-int materialize(qsv_state* s) {
+// `amp` (optional): this rank's amplitude at the basis state's local index when a sharded plan folded its leading
+// gates into the initial state (Plan::prefix); default: 1 on the rank that holds the basis state.
+int materialize(qsv_state* s, const cplx* amp = nullptr) {
     if (!s->lazy_basis) return QSV_OK;
     s->lazy_basis = false;
     QSV_CUDA(s, cudaMemsetAsync(s->d_state, 0, sizeof(cplx) << s->n_alloc, s->stream));
     const uint64_t phys = to_physical(s, s->lazy_index);
-    if ((phys >> s->n_local) == (uint64_t)s->rank)
+    if (amp) {
+        if (amp->x != 0.0 || amp->y != 0.0) QSV_CUDA(s, launch_set_amp(s->d_state, phys & (local_len(s) - 1), amp->x, amp->y, s->stream));
+    } else if ((phys >> s->n_local) == (uint64_t)s->rank) {
         QSV_CUDA(s, launch_set_amp(s->d_state, phys & (local_len(s) - 1), 1.0, 0.0, s->stream));
+    }
     s->prefix_valid = false;
     return QSV_OK;
 }
@@ -295,6 +300,16 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     } else if (memcmp(s->layout, plan.initial_layout.data(), s->n_qubits) != 0) {
         return set_error(s, QSV_ERR_INVALID_ARG, "the plan starts from a different qubit layout than the register is in");
     }
+    // A sharded plan may have folded the circuit's leading gates on the rank-id qubits into the initial state: every rank
+    // then starts from its own amplitude at the basis state's local index
+    cplx rank_amp{1.0, 0.0};
+    const bool folded = !plan.prefix.empty();
+    if (folded) {
+        if (!s->lazy_basis) return set_error(s, QSV_ERR_INVALID_ARG, "this plan was built for a register that is a basis state (qsv_init_basis)");
+        std::vector<cplx> amps;
+        prefix_amplitudes(plan, s->lazy_index, amps);
+        rank_amp = amps[(size_t)s->rank];
+    }
     // Fused initialisation (pass_kernel_tma.cu): a pending basis state is not written to HBM when the plan's first step is
     // a pass the pipelined kernel runs; that pass synthesises the one tile holding the amplitude and writes every other
     // tile as zeros (mode 2).  QSV_FUSED_INIT=0 turns it off (memset + ordinary first pass), 1 computes every tile.
@@ -304,11 +319,16 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     if (s->lazy_basis && fused_init_mode > 0 && !plan.steps.empty() && plan.steps[0].kind == PlanStep::PASS && s->n_alloc == s->n_local &&
         pass_init_supported(plan.passes[plan.steps[0].pass_index].data(), s->n_alloc, s->sm_count)) {
         const DevPass& h0 = *reinterpret_cast<const DevPass*>(plan.passes[plan.steps[0].pass_index].data());
-        pass_init = make_pass_init(h0, to_physical(s, s->lazy_index), s->n_local, fused_init_mode >= 2 ? 2u : 1u);
+        uint64_t phys = to_physical(s, s->lazy_index);
+        if (folded) phys = (phys & (local_len(s) - 1)) | rank_base(s);  // every rank holds an amplitude at that local index
+        pass_init = make_pass_init(h0, phys, s->n_local, fused_init_mode >= 2 ? 2u : 1u);
+        pass_init.amp_re = rank_amp.x;
+        pass_init.amp_im = rank_amp.y;
+        if (rank_amp.x == 0.0 && rank_amp.y == 0.0) pass_init.base_full = ~0ull;  // nothing to synthesise: the shard is all zero
         fused_init = true;
         s->lazy_basis = false;
     }
-    int rc = materialize(s);
+    int rc = materialize(s, folded ? &rank_amp : nullptr);
     if (rc != QSV_OK) return rc;
     rc = upload_plan(s, p);
     if (rc != QSV_OK) return rc;

@@ -116,7 +116,7 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
             const uint32_t soff_t = swz(tid) << 4;
             for (uint32_t i = 0; i < n_loads; ++i)
                 if (i * threads + tid < tile_len) {
-                    cplx v = init ? cplx{(holds && i * threads + tid == init->local) ? 1.0 : 0.0, 0.0}  // synthesised, the register is not read
+                    cplx v = init ? ((holds && i * threads + tid == init->local) ? cplx{init->amp_re, init->amp_im} : cplx{0.0, 0.0})  // synthesised, the register is not read
                                   : state[base + goff_t + P.loads.goff[i]];
                     *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) = v;
                 }

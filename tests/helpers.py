@@ -293,7 +293,11 @@ def emu_simulate_sharded(n, enc, world, *, basis_index=0, register=None, tile_bi
     assert lib.qsv_emu_alloc_qubits(plan.handle) == nl  # shards are never padded (sharded registers need >= 4 local qubits)
     full = np.zeros(1 << n, dtype=np.complex128)
     if register is None:
-        full[logical_to_physical(basis_index, lay0)] = 1.0
+        # every rank starts from its own amplitude at the basis state's local index (one rank holds 1 unless the plan
+        # folded the circuit's leading gates on the rank-id qubits into the initial state)
+        local = logical_to_physical(basis_index, lay0) & ((1 << nl) - 1)
+        for r, a in enumerate(plan.initial_amplitudes(basis_index)):
+            full[(r << nl) | local] = a
     else:
         assert lay0 == list(range(n))
         full[:] = register

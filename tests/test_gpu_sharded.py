@@ -55,6 +55,14 @@ def _worker(rank, world, port, result_dir):
     results["qft_norm"] = s.norm_sqr()
     u = np.random.default_rng(5).random(20000)
     results["qft_samples"] = s.sample(u)
+    # the same without folding the leading rank-qubit stages into the initial amplitudes: one global-qubit remap
+    os.environ["QSV_FOLD_PREFIX"] = "0"
+    s.set_option("tile_bits", 9)  # another plan-cache key: the handle would otherwise re-run the folded plan
+    s.init_basis(x)
+    stats = s.apply(enc)
+    results["qft_unfolded"] = s.gather(allidx)
+    results["qft_unfolded_exchanges"] = stats["n_exchanges"]
+    del os.environ["QSV_FOLD_PREFIX"]
     s.close()
     # random circuit on an uploaded register (canonical layout, several remaps)
     n2 = 14
@@ -92,8 +100,10 @@ def test_two_gpu_sharded_register_matches_oracle(tmp_path):
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     out = np.load(tmp_path / "out.npz")
     n, x = 16, 0xACE1
-    assert int(out["qft_exchanges"]) == 1
+    assert int(out["qft_exchanges"]) == 0  # the first stage (the rank qubit) is folded into the ranks' initial amplitudes
     assert np.max(np.abs(out["qft"] - qft_expected(n, x))) < 1e-12
+    assert int(out["qft_unfolded_exchanges"]) == 1
+    assert np.max(np.abs(out["qft_unfolded"] - qft_expected(n, x))) < 1e-12
     assert abs(float(out["qft_norm"]) - 1.0) < 1e-12
     counts = np.bincount(out["qft_samples"].astype(np.int64), minlength=1 << n)
     assert counts.sum() == 20000 and counts.max() <= 6  # uniform distribution over 65536 outcomes

@@ -19,8 +19,26 @@ G = qb.Gate
 
 
 @pytest.mark.parametrize("n,world", [(8, 2), (9, 4), (10, 8), (12, 4)])
-def test_qft_needs_exactly_one_remap(n, world):
-    """QFT-n on P ranks: every H target must be local once -> one EXCHANGE, free initial layout."""
+def test_qft_needs_no_remap_from_a_basis_state(n, world):
+    """QFT-n on P ranks from a basis state: the first log2 P stages act on the qubits in the rank id while the state is
+    still a product state, so the scheduler folds them into the ranks' initial amplitudes; every later stage is local.
+    Canonical layout, no EXCHANGE."""
+    enc = encode_gates(qft_circuit(OracleCircuit, G, n).circuit_gates, n)
+    for x in (0, 5, (1 << n) - 3):
+        out, plan, n_exchanges = emu_simulate_sharded(n, enc, world, basis_index=x, tile_bits=5, low_bits=2)
+        assert n_exchanges == 0
+        assert np.max(np.abs(out - qft_expected(n, x))) < 1e-13
+    assert plan.layout(False) == list(range(n)) and plan.layout(True) == list(range(n))
+    assert plan.describe()["prefix_ops"] > 0
+    amps = plan.initial_amplitudes(5)
+    assert abs(np.sum(np.abs(amps) ** 2) - 1.0) < 1e-14 and np.all(np.abs(np.abs(amps) - 1 / np.sqrt(world)) < 1e-14)
+
+
+@pytest.mark.parametrize("n,world", [(8, 2), (9, 4), (10, 8), (12, 4)])
+def test_qft_needs_exactly_one_remap_without_prefix_folding(n, world, monkeypatch):
+    """The same with the folding switched off: every H target must be local once -> one EXCHANGE, the
+    last-targeted qubits start in the rank id (free initial layout)."""
+    monkeypatch.setenv("QSV_FOLD_PREFIX", "0")
     enc = encode_gates(qft_circuit(OracleCircuit, G, n).circuit_gates, n)
     for x in (0, 5, (1 << n) - 3):
         out, plan, n_exchanges = emu_simulate_sharded(n, enc, world, basis_index=x, tile_bits=5, low_bits=2)
@@ -105,8 +123,7 @@ def _gloo_worker(rank, world, port, n, seed, result_dir):
     lay0 = plan.layout(False)
     shard = np.zeros(1 << nl, dtype=np.complex128)
     phys0 = logical_to_physical(3, lay0)
-    if phys0 >> nl == rank:
-        shard[phys0 & ((1 << nl) - 1)] = 1.0
+    shard[phys0 & ((1 << nl) - 1)] = plan.initial_amplitudes(3)[rank]
     for kind, arg in plan.steps():
         if kind == "pass":
             assert lib.qsv_emu_run_pass(plan.handle, arg, shard.ctypes.data_as(C.POINTER(C.c_double)), rank) == 0

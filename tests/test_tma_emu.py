@@ -127,4 +127,4 @@ def test_sharded_plans_through_tma_path(world, tma_mode):
     x = 1234
     enc = encode_gates(qft_circuit(OracleCircuit, G, n).circuit_gates, n)
     out, _, n_exch = emu_simulate_sharded(n, enc, world, basis_index=x, tile_bits=8, low_bits=3)
-    assert n_exch == 1 and np.max(np.abs(out - qft_expected(n, x))) < 1e-13
+    assert n_exch == 0 and np.max(np.abs(out - qft_expected(n, x))) < 1e-13  # the first stages are folded into the ranks' initial amplitudes
