@@ -268,8 +268,8 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
             const bool holds = base_full == init.base_full;  // uniform over the group
             if (init.mode == 2 && !holds) continue;  // zero tile in, zero tile out: written by the stream above
             tile = tiles + (size_t)group * kTileLen;
-            if (gtid == 0 && refill_pending) {
-                bulk_wait_read_all();
+            if (gtid < 32u && refill_pending) {  // the group's previous tile left through this buffer: wait until the bulk store has read it
+                if (lane == 0) bulk_wait_read_all();
                 refill_pending = false;
             }
             group_barrier(group, kGT);
@@ -295,7 +295,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
         for (int w = 0; w < W; ++w) act[w] = thr_act[w];
         if constexpr (!FAST) tile_active_mask<W>(P.hdr, P.ops, base_full, act);
         group_barrier(group, kGT);  // the tile phases (and a synthesised tile) are written
-        if (refill_pending && gtid < 32u) {  // the previous tile's bulk store has had a barrier's time to read its buffer
+        if (refill_pending && !init.mode && gtid < 32u) {  // the previous tile's bulk store has had a barrier's time to read its buffer
             if (lane == 0) bulk_wait_read_all();
             __syncwarp();
             issue_load(refill_t, refill_slot, refill_use);

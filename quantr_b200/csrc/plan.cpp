@@ -239,6 +239,7 @@ cplx unit_phase(double half_turns) {
 }
 
 constexpr int kBigTileBits = 12;  // tile of a pass over the contiguous low index bits (no short runs to pay for)
+constexpr int kReorderWindow = 4096;  // ops a pass looks ahead for work that commutes with what it left behind
 
 void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
     const int T = pb.big ? kBigTileBits : std::min<int>(plan.opt.tile_bits, (int)plan.n_alloc);
@@ -677,30 +678,73 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
         uint64_t low_mask = (T == nloc) ? 0 : ((1ull << L_first) - 1);  // single-tile states: every bit is a tile bit
         const bool allow_big = plan.opt.fuse && T == 11 && nloc >= 23 && plan.opt.big_low_pass;
         PassB cur;
+        // Rounds of a finished pass, re-packed with the same commutation rule one level down: a register round takes, in
+        // order, every op of the pass whose target is one of its (at most four) register bits and that commutes with the
+        // ops it left for later rounds.  Every round is a trip of the tile through shared memory, so fewer, fuller rounds.
+        auto repack_rounds = [&](PassB& pb) {
+            std::vector<size_t> order;
+            for (const RoundB& r : pb.rounds) order.insert(order.end(), r.ops.begin(), r.ops.end());
+            std::sort(order.begin(), order.end());
+            std::vector<char> used(order.size(), 0);
+            std::vector<RoundB> packed;
+            size_t left = order.size(), first = 0;
+            while (left) {
+                while (used[first]) ++first;
+                RoundB r;
+                if (lops[order[first]].kind == LOp::DENSE) {
+                    r.dense = true;
+                    r.ops.push_back(order[first]);
+                    used[first] = 1;
+                    --left;
+                    packed.push_back(std::move(r));
+                    continue;
+                }
+                uint64_t blocked_t = 0, blocked_s = 0;
+                for (size_t k = first; k < order.size(); ++k) {
+                    if (used[k]) continue;
+                    const LOp& lop = lops[order[k]];
+                    const uint64_t tg = lop.targets(), sup = lop.support();
+                    bool ok = lop.kind != LOp::DENSE && !(tg & blocked_s) && !(sup & blocked_t) && r.ops.size() < (size_t)kMaxRoundOps;
+                    if (ok && lop.kind == LOp::MAT && std::find(r.reg.begin(), r.reg.end(), lop.target) == r.reg.end()) {
+                        if ((int)r.reg.size() == kRegBits) ok = false;
+                        else r.reg.push_back(lop.target);
+                    }
+                    if (ok) {
+                        r.ops.push_back(order[k]);
+                        used[k] = 1;
+                        --left;
+                    } else {
+                        blocked_t |= tg;
+                        blocked_s |= sup;
+                    }
+                }
+                packed.push_back(std::move(r));
+            }
+            if (packed.size() < pb.rounds.size()) pb.rounds.swap(packed);
+        };
         auto close_pass = [&]() {
             if (!cur.empty()) {
+                if (plan.opt.fuse && plan.opt.reorder && cur.rounds.size() > 2) repack_rounds(cur);
                 out.push_back(std::move(cur));
                 low_mask = (T == nloc) ? 0 : ((1ull << L) - 1);
             }
             cur = PassB();
         };
-        for (size_t i = 0; i < lops.size(); ++i) {
+        // Commutation-aware greedy: a pass takes, in circuit order, every op that fits its tile and commutes with all
+        // the ops it had to leave behind (an op left behind blocks the qubits it acts on: later ops commute with it iff
+        // they share none of its targets and it shares none of theirs - controls and diagonal phases on common qubits
+        // are fine).  Ops left behind start the next pass.  With reorder off (or fuse off) this is the plain in-order
+        // grouping: the first op that does not fit closes the pass.
+        const size_t n_all = lops.size();
+        std::vector<char> done(n_all, 0);
+        std::vector<uint64_t> tgs(n_all), sups(n_all);
+        for (size_t i = 0; i < n_all; ++i) { tgs[i] = lops[i].targets(); sups[i] = lops[i].support(); }
+        const bool reorder = plan.opt.fuse && plan.opt.reorder;
+        const uint64_t all_bits = nloc >= 64 ? ~0ull : ((1ull << n) - 1ull);
+        size_t first_undone = 0;
+        auto take = [&](size_t i, bool relaxed, bool now_big) {
             const LOp& lop = lops[i];
-            const uint64_t tg = lop.targets();
-            if (!plan.opt.fuse) close_pass();
-            // Can the op join the open pass?  Its targets must fit next to the pass's tile bits and the
-            // low passenger bits, and the pass must stay within the kernel's round/op caps.
-            const bool caps_ok = cur.n_ops + 1 <= (size_t)kMaxOps && cur.rounds.size() + 2 <= (size_t)kMaxRounds;
-            const bool fits = !cur.big && popcnt(cur.req | tg | low_mask) <= T;
-            // a pass whose targets all lie in the lowest kBigTileBits index bits streams contiguous 64 KiB tiles whatever
-            // its size, so it may hold more targets than the strided passes (large registers only)
-            const bool fits_big = allow_big && ((cur.req | tg) >> kBigTileBits) == 0;
-            const bool can_join = !cur.relaxed_low && (fits || fits_big) && caps_ok;
-            if (!can_join) close_pass();
-            const bool now_big = allow_big && ((cur.req | tg) >> kBigTileBits) == 0 && popcnt(cur.req | tg | low_mask) > T;
-            // A Custom gate wider than T - low_bits gets a pass of its own without passenger bits.
-            const bool relaxed = !now_big && !cur.big && popcnt(cur.req | tg | low_mask) > T;
-            cur.req |= tg;
+            cur.req |= tgs[i];
             cur.big |= now_big;
             cur.relaxed_low |= relaxed;
             if (lop.kind == LOp::DENSE) {
@@ -723,7 +767,45 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
                 }
             }
             cur.n_ops++;
-            if (relaxed) close_pass();
+            done[i] = 1;
+        };
+        while (first_undone < n_all) {
+            uint64_t blocked_t = 0, blocked_s = 0;  // targets / supports of the ops left behind by the open pass
+            size_t scanned = 0;
+            for (size_t i = first_undone; i < n_all; ++i) {
+                if (done[i]) continue;
+                if (++scanned > (size_t)kReorderWindow) break;
+                const uint64_t tg = tgs[i];
+                const bool commutes = !(tg & blocked_s) && !(sups[i] & blocked_t);
+                // Can the op join the open pass?  Its targets must fit next to the pass's tile bits and the low
+                // passenger bits, and the pass must stay within the kernel's round/op caps.
+                const bool caps_ok = cur.n_ops + 1 <= (size_t)kMaxOps && cur.rounds.size() + 2 <= (size_t)kMaxRounds;
+                const bool fits = !cur.big && popcnt(cur.req | tg | low_mask) <= T;
+                // a pass whose targets all lie in the lowest kBigTileBits index bits streams contiguous 64 KiB tiles
+                // whatever its size, so it may hold more targets than the strided passes (large registers only)
+                const bool fits_big = allow_big && ((cur.req | tg) >> kBigTileBits) == 0;
+                const bool can_join = plan.opt.fuse && commutes && !cur.relaxed_low && (fits || fits_big) && caps_ok;
+                if (cur.empty() && commutes) {
+                    // the first op of a pass is always taken; a Custom gate wider than T - low_bits gets a pass of its
+                    // own without passenger bits
+                    const bool now_big = allow_big && (tg >> kBigTileBits) == 0 && popcnt(tg | low_mask) > T;
+                    const bool relaxed = !now_big && popcnt(tg | low_mask) > T;
+                    take(i, relaxed, now_big);
+                    if (relaxed || !plan.opt.fuse) break;  // fuse off: one gate per pass
+                    continue;
+                }
+                if (can_join) {
+                    const bool now_big = allow_big && ((cur.req | tg) >> kBigTileBits) == 0 && popcnt(cur.req | tg | low_mask) > T;
+                    take(i, false, now_big);
+                    continue;
+                }
+                if (!reorder) break;  // in-order grouping: the pass ends at the first op it cannot take
+                blocked_t |= tg;
+                blocked_s |= sups[i];
+                if ((blocked_s & all_bits) == all_bits && (blocked_t & all_bits) == all_bits) break;  // nothing later can commute
+            }
+            close_pass();
+            while (first_undone < n_all && done[first_undone]) ++first_undone;
         }
         close_pass();
     };

@@ -43,6 +43,7 @@ struct PlanOptions {
     int qft4 = 1;         // whole QFT-ladder rounds become one radix-16 macro-op (pass_core.h qft4_apply)
     int big_low_pass = 1; // a pass over the contiguous low index bits may use a 2^12 tile next to 2^11 strided passes
     int fold_prefix = 1;  // sharded basis states: leading gates on the qubits held in the rank id are applied on the host (build_plan)
+    int reorder = 1;      // passes take later ops that commute with the ops they had to leave behind (plan.cpp schedule)
 };
 
 // One step of a plan: a fused pass over the local shard, or a global-qubit remap that swaps the index bits held in

@@ -12,6 +12,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A device-side protocol error must fail a test, not hang the box: every GPU test gets a wall-clock limit
+    (pytest-timeout; the kernels themselves trap after a few seconds of waiting on a barrier that never completes)."""
+    try:
+        import pytest_timeout  # noqa: F401
+    except Exception:
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(900))
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built_artifacts():
     """Builds the oracle, the emulation harness and libqsv.so if they are missing (CPU box: nvcc cross-compiles)."""

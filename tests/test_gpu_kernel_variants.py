@@ -17,8 +17,8 @@ def run_inner(env_extra, select):
     if os.environ.get("QSV_VARIANT_INNER"):
         pytest.skip("inner run")
     env = dict(os.environ, QSV_VARIANT_INNER="1", **env_extra)
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k", select],
-                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "--timeout", "300", "-k", select],
+                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 

@@ -58,14 +58,15 @@ c = random_layered_circuit(OracleCircuit, G, n3, 100, seed=30)
 gates = list(c.circuit_gates)
 n_gates = sum(1 for g in gates if g.kind != 0)
 enc = encode_gates(gates, n3)
-for tile_bits in (12, 11):
+for label, opts in (("auto", {}), ("low_bits=3", {"low_bits": 3}), ("low_bits=4", {"low_bits": 4}), ("low_bits=5", {"low_bits": 5}), ("tile 12 low 4", {"tile_bits": 12, "low_bits": 4})):
     s = qb.DeviceState(n3)
-    s.set_option("tile_bits", tile_bits)
+    for k, v in opts.items():
+        s.set_option(k, v)
     s.set_option("timing", 1)
     s.init_basis(0); s.apply(enc)  # warm-up
     t0 = time.perf_counter(); s.init_basis(0); stats = s.apply(enc); s.synchronize(); dt = time.perf_counter() - t0
     norm = s.norm_sqr()
     eff = stats["n_passes"] * stats["bytes_per_pass"] / (stats["device_ms"] * 1e-3) / 1e9
-    print(f"config 3  random layered n={n3} depth 100 ({n_gates} gates) tile_bits={tile_bits}: {dt*1e3:9.1f} ms wall  device {stats['device_ms']:.1f} ms  passes {stats['n_passes']} "
-          f"(passes/gate {stats['n_passes']/n_gates:.3f})  {eff:.0f} GB/s per pass = {eff/6545.9:.3f} of HBM peak  norm {norm:.12f}")
+    print(f"config 3  random layered n={n3} depth 100 ({n_gates} gates) {label:14s}: {dt*1e3:9.1f} ms wall  device {stats['device_ms']:.1f} ms  passes {stats['n_passes']} "
+          f"(passes/gate {stats['n_passes']/n_gates:.3f}, per layer {stats['n_passes']/100:.2f})  rounds {stats['n_rounds']}  {eff:.0f} GB/s per pass = {eff/6544.3:.3f} of HBM peak  norm {norm:.12f}", flush=True)
     s.close()
