@@ -100,6 +100,13 @@ enum {
  *               ("leave this basis state untouched", src/circuit/simulation.rs:120-133).
  *               May be NULL (no None results).  Column s of `matrix` is ignored
  *               where none_mask[s] != 0.
+ * Dense Custom gates are applied by a small-dense-gate round and limited to 13 wires.  A gate
+ * that is the identity except on one basis sub-state, or on one pair of sub-states that differ
+ * in a single wire (multi-controlled gates: the reference's multicnot::<N>, tests/grovers.rs:157-172),
+ * is recognised and lowered to controlled ops of the fused pass instead; for these the limit is
+ * 30 wires, and beyond 13 wires the host passes compact columns:
+ *   iparam = 1: `matrix` holds one column of 2^k complex f64 per sub-state with none_mask == 0, in
+ *               ascending sub-state order (at most 64 of them); none_mask is then mandatory.
  */
 typedef struct qsv_op {
     uint32_t kind;            /* QSV_GATE_* */
@@ -177,7 +184,10 @@ int qsv_init_basis(qsv_state* s, uint64_t index);
 
 /* Copies `count` amplitudes starting at canonical index `first` from / to host
  * memory (interleaved f64).  On a sharded handle the range must lie inside the
- * rank's shard. */
+ * rank's shard.  Exception: after a plan with global-qubit remaps (qsv_get_layout is
+ * not the identity) qsv_download undoes the qubit permutation on the device and is
+ * collective - every rank passes the same range, which may be any part of the register
+ * and arrives on every rank. */
 int qsv_upload(qsv_state* s, const double* host_amps, uint64_t first, uint64_t count);
 int qsv_download(qsv_state* s, double* host_amps, uint64_t first, uint64_t count);
 
@@ -236,7 +246,10 @@ int qsv_run_plan(qsv_state* s, qsv_plan* p, qsv_stats* stats);
 /* For each uniform u in [0,1): the first canonical index i with
  * u < sum_{j<=i} |amp_j|^2, or UINT64_MAX if u >= total ("failed to collapse",
  * src/circuit/states/super_positions.rs:341).  The caller draws the uniforms
- * (fastrand::f64() per shot in the reference, src/circuit/states/super_positions.rs:334). */
+ * (fastrand::f64() per shot in the reference, src/circuit/states/super_positions.rs:334).
+ * On a register in a remapped qubit layout (sharded plans with global-qubit remaps) the
+ * cumulative sums run in the physical order of the amplitudes: the distribution of the
+ * returned canonical indices is the same, the map u -> index is a different inverse CDF. */
 int qsv_sample(qsv_state* s, const double* uniforms, uint64_t shots, uint64_t* out_indices);
 
 /* sum |amp|^2 over the local state (sharded: over all ranks). */

@@ -65,6 +65,36 @@ class EncodedOps:
         return C.sizeof(self.ops) + sum(getattr(k, "nbytes", 0) for k in self.keep)
 
 
+COMPACT_CUSTOM_WIRES = 11  # Custom gates on more wires are passed as the columns of their non-None sub-states only
+
+
+def expand_custom_compact(gate: Gate):
+    """Wide Custom gates (multi-controlled gates such as the reference's multicnot::<N>, tests/grovers.rs:157-172): the
+    closure is still evaluated on all 2^k basis sub-states, but only the images it returns are kept - one 2^k column per
+    non-None sub-state, ascending (qsv_op.iparam = 1, include/qsv.h).  -> (columns[n_active, 2^k] complex, none_mask[2^k])."""
+    k = len(gate.controls) + 1
+    dim = 1 << k
+    none = np.ones(dim, dtype=np.uint8)
+    cols = []
+    for s in range(dim):
+        image = gate.func(ProductState.binary_basis(s, k))
+        if image is None:
+            continue
+        image = into_super_position(image)
+        if image.get_dimension() != dim:
+            raise QuantrError(
+                f"The custom gate {gate.name!r} returned a superposition of dimension {image.get_dimension()} "
+                f"for a {k}-qubit input; it must have dimension {dim}."
+            )
+        none[s] = 0
+        cols.append(np.asarray(image.get_amplitudes(), dtype=np.complex128))
+        if len(cols) > 64:
+            raise QuantrError(f"The custom gate {gate.name!r} acts on {k} wires and answers for more than 64 basis states; "
+                              f"dense Custom gates are limited to {13} wires.")
+    matrix = np.stack(cols) if cols else np.zeros((0, dim), dtype=np.complex128)
+    return matrix, none
+
+
 def expand_custom(gate: Gate):
     """Evaluates a Custom closure on the 2^k basis states of [controls..., target]
     (src/circuit/simulation.rs:137-156) -> (matrix[2^k, 2^k] complex, none_mask[2^k])."""
@@ -109,7 +139,11 @@ def encode_gates(circuit_gates, num_qubits) -> EncodedOps:
             keep.append(ctrl)
             op.controls = ctrl
         if gate.kind == F.GATE_CUSTOM:
-            matrix, none = expand_custom(gate)
+            if len(gate.controls) + 1 >= COMPACT_CUSTOM_WIRES:
+                matrix, none = expand_custom_compact(gate)
+                op.iparam = 1
+            else:
+                matrix, none = expand_custom(gate)
             matrix = np.ascontiguousarray(matrix)
             keep.extend([matrix, none])
             op.matrix = matrix.ctypes.data_as(C.POINTER(C.c_double))

@@ -112,6 +112,33 @@ cudaError_t launch_set_amp(cplx* state, uint64_t index, double re, double im, cu
     return cudaGetLastError();
 }
 
+// Canonical range [first, first + count) of a register whose index bits are permuted (layout[b] = physical position of
+// logical bit b, rank bits on top): this rank's amplitudes land in `out`, the others' entries are zero (the caller sums
+// over ranks).  K4 "applying the logical->physical permutation" (SURVEY.md 2.2).
+struct LayoutArg {
+    uint8_t pos[64];
+};
+__global__ void __launch_bounds__(256) gather_range_kernel(const cplx* __restrict__ state, cplx* __restrict__ out, uint64_t first, uint64_t count, LayoutArg layout,
+                                                         uint32_t n_qubits, uint32_t n_local, uint64_t rank) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t logical = first + i;
+        uint64_t phys = 0;
+        for (uint32_t b = 0; b < n_qubits; ++b) phys |= ((logical >> b) & 1ull) << layout.pos[b];
+        out[i] = (phys >> n_local) == rank ? state[phys & ((1ull << n_local) - 1ull)] : cplx{0.0, 0.0};
+    }
+}
+
+cudaError_t launch_gather_range(const cplx* state, cplx* out, uint64_t first, uint64_t count, const uint8_t* layout, uint32_t n_qubits, uint32_t n_local, uint64_t rank,
+                                int sm_count, cudaStream_t stream) {
+    LayoutArg la{};
+    for (uint32_t b = 0; b < n_qubits && b < 64; ++b) la.pos[b] = layout[b];
+    uint64_t grid = (count + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count * 8;
+    if (grid > cap) grid = cap;
+    gather_range_kernel<<<(unsigned)(grid ? grid : 1), 256, 0, stream>>>(state, out, first, count, la, n_qubits, n_local, rank);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gather(const cplx* state, const uint64_t* idx, cplx* out, uint64_t count, cudaStream_t stream) {
     const unsigned grid = (unsigned)((count + 255) / 256 > 1184 ? 1184 : (count + 255) / 256);
     gather_kernel<<<grid ? grid : 1, 256, 0, stream>>>(state, idx, out, count);

@@ -56,6 +56,9 @@ cudaError_t launch_set_amp(cplx* state, uint64_t index, double re, double im, cu
 // in-place swap of this rank's block 'spelled' peer with the peer's block 'spelled' rank (peer-mapped memory, NVLink)
 cudaError_t launch_peer_swap(cplx* local, cplx* remote, uint32_t n_local, const uint8_t* partner, uint32_t g, int rank, int peer, int sm_count, cudaStream_t stream);
 cudaError_t launch_gather(const cplx* state, const uint64_t* idx, cplx* out, uint64_t count, cudaStream_t stream);
+// canonical range of a register in a permuted qubit layout; entries held by other ranks come back as zero
+cudaError_t launch_gather_range(const cplx* state, cplx* out, uint64_t first, uint64_t count, const uint8_t* layout, uint32_t n_qubits, uint32_t n_local, uint64_t rank,
+                                int sm_count, cudaStream_t stream);
 cudaError_t launch_prob_block_sums(const cplx* state, double* sums, uint64_t n_blocks, uint32_t block_bits, int sm_count, cudaStream_t stream);
 // `prefix` must hold n + 2 + 2 * kScanMaxChunks doubles (prefix[n] = total, the rest is scratch of the chunked scan)
 constexpr int kScanMaxChunks = 1024;

@@ -8,6 +8,7 @@
 #include "plan.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -53,6 +54,12 @@ LOp make_diag(uint32_t src, uint64_t cmask, double theta0, std::vector<std::pair
     return o;
 }
 
+// developer A/B switch: QSV_STRUCTURED_CUSTOM=0 sends every Custom gate through the dense round
+bool plan_structured_custom() {
+    const char* env = getenv("QSV_STRUCTURED_CUSTOM");
+    return !env || atoi(env) != 0;
+}
+
 int expected_controls(uint32_t kind) {
     if (kind == QSV_GATE_TOFFOLI) return 2;
     if (kind >= QSV_GATE_CR && kind <= QSV_GATE_SWAP) return 1;
@@ -77,7 +84,7 @@ void lower_gates(uint32_t n, const qsv_op* ops, size_t n_ops, std::vector<LOp>& 
         const int want = expected_controls(op.kind);
         if (want >= 0 && (int)op.n_controls != want) fail(where.str() + "wrong number of control wires for this gate kind");
         if (op.n_controls && !op.controls) fail(where.str() + "controls is NULL");
-        if (op.n_controls > 20) fail(where.str() + "too many control wires");
+        if (op.n_controls > 29) fail(where.str() + "too many control wires");
         for (uint32_t i = 0; i < op.n_controls; ++i) {
             if (op.controls[i] >= n) fail(where.str() + "control wire out of range");
             if (op.controls[i] == op.target) fail(where.str() + "control wire equals the gate's position");  // circuit.rs:272-293
@@ -129,12 +136,96 @@ void lower_gates(uint32_t n, const qsv_op* ops, size_t n_ops, std::vector<LOp>& 
             case QSV_GATE_CUSTOM: {
                 if (!op.matrix) fail(where.str() + "Custom gate without a matrix");
                 const uint32_t k = op.n_controls + 1;
-                if (k > (uint32_t)kMaxTileBits) fail(where.str() + "Custom gates on more than 13 wires are not supported");
+                const bool compact = op.iparam == 1;  // matrix = the columns of the sub-states the closure answered for (include/qsv.h)
+                if (k > 30) fail(where.str() + "Custom gates on more than 30 wires are not supported");
+                if (!compact && k > (uint32_t)kMaxTileBits) fail(where.str() + "Custom gates on more than 13 wires are not supported unless they act on one basis state or on one pair of them (pass compact columns, qsv.h)");
                 const uint64_t dim = 1ull << k;
+                if (compact && !op.none_mask) fail(where.str() + "compact Custom columns need a none_mask");
+                std::vector<int> gbits;  // bits[0] = MSB of the sub-index = first control
+                for (uint32_t i = 0; i < op.n_controls; ++i) gbits.push_back((int)(n - 1 - op.controls[i]));
+                gbits.push_back(t);
+                // The reference's rule (simulation.rs:120-133): sub-states the closure returned None for keep their own
+                // amplitude (identity row, overwrite) and contribute nothing else; every other column is the closure's image
+                // with its entries on None rows dropped.  Collect the rows that differ from the identity.
+                struct Ent { uint64_t r, s; cplx v; };
+                std::vector<Ent> ents;            // entries of the folded matrix outside its None rows
+                std::vector<uint64_t> active;     // sub-states with a closure image
+                if (compact) {
+                    for (uint64_t s0 = 0; s0 < dim; ++s0) if (!op.none_mask[s0]) active.push_back(s0);
+                    if (active.size() > 64) fail(where.str() + "compact Custom columns: at most 64 sub-states may have an image");
+                } else {
+                    for (uint64_t s0 = 0; s0 < dim; ++s0) if (!(op.none_mask && op.none_mask[s0])) active.push_back(s0);
+                }
+                for (size_t ci = 0; ci < active.size(); ++ci) {
+                    const uint64_t s0 = active[ci];
+                    const double* col = compact ? op.matrix + ci * dim * 2 : nullptr;
+                    for (uint64_t r = 0; r < dim; ++r) {
+                        if (op.none_mask && op.none_mask[r]) continue;
+                        const cplx v = compact ? cplx{col[2 * r], col[2 * r + 1]} : cplx{op.matrix[(r * dim + s0) * 2], op.matrix[(r * dim + s0) * 2 + 1]};
+                        if (v.x != 0.0 || v.y != 0.0) ents.push_back(Ent{r, s0, v});
+                    }
+                }
+                // Structured gates: the folded matrix is the identity except on one basis sub-state (a multi-controlled
+                // phase / scaling) or on one pair of sub-states that differ in a single wire (a multi-controlled 2x2 gate,
+                // e.g. the reference's multicnot::<N>, tests/grovers.rs:157-172).  These become controlled ops of the fused
+                // pass - no dense round, no limit of 13 wires.
+                std::vector<uint64_t> moved;  // sub-states whose row or column is not the identity's
+                auto note = [&](uint64_t x) { if (std::find(moved.begin(), moved.end(), x) == moved.end()) moved.push_back(x); };
+                std::vector<char> has_diag(active.size(), 0);
+                for (const Ent& e : ents) {
+                    if (e.r == e.s && e.v.x == 1.0 && e.v.y == 0.0) { has_diag[std::find(active.begin(), active.end(), e.s) - active.begin()] = 1; continue; }
+                    note(e.r);
+                    note(e.s);
+                    if (moved.size() > 2) break;
+                }
+                for (size_t ci = 0; ci < active.size() && moved.size() <= 2; ++ci) {
+                    if (has_diag[ci]) continue;
+                    bool unit = false;
+                    for (const Ent& e : ents) unit |= (e.r == active[ci] && e.s == active[ci] && e.v.x == 1.0 && e.v.y == 0.0);
+                    if (!unit) note(active[ci]);  // the column lost its diagonal 1 (e.g. maps to zero)
+                }
+                bool structured = moved.size() <= 2 && plan_structured_custom();
+                if (structured && moved.size() == 2 && __builtin_popcountll(moved[0] ^ moved[1]) != 1) structured = false;
+                if (structured && moved.empty()) break;  // the identity
+                if (structured) {
+                    std::sort(moved.begin(), moved.end());
+                    auto entry = [&](uint64_t r, uint64_t s0) {
+                        for (const Ent& e : ents) if (e.r == r && e.s == s0) return e.v;
+                        return cplx{0.0, 0.0};
+                    };
+                    const uint64_t s_lo = moved[0];
+                    const uint64_t diff = moved.size() == 2 ? (moved[0] ^ moved[1]) : 0;
+                    // sub-index bit e (MSB first) <-> physical bit gbits[e]
+                    auto phys_of_sub_bit = [&](uint64_t sub_bit_mask) { int e = 0; while (!((sub_bit_mask >> (k - 1 - e)) & 1ull)) ++e; return gbits[e]; };
+                    uint64_t cmask = 0, flip = 0;  // controls (all other wires); wires whose control value is 0 are X-conjugated
+                    for (uint32_t e = 0; e < k; ++e) {
+                        const uint64_t sb = 1ull << (k - 1 - e);
+                        if (sb == diff) continue;
+                        cmask |= 1ull << gbits[e];
+                        if (!(s_lo & sb)) flip |= 1ull << gbits[e];
+                    }
+                    for (int b = 0; b < 64; ++b) if ((flip >> b) & 1ull) out.push_back(make_xswap(src, b, 0));
+                    if (moved.size() == 1) {
+                        // one basis sub-state scaled by v: a multi-controlled 2x2 diag(1, v) on any one of its wires
+                        const cplx v = entry(s_lo, s_lo);
+                        const int tb = gbits[k - 1];
+                        const uint64_t cm = cmask & ~(1ull << tb);
+                        out.push_back(make_mat(src, OP_MAT_GENERAL, tb, cm, 1, 0, 0, 0, 0, 0, v.x, v.y));
+                    } else {
+                        const int tb = phys_of_sub_bit(diff);
+                        const uint64_t s_hi = moved[1];  // target bit set
+                        const cplx m00 = entry(s_lo, s_lo), m01 = entry(s_lo, s_hi), m10 = entry(s_hi, s_lo), m11 = entry(s_hi, s_hi);
+                        const bool is_x = m00.x == 0 && m00.y == 0 && m11.x == 0 && m11.y == 0 && m01.x == 1 && m01.y == 0 && m10.x == 1 && m10.y == 0;
+                        if (is_x) out.push_back(make_xswap(src, tb, cmask));
+                        else out.push_back(make_mat(src, OP_MAT_GENERAL, tb, cmask, m00.x, m00.y, m01.x, m01.y, m10.x, m10.y, m11.x, m11.y));
+                    }
+                    for (int b = 63; b >= 0; --b) if ((flip >> b) & 1ull) out.push_back(make_xswap(src, b, 0));
+                    break;
+                }
+                if (compact) fail(where.str() + "a Custom gate given as compact columns must act on one basis state or on one pair that differs in one wire");
                 LOp o;
                 o.kind = LOp::DENSE; o.src_gate = src;
-                for (uint32_t i = 0; i < op.n_controls; ++i) o.bits.push_back((int)(n - 1 - op.controls[i]));
-                o.bits.push_back(t);
+                o.bits = gbits;
                 o.rowptr.assign(dim + 1, 0);
                 for (uint64_t r = 0; r < dim; ++r) {
                     const bool none_r = op.none_mask && op.none_mask[r];

@@ -414,6 +414,27 @@ int ensure_total(qsv_state* s) {
     return QSV_OK;
 }
 
+// qsv_download on a register whose qubits were remapped by a sharded plan: the canonical range is assembled by undoing
+// the index-bit permutation on the device (every rank contributes the amplitudes it holds, zeros elsewhere) and summing
+// over ranks, chunk by chunk.  Collective: every rank must ask for the same range.
+int download_permuted(qsv_state* s, double* host_amps, uint64_t first, uint64_t count) {
+    const uint64_t chunk = 1ull << 20;  // 16 MiB of amplitudes per round trip
+    int rc = ensure_scratch(s, sizeof(cplx) * (count < chunk ? count : chunk));
+    if (rc != QSV_OK) return rc;
+    cplx* d_out = static_cast<cplx*>(s->d_scratch);
+    for (uint64_t done = 0; done < count; done += chunk) {
+        const uint64_t m = count - done < chunk ? count - done : chunk;
+        QSV_CUDA(s, launch_gather_range(s->d_state, d_out, first + done, m, s->layout, s->n_qubits, s->n_local, (uint64_t)s->rank, s->sm_count, s->stream));
+        if (s->comm) {
+            std::string err;
+            if (!shard_allreduce_sum_f64(s->comm, reinterpret_cast<double*>(d_out), 2 * m, err)) return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
+        }
+        QSV_CUDA(s, cudaMemcpyAsync(host_amps + 2 * done, d_out, sizeof(cplx) * m, cudaMemcpyDeviceToHost, s->stream));
+        QSV_CUDA(s, cudaStreamSynchronize(s->stream));
+    }
+    return QSV_OK;
+}
+
 // Serialises everything a plan depends on (qsv_apply's cache key).  Returns false when the key would be too large to be
 // worth keeping (huge Custom matrices).
 bool plan_cache_key(const qsv_state* s, const qsv_op* ops, size_t n_ops, bool free_layout, std::vector<uint8_t>& key) {
@@ -614,9 +635,14 @@ int qsv_upload(qsv_state* s, const double* host_amps, uint64_t first, uint64_t c
 int qsv_download(qsv_state* s, double* host_amps, uint64_t first, uint64_t count) {
     QSV_ENTER(s);
     if (!host_amps && count) return set_error(s, QSV_ERR_INVALID_ARG, "host_amps is NULL");
+    if (!s->lazy_basis && !s->layout_identity) {
+        // remapped layout (a sharded plan with global-qubit remaps has run): any canonical range, collectively
+        if ((first >> s->n_qubits) || count > (1ull << s->n_qubits) - first) return set_error(s, QSV_ERR_INVALID_ARG, "range is outside the register");
+        return download_permuted(s, host_amps, first, count);
+    }
     if (first < rank_base(s) || first - rank_base(s) + count > local_len(s)) return set_error(s, QSV_ERR_INVALID_ARG, "range is outside this rank's shard");
     { int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
-    if (!s->layout_identity) return set_error(s, QSV_ERR_UNSUPPORTED, "the register is in a remapped qubit layout (see qsv_get_layout): use qsv_gather");
+    if (!s->layout_identity) return download_permuted(s, host_amps, first, count);
     QSV_CUDA(s, cudaMemcpyAsync(host_amps, s->d_state + (first - rank_base(s)), sizeof(cplx) * count, cudaMemcpyDeviceToHost, s->stream));
     QSV_CUDA(s, cudaStreamSynchronize(s->stream));
     return QSV_OK;

@@ -113,3 +113,73 @@ def test_custom_expansion_matrix_and_none_mask():
         return st.SuperPosition.new_with_amplitudes_unchecked([1, 0, 0, 0])
     with pytest.raises(QuantrError):
         expand_custom(G.Custom(bad, [], "bad"))
+
+
+def test_structured_custom_gates_are_lowered_to_controlled_ops():
+    """Permutation-with-phase closures (multi-controlled gates, tests/grovers.rs:157-172 multicnot::<N>) do not need the
+    dense Custom round: x3sudoko schedules without one, a 13-wire multi-CNOT closure is passed as compact columns and acts
+    like the reference's closure, and a 21-wire one - far beyond the 13-wire limit of dense Custom gates - is accepted."""
+    import numpy as np
+    from golden import reference_vectors as rv
+    from helpers import EmuCircuit, OracleCircuit, emu_lib, emu_simulate, encode_gates, orc, qb
+    from quantr_b200 import states as st
+    G = qb.Gate
+    lib = emu_lib()
+    enc = encode_gates(rv.build_x3sudoko(OracleCircuit, G, st).circuit_gates, 10)
+    desc = qb.Plan(10, enc, tile_bits=8, low_bits=3, lib=lib).describe()
+    assert all(r["type"] == 0 for p in desc["passes"] for r in p["rounds"])  # no dense round
+    ref = orc.simulate(10, enc.ops, enc.n_ops, None, mode="dense")
+    assert np.max(np.abs(emu_simulate(10, enc, None, tile_bits=8, low_bits=3) - ref)) < 1e-12
+
+    def multicnot(prod):  # the reference's multicnot::<N>: flips the last qubit when every other one is |1>
+        q = prod.get_qubits()
+        if all(b == st.Qubit.One for b in q[:-1]):
+            amps = np.zeros(1 << len(q), dtype=np.complex128)
+            idx = (1 << len(q)) - 2 if q[-1] == st.Qubit.One else (1 << len(q)) - 1
+            amps[idx] = 1.0
+            return st.SuperPosition.new_with_amplitudes_unchecked(amps)
+        return None
+
+    n = 13
+    for pattern in ((1 << n) - 2, ((1 << n) - 2) & ~0b1000, 0b101):  # all controls set / one control clear / most clear
+        c = OracleCircuit.new(n)
+        for w in range(n):
+            if (pattern >> (n - 1 - w)) & 1:
+                c.add_gate(G.X, w)
+        c.add_gate(G.H, 3)
+        c.add_gate(G.Custom(multicnot, list(range(n - 1)), "mcx"), n - 1)  # 13 wires: compact columns
+        enc = encode_gates(c.circuit_gates, n)
+        assert enc.ops[enc.n_ops - 1].iparam == 1
+        reg = np.zeros(1 << n, dtype=np.complex128)
+        reg[0] = 1.0
+        out = emu_simulate(n, enc, reg, tile_bits=8, low_bits=3)
+        # expected: X pattern, H on wire 3, then the target flips on the branch where every control is 1
+        exp = np.zeros(1 << n, dtype=np.complex128)
+        b3 = 1 << (n - 1 - 3)
+        for sign_idx, amp in ((pattern & ~b3, np.sqrt(0.5)), (pattern | b3, np.sqrt(0.5) * (-1.0 if (pattern & b3) else 1.0))):
+            idx = sign_idx
+            if (idx >> 1) == (1 << (n - 1)) - 1:
+                idx ^= 1
+            exp[idx] += amp
+        assert np.max(np.abs(out - exp)) < 1e-14
+
+    # 21 wires (20 controls): built directly as a qsv_op with compact columns (2 x 2^21 amplitudes)
+    import ctypes as C
+    from quantr_b200 import _ffi as F
+    k, n = 21, 22
+    dim = 1 << k
+    none = np.ones(dim, dtype=np.uint8)
+    none[dim - 2] = none[dim - 1] = 0
+    cols = np.zeros((2, dim), dtype=np.complex128)
+    cols[0, dim - 1] = 1.0  # |1..10> -> |1..11>
+    cols[1, dim - 2] = 1.0
+    ops = (F.QsvOp * 1)()
+    ctrl = (C.c_uint32 * (k - 1))(*range(k - 1))
+    ops[0].kind, ops[0].target, ops[0].n_controls, ops[0].controls, ops[0].iparam = F.GATE_CUSTOM, k - 1, k - 1, ctrl, 1
+    ops[0].matrix = cols.ctypes.data_as(C.POINTER(C.c_double))
+    ops[0].none_mask = none.ctypes.data_as(C.POINTER(C.c_uint8))
+    enc = qb.EncodedOps(ops, [ctrl, cols, none], [])
+    enc.n_ops = 1
+    plan = qb.Plan(n, enc, lib=lib)
+    d = plan.describe()
+    assert d["n_lowered_ops"] == 1 and plan.stats()["n_passes"] == 1

@@ -119,9 +119,24 @@ def test_plan_errors():
     plan = qb.Plan(6, enc, n_local=4)  # H on a rank bit: the plan inserts a global-qubit remap
     assert any(kind == "exchange" for kind, _ in plan.steps())
     c = OracleCircuit.new(6)
-    c.add_gate(G.Custom(lambda p: None, [0, 1, 2, 3, 4], "wide"), 5)
+    def increment(prod):  # a cyclic shift of the 64 basis states: dense as far as the scheduler is concerned
+        q = prod.get_qubits()
+        v = 0
+        for b in q:
+            v = (v << 1) | (1 if b == st.Qubit.One else 0)
+        amps = np.zeros(1 << len(q), dtype=np.complex128)
+        amps[(v + 1) % (1 << len(q))] = 1.0
+        return st.SuperPosition.new_with_amplitudes_unchecked(amps)
+
+    c.add_gate(G.Custom(increment, [0, 1, 2, 3, 4], "wide"), 5)
     with pytest.raises(F.QsvError) as e:
-        qb.Plan(6, encode_gates(c.circuit_gates, 6), n_local=4)  # a 6-wire Custom gate cannot be made local on 4 bits
+        qb.Plan(6, encode_gates(c.circuit_gates, 6), n_local=4)  # a dense 6-wire Custom gate cannot be made local on 4 bits
+    assert e.value.code == 5
+    c = OracleCircuit.new(6)
+    c.add_gate(G.Custom(lambda p: None, [0, 1, 2, 3, 4], "nothing"), 5)  # the identity: lowered to no op at all
+    assert qb.Plan(6, encode_gates(c.circuit_gates, 6), n_local=4).stats()["n_passes"] == 0
+    with pytest.raises(F.QsvError) as e:
+        qb.Plan(6, encode_gates(OracleCircuit.new(6).add_gate(G.Custom(increment, [0, 1, 2, 3, 4], "wide"), 5).circuit_gates, 6), n_local=4)
     assert e.value.code == 5
     bad = (F.QsvOp * 1)()
     bad[0].kind = F.GATE_CNOT
