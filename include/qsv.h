@@ -267,6 +267,14 @@ int qsv_synchronize(qsv_state* s);
  * Writes min(*n_steps, cap) entries; out_ms may be NULL to query the count. */
 int qsv_last_step_ms(const qsv_state* s, double* out_ms, size_t cap, size_t* n_steps);
 
+/* State checkpoint (the reference carries a state between circuits by hand: SimulatedCircuit::take_state +
+ * Circuit::change_register, src/simulated_circuit.rs:185-187, src/circuit.rs:463-473).  File = 256-byte header
+ * ("QSVCKPT1", n_qubits, n_local_qubits, rank, world, the qubit layout) + the rank's amplitudes, raw little-endian
+ * interleaved f64 in physical order.  A sharded register is one file per rank (the caller names them); qsv_load needs a
+ * handle of the same shape (n_qubits, rank, world) and restores the layout as well. */
+int qsv_save(qsv_state* s, const char* path);
+int qsv_load(qsv_state* s, const char* path);
+
 /* Raw device pointer / stream of the handle, for callers that time with their
  * own CUDA events or wrap the memory (no ownership transfer). */
 int qsv_device_pointer(qsv_state* s, void** dev_ptr, void** cuda_stream);

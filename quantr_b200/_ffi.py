@@ -107,6 +107,8 @@ def load_library():
         "qsv_run_plan": [vp, vp, C.POINTER(QsvStats)],
         "qsv_sample": [vp, dp, u64, C.POINTER(u64)],
         "qsv_norm_sqr": [vp, dp],
+        "qsv_save": [vp, C.c_char_p],
+        "qsv_load": [vp, C.c_char_p],
         "qsv_synchronize": [vp],
         "qsv_last_step_ms": [vp, C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_size_t)],
         "qsv_device_pointer": [vp, C.POINTER(vp), C.POINTER(vp)],
@@ -128,7 +130,7 @@ EXPORTED_SYMBOLS = [
     "qsv_get_info", "qsv_init_basis", "qsv_upload", "qsv_download", "qsv_gather", "qsv_apply", "qsv_plan_create",
     "qsv_plan_create_ex", "qsv_plan_num_steps", "qsv_plan_get_step", "qsv_plan_get_layout", "qsv_get_layout",
     "qsv_plan_destroy", "qsv_plan_initial_amplitudes", "qsv_plan_stats", "qsv_plan_serialize", "qsv_plan_last_error", "qsv_run_plan", "qsv_sample",
-    "qsv_norm_sqr", "qsv_synchronize", "qsv_last_step_ms", "qsv_device_pointer",
+    "qsv_norm_sqr", "qsv_save", "qsv_load", "qsv_synchronize", "qsv_last_step_ms", "qsv_device_pointer",
 ]
 
 

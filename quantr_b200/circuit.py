@@ -256,6 +256,13 @@ class DeviceState:
     def synchronize(self):
         F.check(self.lib.qsv_synchronize(self.handle), self.handle)
 
+    def save(self, path: str):
+        """State checkpoint: header + this rank's amplitudes, raw interleaved f64 (qsv_save)."""
+        F.check(self.lib.qsv_save(self.handle, os.fsencode(path)), self.handle)
+
+    def load(self, path: str):
+        F.check(self.lib.qsv_load(self.handle, os.fsencode(path)), self.handle)
+
     def last_step_ms(self) -> list:
         """Device time of every step (pass or exchange) of the last plan run; needs set_option("timing", 1)."""
         n = C.c_size_t()

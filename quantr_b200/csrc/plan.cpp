@@ -281,6 +281,102 @@ void merge_diagonals(std::vector<LOp>& lops) {
     lops.swap(kept);
 }
 
+// Peephole over commuting ops (SURVEY.md 8f "circuit-level optimiser"): a 2x2 gate is multiplied into the nearest earlier
+// 2x2 gate on the same target with the same controls when every op between them commutes with it.  H.H, X.X and the
+// like vanish; runs of rotations become one matrix (a diagonal product becomes a phase op and joins the diagonal merging).
+void merge_single_qubit_gates(std::vector<LOp>& lops) {
+    std::vector<char> dead(lops.size(), 0);
+    auto classify = [](LOp& o) {  // picks the cheapest op type for the product matrix; returns false if it is the identity
+        const double* m = o.m;
+        auto zero = [](double x) { return fabs(x) < 1e-300; };
+        const bool off_zero = zero(m[2]) && zero(m[3]) && zero(m[4]) && zero(m[5]);
+        const bool diag_zero = zero(m[0]) && zero(m[1]) && zero(m[6]) && zero(m[7]);
+        if (off_zero && m[0] == 1.0 && zero(m[1]) && m[6] == 1.0 && zero(m[7])) return false;
+        if (diag_zero && m[2] == 1.0 && zero(m[3]) && m[4] == 1.0 && zero(m[5])) o.mtype = OP_MAT_XSWAP;
+        else if (diag_zero) o.mtype = OP_MAT_ANTIDIAG;
+        else if (zero(m[1]) && zero(m[3]) && zero(m[5]) && zero(m[7])) o.mtype = OP_MAT_REAL;
+        else o.mtype = OP_MAT_GENERAL;
+        return true;
+    };
+    // an uncontrolled one-wire phase gate (Rz, Z, S, T, ...) as the diagonal matrix it is
+    auto diag_1q = [](const LOp& o, int* t, double* m) {
+        if (o.kind != LOp::DIAG || o.cmask != 0 || o.lin.size() != 1) return false;
+        *t = o.lin[0].first;
+        double s0, c0, s1, c1;
+        sincospi_hd(o.theta0, &s0, &c0);
+        sincospi_hd(o.theta0 + o.lin[0].second, &s1, &c1);
+        const double mm[8] = {c0, s0, 0, 0, 0, 0, c1, s1};
+        memcpy(m, mm, sizeof(mm));
+        return true;
+    };
+    for (size_t i = 0; i < lops.size(); ++i) {
+        int dt = -1;
+        double dm[8];
+        const bool i_diag = diag_1q(lops[i], &dt, dm);
+        if (lops[i].kind != LOp::MAT && !i_diag) continue;
+        const uint64_t tg = i_diag ? 0 : lops[i].targets(), sup = lops[i].support();
+        const size_t lo = i > 256 ? i - 256 : 0;
+        for (size_t j = i; j-- > lo;) {
+            if (dead[j]) continue;
+            LOp& p = lops[j];
+            const bool conflict = (p.targets() & sup) || (tg & p.support());
+            if (!conflict) continue;
+            int pt = -1;
+            double pm[8];
+            if (i_diag) {
+                // a phase gate right after (in commutation order) an uncontrolled 2x2 gate on its wire: fold it into the matrix
+                if (p.kind == LOp::MAT && p.cmask == 0 && p.target == dt) {
+                    double r[8];
+                    auto mul = [](const double* x, const double* y, double* out) { out[0] = x[0] * y[0] - x[1] * y[1]; out[1] = x[0] * y[1] + x[1] * y[0]; };
+                    mul(dm + 0, p.m + 0, r + 0); mul(dm + 0, p.m + 2, r + 2); mul(dm + 6, p.m + 4, r + 4); mul(dm + 6, p.m + 6, r + 6);
+                    memcpy(p.m, r, sizeof(r));
+                    if (p.mtype == OP_MAT_HADAMARD || p.mtype == OP_MAT_REAL || p.mtype == OP_MAT_XSWAP) p.mtype = OP_MAT_GENERAL;
+                    dead[i] = 1;
+                }
+                break;
+            }
+            if (lops[i].cmask == 0 && diag_1q(p, &pt, pm) && pt == lops[i].target) {
+                // an uncontrolled 2x2 gate right after a phase gate on its wire: absorb the phase gate and keep looking back
+                double r[8];
+                auto mul = [](const double* x, const double* y, double* out) { out[0] = x[0] * y[0] - x[1] * y[1]; out[1] = x[0] * y[1] + x[1] * y[0]; };
+                const double* a = lops[i].m;
+                mul(a + 0, pm + 0, r + 0); mul(a + 2, pm + 6, r + 2); mul(a + 4, pm + 0, r + 4); mul(a + 6, pm + 6, r + 6);
+                memcpy(lops[i].m, r, sizeof(r));
+                lops[i].mtype = OP_MAT_GENERAL;
+                dead[j] = 1;
+                continue;
+            }
+            if (p.kind == LOp::MAT && p.target == lops[i].target && p.cmask == lops[i].cmask) {
+                // product = M_i * M_j (j acts first)
+                const double* a = lops[i].m;
+                double b[8], r[8];
+                memcpy(b, p.m, sizeof(b));
+                auto mul = [](const double* x, const double* y, double* out) { out[0] = x[0] * y[0] - x[1] * y[1]; out[1] = x[0] * y[1] + x[1] * y[0]; };
+                double t0[2], t1[2];
+                mul(a + 0, b + 0, t0); mul(a + 2, b + 4, t1); r[0] = t0[0] + t1[0]; r[1] = t0[1] + t1[1];  // r00 = a00 b00 + a01 b10
+                mul(a + 0, b + 2, t0); mul(a + 2, b + 6, t1); r[2] = t0[0] + t1[0]; r[3] = t0[1] + t1[1];  // r01 = a00 b01 + a01 b11
+                mul(a + 4, b + 0, t0); mul(a + 6, b + 4, t1); r[4] = t0[0] + t1[0]; r[5] = t0[1] + t1[1];  // r10 = a10 b00 + a11 b10
+                mul(a + 4, b + 2, t0); mul(a + 6, b + 6, t1); r[6] = t0[0] + t1[0]; r[7] = t0[1] + t1[1];  // r11 = a10 b01 + a11 b11
+                // H.H and friends: snap products that are the identity up to rounding (|x| < 2^-50) to exact values
+                for (int q = 0; q < 8; ++q) {
+                    if (fabs(r[q]) < 8.9e-16) r[q] = 0.0;
+                    if (fabs(r[q] - 1.0) < 8.9e-16) r[q] = 1.0;
+                    if (fabs(r[q] + 1.0) < 8.9e-16) r[q] = -1.0;
+                }
+                memcpy(p.m, r, sizeof(r));
+                dead[i] = 1;
+                if (!classify(p)) dead[j] = 1;
+            }
+            break;  // the nearest op that does not commute decides
+        }
+    }
+    std::vector<LOp> kept;
+    kept.reserve(lops.size());
+    for (size_t i = 0; i < lops.size(); ++i)
+        if (!dead[i]) kept.push_back(std::move(lops[i]));
+    lops.swap(kept);
+}
+
 namespace {
 
 struct RoundB {
@@ -686,6 +782,7 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
     plan.lops.clear();
     plan.n_rounds = 0;
     lower_gates(n_qubits, ops, n_ops, plan.lops, &plan.n_gates);
+    if (plan.opt.fuse && plan.opt.merge_1q) merge_single_qubit_gates(plan.lops);
     if (plan.opt.fuse) merge_diagonals(plan.lops);
     // tile size: 11 for registers the pipelined kernel serves (measured on B200, DESIGN.md 6: four compute groups of
     // 128 threads overlap better than two of 256), else 12; widened when a Custom gate needs more tile bits

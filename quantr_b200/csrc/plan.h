@@ -44,6 +44,7 @@ struct PlanOptions {
     int big_low_pass = 1; // a pass over the contiguous low index bits may use a 2^12 tile next to 2^11 strided passes
     int fold_prefix = 1;  // sharded basis states: leading gates on the qubits held in the rank id are applied on the host (build_plan)
     int reorder = 1;      // passes take later ops that commute with the ops they had to leave behind (plan.cpp schedule)
+    int merge_1q = 1;     // 2x2 gates on the same target and controls are multiplied together across commuting ops; identities vanish
 };
 
 // One step of a plan: a fused pass over the local shard, or a global-qubit remap that swaps the index bits held in
@@ -82,6 +83,7 @@ struct Plan {
 // Throws std::runtime_error with a message on invalid input / unsupported circuits.
 void lower_gates(uint32_t n_qubits, const qsv_op* ops, size_t n_ops, std::vector<LOp>& out, uint64_t* n_gates);
 void merge_diagonals(std::vector<LOp>& lops);
+void merge_single_qubit_gates(std::vector<LOp>& lops);
 // initial_layout: nullptr = identity; free_layout: let the scheduler choose the initial layout (sharded basis states).
 void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* ops, size_t n_ops, const PlanOptions& opt,
                 const uint8_t* initial_layout = nullptr, bool free_layout = false);

@@ -832,6 +832,75 @@ int qsv_last_step_ms(const qsv_state* s, double* out_ms, size_t cap, size_t* n_s
     return QSV_OK;
 }
 
+namespace {
+struct CkptHeader {
+    char magic[8];
+    uint32_t n_qubits, n_local, rank, world;
+    uint8_t layout[64];
+    uint8_t pad[256 - 8 - 16 - 64];
+};
+static_assert(sizeof(CkptHeader) == 256, "checkpoint header");
+constexpr size_t kCkptChunk = (size_t)64 << 20;
+}  // namespace
+
+int qsv_save(qsv_state* s, const char* path) {
+    QSV_ENTER(s);
+    if (!path) return set_error(s, QSV_ERR_INVALID_ARG, "path is NULL");
+    { int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
+    FILE* f = fopen(path, "wb");
+    if (!f) return set_error(s, QSV_ERR_INVALID_ARG, "cannot open %s for writing", path);
+    CkptHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "QSVCKPT1", 8);
+    h.n_qubits = s->n_qubits; h.n_local = s->n_local; h.rank = (uint32_t)s->rank; h.world = (uint32_t)s->world;
+    memcpy(h.layout, s->layout, sizeof(h.layout));
+    int rc = fwrite(&h, sizeof(h), 1, f) == 1 ? QSV_OK : set_error(s, QSV_ERR_INTERNAL, "write to %s failed", path);
+    void* host = nullptr;
+    if (rc == QSV_OK && cudaMallocHost(&host, kCkptChunk) != cudaSuccess) { cudaGetLastError(); rc = set_error(s, QSV_ERR_OUT_OF_MEMORY, "pinned staging buffer"); }
+    const size_t total = sizeof(cplx) << s->n_local;
+    for (size_t off = 0; rc == QSV_OK && off < total; off += kCkptChunk) {
+        const size_t m = total - off < kCkptChunk ? total - off : kCkptChunk;
+        cudaError_t e = cudaMemcpyAsync(host, reinterpret_cast<const char*>(s->d_state) + off, m, cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) rc = set_error(s, QSV_ERR_CUDA, "checkpoint read-back: %s", cudaGetErrorString(e));
+        else if (fwrite(host, 1, m, f) != m) rc = set_error(s, QSV_ERR_INTERNAL, "write to %s failed", path);
+    }
+    if (host) cudaFreeHost(host);
+    if (fclose(f) != 0 && rc == QSV_OK) rc = set_error(s, QSV_ERR_INTERNAL, "closing %s failed", path);
+    return rc;
+}
+
+int qsv_load(qsv_state* s, const char* path) {
+    QSV_ENTER(s);
+    if (!path) return set_error(s, QSV_ERR_INVALID_ARG, "path is NULL");
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_error(s, QSV_ERR_INVALID_ARG, "cannot open %s", path);
+    CkptHeader h;
+    int rc = QSV_OK;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "QSVCKPT1", 8) != 0) rc = set_error(s, QSV_ERR_INVALID_ARG, "%s is not a checkpoint", path);
+    else if (h.n_qubits != s->n_qubits || h.n_local != s->n_local || h.rank != (uint32_t)s->rank || h.world != (uint32_t)s->world)
+        rc = set_error(s, QSV_ERR_INVALID_ARG, "%s holds rank %u/%u of a %u-qubit register; the handle is rank %d/%d of %u qubits", path, h.rank, h.world, h.n_qubits, s->rank,
+                       s->world, s->n_qubits);
+    void* host = nullptr;
+    if (rc == QSV_OK && cudaMallocHost(&host, kCkptChunk) != cudaSuccess) { cudaGetLastError(); rc = set_error(s, QSV_ERR_OUT_OF_MEMORY, "pinned staging buffer"); }
+    const size_t total = sizeof(cplx) << s->n_local;
+    for (size_t off = 0; rc == QSV_OK && off < total; off += kCkptChunk) {
+        const size_t m = total - off < kCkptChunk ? total - off : kCkptChunk;
+        if (fread(host, 1, m, f) != m) { rc = set_error(s, QSV_ERR_INVALID_ARG, "%s is truncated", path); break; }
+        cudaError_t e = cudaMemcpyAsync(reinterpret_cast<char*>(s->d_state) + off, host, m, cudaMemcpyHostToDevice, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) rc = set_error(s, QSV_ERR_CUDA, "checkpoint upload: %s", cudaGetErrorString(e));
+    }
+    if (host) cudaFreeHost(host);
+    fclose(f);
+    if (rc == QSV_OK) {
+        s->lazy_basis = false;
+        set_layout(s, h.layout);
+        s->prefix_valid = false;
+    }
+    return rc;
+}
+
 int qsv_synchronize(qsv_state* s) {
     QSV_ENTER(s);
     QSV_CUDA(s, cudaStreamSynchronize(s->stream));

@@ -45,19 +45,49 @@ pub mod ffi {
         _private: [u8; 0],
     }
 
+    #[repr(C)]
+    pub struct QsvPlan {
+        _private: [u8; 0],
+    }
+
+    // Every export of include/qsv.h, in the header's order (tests/test_abi.py checks the library exports the same list).
     extern "C" {
         pub fn qsv_create(out: *mut *mut QsvState, n_qubits: u32, device: c_int) -> c_int;
+        pub fn qsv_create_sharded(out: *mut *mut QsvState, n_qubits: u32, device: c_int, rank: c_int, world: c_int,
+                                  nccl_unique_id: *const c_void, nccl_unique_id_bytes: usize) -> c_int;
+        pub fn qsv_nccl_unique_id(out: *mut c_void, out_bytes: usize) -> c_int;
+        pub fn qsv_peer_export(s: *mut QsvState, out_handle: *mut c_void, out_bytes: usize) -> c_int;
+        pub fn qsv_peer_import(s: *mut QsvState, handles: *const c_void, n_handles: usize) -> c_int;
         pub fn qsv_destroy(s: *mut QsvState) -> c_int;
         pub fn qsv_last_error(s: *const QsvState) -> *const c_char;
         pub fn qsv_set_option(s: *mut QsvState, key: *const c_char, value: i64) -> c_int;
+        pub fn qsv_get_info(s: *const QsvState, key: *const c_char, value: *mut i64) -> c_int;
         pub fn qsv_init_basis(s: *mut QsvState, index: u64) -> c_int;
         pub fn qsv_upload(s: *mut QsvState, host_amps: *const f64, first: u64, count: u64) -> c_int;
         pub fn qsv_download(s: *mut QsvState, host_amps: *mut f64, first: u64, count: u64) -> c_int;
         pub fn qsv_gather(s: *mut QsvState, indices: *const u64, count: u64, host_amps: *mut f64) -> c_int;
         pub fn qsv_apply(s: *mut QsvState, ops: *const QsvOp, n_ops: usize, stats: *mut QsvStats) -> c_int;
+        pub fn qsv_plan_create(out: *mut *mut QsvPlan, n_qubits: u32, n_local_qubits: u32, ops: *const QsvOp, n_ops: usize,
+                               tile_bits: u32, low_bits: u32, fuse: c_int) -> c_int;
+        pub fn qsv_plan_create_ex(out: *mut *mut QsvPlan, n_qubits: u32, n_local_qubits: u32, ops: *const QsvOp, n_ops: usize,
+                                  tile_bits: u32, low_bits: u32, fuse: c_int, layout: *const u8, free_layout: c_int) -> c_int;
+        pub fn qsv_plan_destroy(p: *mut QsvPlan) -> c_int;
+        pub fn qsv_plan_initial_amplitudes(p: *const QsvPlan, basis_index: u64, out: *mut f64, cap: usize) -> c_int;
+        pub fn qsv_plan_num_steps(p: *const QsvPlan, n_steps: *mut usize) -> c_int;
+        pub fn qsv_plan_get_step(p: *const QsvPlan, i: usize, kind: *mut c_int, pass_index: *mut u32, partner_bits: *mut u8, cap: usize) -> c_int;
+        pub fn qsv_plan_get_layout(p: *const QsvPlan, which: c_int, out_layout: *mut u8, cap: usize) -> c_int;
+        pub fn qsv_plan_stats(p: *const QsvPlan, stats: *mut QsvStats) -> c_int;
+        pub fn qsv_plan_serialize(p: *const QsvPlan, out: *mut c_void, cap: usize, size: *mut usize) -> c_int;
+        pub fn qsv_plan_last_error() -> *const c_char;
+        pub fn qsv_run_plan(s: *mut QsvState, p: *mut QsvPlan, stats: *mut QsvStats) -> c_int;
         pub fn qsv_sample(s: *mut QsvState, uniforms: *const f64, shots: u64, out_indices: *mut u64) -> c_int;
         pub fn qsv_norm_sqr(s: *mut QsvState, out: *mut f64) -> c_int;
+        pub fn qsv_get_layout(s: *const QsvState, out_layout: *mut u8, cap: usize) -> c_int;
+        pub fn qsv_last_step_ms(s: *const QsvState, out_ms: *mut f64, cap: usize, n_steps: *mut usize) -> c_int;
+        pub fn qsv_save(s: *mut QsvState, path: *const c_char) -> c_int;
+        pub fn qsv_load(s: *mut QsvState, path: *const c_char) -> c_int;
         pub fn qsv_synchronize(s: *mut QsvState) -> c_int;
+        pub fn qsv_device_pointer(s: *mut QsvState, dev_ptr: *mut *mut c_void, cuda_stream: *mut *mut c_void) -> c_int;
     }
 
     pub const GATE_CUSTOM: u32 = 24; // QSV_GATE_* follow the declaration order of quantr's `enum Gate`
@@ -127,11 +157,31 @@ impl DeviceState {
     }
 }
 
+impl DeviceState {
+    /// Arbitrary canonical indices (registers too large for a host `Vec`, SURVEY.md 7.2 hard part 4).
+    pub fn gather(&mut self, indices: &[u64]) -> Vec<Complex64> {
+        let mut out = vec![Complex64::new(0.0, 0.0); indices.len()];
+        let c = unsafe { ffi::qsv_gather(self.handle, indices.as_ptr(), indices.len() as u64, out.as_mut_ptr() as *mut f64) };
+        self.check(c, "qsv_gather");
+        out
+    }
+
+    pub fn norm_sqr(&mut self) -> f64 {
+        let mut out = 0f64;
+        let c = unsafe { ffi::qsv_norm_sqr(self.handle, &mut out) };
+        self.check(c, "qsv_norm_sqr");
+        out
+    }
+}
+
 impl Drop for DeviceState {
     fn drop(&mut self) {
         unsafe { ffi::qsv_destroy(self.handle) };
     }
 }
+
+/// Custom gates on this many wires or more are passed as compact columns (include/qsv.h, qsv_op.iparam = 1).
+pub const COMPACT_CUSTOM_WIRES: usize = 11;
 
 /// `qsv_op[]` plus the buffers it borrows from for the duration of `qsv_apply`.
 pub struct EncodedOps {
@@ -176,6 +226,28 @@ pub fn encode(gates: &[GateView], num_qubits: usize) -> EncodedOps {
         if let Some(closure) = g.custom {
             let k = g.controls.len() + 1;
             let dim = 1usize << k;
+            if k >= COMPACT_CUSTOM_WIRES {
+                // wide (multi-controlled) Custom gates: one 2^k column per sub-state the closure answers for,
+                // ascending (qsv_op.iparam = 1); the engine lowers them to controlled ops of the fused pass
+                let mut cols: Vec<f64> = Vec::new();
+                let mut none = vec![1u8; dim];
+                for s in 0..dim {
+                    if let Some(column) = closure(s) {
+                        none[s] = 0;
+                        for t in 0..dim {
+                            cols.push(column[t].re);
+                            cols.push(column[t].im);
+                        }
+                    }
+                }
+                enc.matrices.push(cols);
+                enc.masks.push(none);
+                op.iparam = 1;
+                op.matrix = enc.matrices.last().unwrap().as_ptr();
+                op.none_mask = enc.masks.last().unwrap().as_ptr();
+                enc.ops.push(op);
+                continue;
+            }
             let mut m = vec![0f64; 2 * dim * dim];
             let mut none = vec![0u8; dim];
             for s in 0..dim {

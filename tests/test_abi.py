@@ -19,6 +19,14 @@ def test_header_and_binding_agree():
     assert declared_functions() == sorted(F.EXPORTED_SYMBOLS)
 
 
+def test_rust_shim_declares_the_same_exports():
+    """rust/quantr-b200-shim is source-only (no rustc in the image): at least keep its extern "C" block in step with the header."""
+    text = open(os.path.join(ROOT, "rust", "quantr-b200-shim", "src", "lib.rs")).read()
+    block = text[text.index('extern "C" {'):]
+    block = block[:block.index("\n    }\n")]
+    assert sorted(set(re.findall(r"pub fn (qsv_[a-z_0-9]+)\s*\(", block))) == declared_functions()
+
+
 def test_library_exports_every_declared_symbol():
     lib = F.load_library()
     for name in declared_functions():

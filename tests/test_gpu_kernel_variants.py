@@ -37,3 +37,9 @@ def test_fused_basis_initialisation_modes(mode):
     """0: memset + ordinary first pass; 1: every tile synthesised and computed; 2 (default): zero tiles written by bulk
     stores.  Forced onto small registers as well (QSV_ASYNC=2) so the golden vectors and random circuits run through it."""
     run_inner({"QSV_FUSED_INIT": mode, "QSV_ASYNC": "2"}, "qft_closed_form or layered or golden or rerun or config3_depth100_live")
+
+
+def test_dense_custom_round_stays_covered():
+    """Multi-controlled Custom gates are lowered to controlled ops by default; with that switched off every Custom gate
+    of the reference's tests goes through the dense (CSR) round again."""
+    run_inner({"QSV_STRUCTURED_CUSTOM": "0"}, "x3sudoko or golden or none_overwrite or qft16 or post_select")

@@ -3,6 +3,8 @@
 Bars (BASELINE.json north_star): amplitudes within 1e-12 max-abs of the oracle on identical circuits;
 measure_all bin counts pass a chi-square test against the oracle's probabilities.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -381,6 +383,30 @@ def test_plan_rerun_and_range_access():
         outs.append(s.download(1000, 5000))
         assert np.max(np.abs(outs[-1] - qft_expected(n, x)[1000:6000])) < TOL
     s.close()
+
+
+def test_checkpoint_round_trip(tmp_path):
+    """qsv_save / qsv_load: a state carried from one circuit to the next through a file equals running them back to back."""
+    n = 14
+    rng = np.random.default_rng(14)
+    c1 = random_any_gate_circuit(OracleCircuit, G, n, 80, rng)
+    c2 = random_any_gate_circuit(OracleCircuit, G, n, 80, rng)
+    e1, e2 = encode_gates(c1.circuit_gates, n), encode_gates(c2.circuit_gates, n)
+    s = qb.DeviceState(n)
+    s.apply(e1)
+    path = str(tmp_path / "state.qsv")
+    s.save(path)
+    assert os.path.getsize(path) == 256 + (16 << n)
+    s.apply(e2)
+    want = s.download()
+    s.close()
+    t = qb.DeviceState(n)
+    t.load(path)
+    t.apply(e2)
+    assert np.max(np.abs(t.download() - want)) == 0.0
+    with pytest.raises(F.QsvError):
+        qb.DeviceState(n + 1).load(path)
+    t.close()
 
 
 def test_error_paths_on_device():

@@ -83,6 +83,8 @@ def _worker(rank, world, port, result_dir):
     st2 = s2.apply(enc2)
     results["rand"] = s2.gather(np.arange(1 << n2, dtype=np.uint64))
     results["rand_exchanges"] = st2["n_exchanges"]
+    results["rand_layout_identity"] = s2.layout() == list(range(n2))
+    results["rand_download"] = s2.download(0, 1 << n2)  # remapped layout: collective, un-permuted on the device
     s2.peer_import([])  # importers unmap their peers before any exporter frees its shard (CUDA IPC teardown order)
     dist.barrier()
     s2.close()
@@ -116,3 +118,4 @@ def test_two_gpu_sharded_register_matches_oracle(tmp_path):
     ref = orc.simulate(n2, enc2.ops, enc2.n_ops, reg, mode="dense")
     assert int(out["rand_exchanges"]) >= 1
     assert np.max(np.abs(out["rand"] - ref)) < 1e-12
+    assert np.max(np.abs(out["rand_download"] - ref)) < 1e-12

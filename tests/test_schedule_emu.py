@@ -176,3 +176,27 @@ def test_basis_initialisation_fused_into_the_first_pass(n, tile_bits, low_bits, 
         assert lib.qsv_emu_run_plan_fused_init(plan.handle, amps.ctypes.data_as(C.POINTER(C.c_double)), 0, x, mode) == 0
         assert np.max(np.abs(amps[:1 << n] - ref)) < 1e-12
         plan.close()
+
+
+def test_peephole_optimiser_merges_and_cancels_single_qubit_gates():
+    """H.H, X.X and Rx.Rx^-1 vanish (also across gates that commute with them); runs of rotations on one wire become one
+    matrix.  Anchor: the reference walks every gate separately (src/circuit/simulation.rs:37-56)."""
+    n = 6
+    c = OracleCircuit.new(n)
+    c.add_gate(G.H, 0).add_gate(G.X, 3).add_gate(G.CNot(1), 2).add_gate(G.H, 0).add_gate(G.X, 3)  # CNot(1->2) commutes with wires 0 and 3
+    c.add_gate(G.Rx(0.4), 5).add_gate(G.Rz(0.3), 4).add_gate(G.Rx(-0.4), 5)
+    enc = encode_gates(c.circuit_gates, n)
+    desc = qb.Plan(n, enc, lib=__import__("helpers").emu_lib()).describe()
+    assert desc["n_gates"] == 8 and desc["n_lowered_ops"] == 2  # CNot and Rz survive
+    rng = np.random.default_rng(3)
+    c2 = OracleCircuit.new(n)
+    for _ in range(40):
+        w = int(rng.integers(0, n))
+        c2.add_gate([G.H, G.Rx(0.3), G.Ry(1.1), G.Rz(0.7), G.X, G.Y, G.T][int(rng.integers(0, 7))], w)
+    enc2 = encode_gates(c2.circuit_gates, n)
+    d2 = qb.Plan(n, enc2, lib=__import__("helpers").emu_lib()).describe()
+    assert d2["n_lowered_ops"] <= 2 * n  # at most one matrix + one merged phase per wire
+    reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    reg /= np.linalg.norm(reg)
+    ref = orc.simulate(n, enc2.ops, enc2.n_ops, reg, mode="dense")
+    assert np.max(np.abs(emu_simulate(n, enc2, reg) - ref)) < 1e-13
