@@ -132,14 +132,18 @@ QSV_HD void c_mul_ip(cplx& a, double fr, double fi) {
 // CTRL = false: no control among the register slots (the common case): straight-line code.
 // m = {m00.re, m00.im, m01.re, m01.im, m10.re, m10.im, m11.re, m11.im}
 
-template <int J, bool CTRL>
-QSV_HD void mat_general(cplx (&a)[kSlots], const double (&m)[16], uint32_t cm) {
+// DUAL (MatFlags::MAT_DUAL): no pair is skipped; a pair takes m[0..8) where every control of the op holds (`sat`: its
+// controls outside the registers, per thread; CTRL: and the pair's register controls) and m[8..16) otherwise.
+template <int J, bool CTRL, bool DUAL = false>
+QSV_HD void mat_general(cplx (&a)[kSlots], const double* m, uint32_t cm, bool sat = true) {
     if constexpr (J < kRegBits) {
-    const double ar = m[0], ai = m[1], br = m[2], bi = m[3], cr = m[4], ci = m[5], dr = m[6], di = m[7];
+    if (DUAL && !CTRL && !sat) m += 8;
 #pragma unroll
     for (int s0 = 0; s0 < kSlots; ++s0) {
         if ((s0 >> J) & 1) continue;
-        if (CTRL && (s0 & cm) != cm) continue;
+        if (!DUAL && CTRL && (s0 & cm) != cm) continue;
+        const double* mm = (DUAL && CTRL && !(sat && (s0 & cm) == cm)) ? m + 8 : m;
+        const double ar = mm[0], ai = mm[1], br = mm[2], bi = mm[3], cr = mm[4], ci = mm[5], dr = mm[6], di = mm[7];
         cplx& x = a[s0];
         cplx& y = a[s0 | (1 << J)];
         // four chains of three into temporaries; each output's last FMA consumes (and overwrites) its own input
@@ -163,14 +167,16 @@ QSV_HD void mat_general(cplx (&a)[kSlots], const double (&m)[16], uint32_t cm) {
     }  // J < kRegBits
 }
 
-template <int J, bool CTRL>
-QSV_HD void mat_real(cplx (&a)[kSlots], const double (&m)[16], uint32_t cm) {
+template <int J, bool CTRL, bool DUAL = false>
+QSV_HD void mat_real(cplx (&a)[kSlots], const double* m, uint32_t cm, bool sat = true) {
     if constexpr (J < kRegBits) {
-    const double ar = m[0], br = m[2], cr = m[4], dr = m[6];
+    if (DUAL && !CTRL && !sat) m += 8;
 #pragma unroll
     for (int s0 = 0; s0 < kSlots; ++s0) {
         if ((s0 >> J) & 1) continue;
-        if (CTRL && (s0 & cm) != cm) continue;
+        if (!DUAL && CTRL && (s0 & cm) != cm) continue;
+        const double* mm = (DUAL && CTRL && !(sat && (s0 & cm) == cm)) ? m + 8 : m;
+        const double ar = mm[0], br = mm[2], cr = mm[4], dr = mm[6];
         cplx& x = a[s0];
         cplx& y = a[s0 | (1 << J)];
         const double t0 = f_mul(br, y.x), t1 = f_mul(br, y.y);
@@ -185,7 +191,7 @@ QSV_HD void mat_real(cplx (&a)[kSlots], const double (&m)[16], uint32_t cm) {
 }
 
 template <int J, bool CTRL>
-QSV_HD void mat_hadamard(cplx (&a)[kSlots], const double (&)[16], uint32_t cm) {
+QSV_HD void mat_hadamard(cplx (&a)[kSlots], const double*, uint32_t cm) {
     if constexpr (J < kRegBits) {
 #pragma unroll
     for (int s0 = 0; s0 < kSlots; ++s0) {
@@ -200,7 +206,7 @@ QSV_HD void mat_hadamard(cplx (&a)[kSlots], const double (&)[16], uint32_t cm) {
 }
 
 template <int J, bool CTRL>
-QSV_HD void mat_antidiag(cplx (&a)[kSlots], const double (&m)[16], uint32_t cm) {
+QSV_HD void mat_antidiag(cplx (&a)[kSlots], const double* m, uint32_t cm) {
     if constexpr (J < kRegBits) {
     const double br = m[2], bi = m[3], cr = m[4], ci = m[5];
 #pragma unroll
@@ -224,7 +230,7 @@ QSV_HD void mat_antidiag(cplx (&a)[kSlots], const double (&m)[16], uint32_t cm) 
 }
 
 template <int J, bool CTRL>
-QSV_HD void mat_xswap(cplx (&a)[kSlots], const double (&)[16], uint32_t cm) {
+QSV_HD void mat_xswap(cplx (&a)[kSlots], const double*, uint32_t cm) {
     if constexpr (J < kRegBits) {
 #pragma unroll
     for (int s0 = 0; s0 < kSlots; ++s0) {
@@ -533,6 +539,7 @@ inline uint32_t op_dispatch_code(const DevOp& op) {
         case OP_MAT_ANTIDIAG: kind = 4; break;
         default: break;
     }
+    if (kind >= 0 && (op.flags & MAT_DUAL)) return kCodeDualBase + (op.type == OP_MAT_GENERAL ? 8u : 0u) + (op.cmask_reg ? 4u : 0u) + op.slot;  // REAL or GENERAL
     if (kind >= 0) return kCodeMatBase + (uint32_t)kind * 8u + (op.cmask_reg ? 4u : 0u) + op.slot;
     if (op.type == OP_DIAG) {
         uint32_t sel = 5;
@@ -552,6 +559,16 @@ inline uint32_t op_dispatch_code(const DevOp& op) {
     case kCodeMatBase + KIND * 8 + 5: FN<1, true>(a, op.m, op.cmask_reg); break;             \
     case kCodeMatBase + KIND * 8 + 6: FN<2, true>(a, op.m, op.cmask_reg); break;             \
     case kCodeMatBase + KIND * 8 + 7: FN<3, true>(a, op.m, op.cmask_reg); break;
+
+#define QSV_DUAL_CASES(GENERAL, FN)                                                                         \
+    case kCodeDualBase + GENERAL * 8 + 0: FN<0, false, true>(a, op.m, 0u, sat); break;                      \
+    case kCodeDualBase + GENERAL * 8 + 1: FN<1, false, true>(a, op.m, 0u, sat); break;                      \
+    case kCodeDualBase + GENERAL * 8 + 2: FN<2, false, true>(a, op.m, 0u, sat); break;                      \
+    case kCodeDualBase + GENERAL * 8 + 3: FN<3, false, true>(a, op.m, 0u, sat); break;                      \
+    case kCodeDualBase + GENERAL * 8 + 4: FN<0, true, true>(a, op.m, op.cmask_reg, sat); break;             \
+    case kCodeDualBase + GENERAL * 8 + 5: FN<1, true, true>(a, op.m, op.cmask_reg, sat); break;             \
+    case kCodeDualBase + GENERAL * 8 + 6: FN<2, true, true>(a, op.m, op.cmask_reg, sat); break;             \
+    case kCodeDualBase + GENERAL * 8 + 7: FN<3, true, true>(a, op.m, op.cmask_reg, sat); break;
 
 #define QSV_HD_CASES(HAS_REG)                                                                   \
     case kCodeHdBase + (HAS_REG ? 4 : 0) + 0: hd_apply<0, HAS_REG, FAST>(a, op, ctx, e); break;       \
@@ -629,36 +646,64 @@ QSV_HD void round_store_tile_scaled(const DevRound& R, uint32_t lb, cplx* tile, 
     for (int s = 0; s < kSlots; ++s) *reinterpret_cast<cplx*>(tb + (sb ^ R.xoff[s])) = cplx{a[s].x * scale, a[s].y * scale};
 }
 
-//   act : bit o set = op o of the pass acts on this thread-group for this tile (W words)
-//   FAST: the uniform fast path (pass_is_fast): act is ignored, every op runs
+//   act : bit o set = every control of op o outside the registers holds for this thread-group and tile (W words).  A plain
+//         op whose bit is clear is skipped; a dual op (kCodeDualBase..) runs either way and picks its matrix by the bit.
+//   FAST: the uniform fast path (pass_is_fast): act is ignored, every control holds
+// The op list is walked with a counted loop: op index, dispatch code and the ops' constants are uniform over the CTA
+// (scalar registers / constant-bank operands); only the test of the thread's act bit diverges.
+#ifndef QSV_UNIFORM_OPS
+#define QSV_UNIFORM_OPS 1  // 0: the round-1 walk over the set bits of the thread's act mask (developer A/B switch)
+#endif
 template <int W, bool FAST = false>
 QSV_HD void round_ops(const DevRound& R, const DevOp* ops, const DiagCtx& ctx, const uint32_t (&act)[W], uint32_t e, cplx (&a)[kSlots]) {
     const uint32_t first = R.first_op, n = R.n_ops;  // n <= kMaxRoundOps
     if (n == 0) return;
-    if constexpr (FAST) {  // every op is active: a counted loop over uniform op indices
+    if constexpr (FAST || QSV_UNIFORM_OPS) {
         for (uint32_t o = first; o < first + n; ++o) {
             const DevOp& op = ops[o];
-            if (op.code == kCodeQft4) {  // the hot case of QFT passes: tested ahead of the dispatch tree
-                qft4_apply<true>(a, &op + 1, op.slot, op.cmask_reg, ctx, e);
-                continue;
+            const uint32_t code = op.code;
+            bool sat = true;
+            if constexpr (!FAST) {
+                uint32_t word = act[0];
+#pragma unroll
+                for (int w = 1; w < W; ++w)
+                    if ((int)(o >> 5) == w) word = act[w];
+                sat = ((word >> (o & 31u)) & 1u) != 0;
+                if (!sat && code < kCodeDualBase) continue;
             }
-            switch (op.code) {
-                QSV_MAT_CASES(0, mat_hadamard)
-                QSV_MAT_CASES(1, mat_xswap)
-                QSV_MAT_CASES(2, mat_real)
-                QSV_MAT_CASES(3, mat_general)
-                QSV_MAT_CASES(4, mat_antidiag)
-                QSV_DIAG_CASES(false)
-                QSV_DIAG_CASES(true)
-                QSV_HD_CASES(false)
-                QSV_HD_CASES(true)
-                QSV_QFT4_CASE
-                default: break;
+            if constexpr (FAST) {
+                if (code == kCodeQft4) {  // the hot case of QFT passes: tested ahead of the dispatch tree
+                    qft4_apply<true>(a, &op + 1, op.slot, op.cmask_reg, ctx, e);
+                    continue;
+                }
+            }
+            // two dispatch trees: the 2x2 routines need nothing but the op's constants; the phase routines share the
+            // DiagCtx address arithmetic, which the compiler would otherwise hoist in front of every op
+            if (code < kCodeDiagBase || code >= kCodeDualBase) {
+                switch (code) {
+                    QSV_MAT_CASES(0, mat_hadamard)
+                    QSV_MAT_CASES(1, mat_xswap)
+                    QSV_MAT_CASES(2, mat_real)
+                    QSV_MAT_CASES(3, mat_general)
+                    QSV_MAT_CASES(4, mat_antidiag)
+                    QSV_DUAL_CASES(0, mat_real)
+                    QSV_DUAL_CASES(1, mat_general)
+                    default: break;
+                }
+            } else {
+                switch (code) {
+                    QSV_QFT4_CASE
+                    QSV_DIAG_CASES(false)
+                    QSV_DIAG_CASES(true)
+                    QSV_HD_CASES(false)
+                    QSV_HD_CASES(true)
+                    default: break;
+                }
             }
         }
         return;
-    }
-    // the round's slice of the active mask, bit j = op first + j
+    } else {
+    // the round's slice of the active mask, bit j = op first + j; dual ops always run
     uint32_t lo = act[0], hi = 0;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
@@ -666,13 +711,17 @@ QSV_HD void round_ops(const DevRound& R, const DevOp* ops, const DiagCtx& ctx, c
         if ((int)(first >> 5) + 1 == w) hi = act[w];
     }
     const uint32_t sh = first & 31u;
-    uint32_t m = sh ? ((lo >> sh) | (hi << (32u - sh))) : lo;
+    const uint32_t sat_m = sh ? ((lo >> sh) | (hi << (32u - sh))) : lo;
+    uint32_t m = sat_m;
+    for (uint32_t j = 0; j < n; ++j)
+        if (ops[first + j].code >= kCodeDualBase) m |= 1u << j;
     if (n < 32u) m &= (1u << n) - 1u;
     if (!m) return;
     uint32_t j = ctz32(m);
     uint32_t code = ops[first + j].code;
     while (true) {
         const DevOp& op = ops[first + j];
+        const bool sat = ((sat_m >> j) & 1u) != 0;
         m &= m - 1;
         uint32_t jn = 0, next_code = kCodeNop;
         if (m) {  // fetch the next op's dispatch code before running this one
@@ -690,11 +739,14 @@ QSV_HD void round_ops(const DevRound& R, const DevOp* ops, const DiagCtx& ctx, c
             QSV_HD_CASES(false)
             QSV_HD_CASES(true)
             QSV_QFT4_CASE
+            QSV_DUAL_CASES(0, mat_real)
+            QSV_DUAL_CASES(1, mat_general)
             default: break;
         }
         if (!m) break;
         j = jn;
         code = next_code;
+    }
     }
 }
 

@@ -281,23 +281,67 @@ void merge_diagonals(std::vector<LOp>& lops) {
     lops.swap(kept);
 }
 
-// Peephole over commuting ops (SURVEY.md 8f "circuit-level optimiser"): a 2x2 gate is multiplied into the nearest earlier
-// 2x2 gate on the same target with the same controls when every op between them commutes with it.  H.H, X.X and the
-// like vanish; runs of rotations become one matrix (a diagonal product becomes a phase op and joins the diagonal merging).
-void merge_single_qubit_gates(std::vector<LOp>& lops) {
+// Peephole over commuting ops (SURVEY.md 8f "circuit-level optimiser").  Every 2x2 op is a pair of matrices: S, applied
+// where all its control bits are 1, and U, applied everywhere else (U = 1 for a plain controlled gate, U = S for an
+// uncontrolled one).  A 2x2 gate is multiplied into the nearest earlier 2x2 gate on the same target when every op
+// between them commutes with it and their controls agree or one of them has none: H.H, X.X and the like vanish, runs
+// of rotations become one matrix, and (merge_ctrl) a CNot/Toffoli absorbs the one-wire gates around its target,
+//   U2 . X^c . U1  =  (c ? U2.X.U1 : U2.U1),
+// a *dual* op: one 2x2 routine with a per-thread choice of constants instead of three ops, and no amplitude moves for
+// the X.  One-wire phase gates on the target fold in the same way.
+namespace {
+void mul2(const double* x, const double* y, double* out) {  // out = x . y (y acts first), 2x2 complex, row-major (re, im)
+    auto mul = [](const double* a, const double* b, double* o) { o[0] = a[0] * b[0] - a[1] * b[1]; o[1] = a[0] * b[1] + a[1] * b[0]; };
+    double t0[2], t1[2];
+    mul(x + 0, y + 0, t0); mul(x + 2, y + 4, t1); out[0] = t0[0] + t1[0]; out[1] = t0[1] + t1[1];
+    mul(x + 0, y + 2, t0); mul(x + 2, y + 6, t1); out[2] = t0[0] + t1[0]; out[3] = t0[1] + t1[1];
+    mul(x + 4, y + 0, t0); mul(x + 6, y + 4, t1); out[4] = t0[0] + t1[0]; out[5] = t0[1] + t1[1];
+    mul(x + 4, y + 2, t0); mul(x + 6, y + 6, t1); out[6] = t0[0] + t1[0]; out[7] = t0[1] + t1[1];
+}
+// H.H and friends: products that are 0 or +-1 up to rounding (|x| < 2^-50) become exact
+void snap(double* r) {
+    for (int q = 0; q < 8; ++q) {
+        if (fabs(r[q]) < 8.9e-16) r[q] = 0.0;
+        if (fabs(r[q] - 1.0) < 8.9e-16) r[q] = 1.0;
+        if (fabs(r[q] + 1.0) < 8.9e-16) r[q] = -1.0;
+    }
+}
+const double kIdentity2[8] = {1, 0, 0, 0, 0, 0, 1, 0};
+bool is_identity2(const double* m) { return memcmp(m, kIdentity2, sizeof(kIdentity2)) == 0 || (m[0] == 1.0 && m[1] == 0.0 && m[2] == 0.0 && m[3] == 0.0 && m[4] == 0.0 && m[5] == 0.0 && m[6] == 1.0 && m[7] == 0.0); }
+bool is_real2(const double* m) { return m[1] == 0.0 && m[3] == 0.0 && m[5] == 0.0 && m[7] == 0.0; }
+// picks the cheapest op type for a matrix; false if it is the identity
+bool classify_mat(const double* m, OpType* t) {
+    const bool off_zero = m[2] == 0.0 && m[3] == 0.0 && m[4] == 0.0 && m[5] == 0.0;
+    const bool diag_zero = m[0] == 0.0 && m[1] == 0.0 && m[6] == 0.0 && m[7] == 0.0;
+    if (off_zero && m[0] == 1.0 && m[1] == 0.0 && m[6] == 1.0 && m[7] == 0.0) return false;
+    if (diag_zero && m[2] == 1.0 && m[3] == 0.0 && m[4] == 1.0 && m[5] == 0.0) *t = OP_MAT_XSWAP;
+    else if (diag_zero) *t = OP_MAT_ANTIDIAG;
+    else if (is_real2(m)) *t = OP_MAT_REAL;
+    else *t = OP_MAT_GENERAL;
+    return true;
+}
+void get_su(const LOp& o, double* s, double* u) {
+    memcpy(s, o.m, sizeof(o.m));
+    memcpy(u, o.dual ? o.m2 : (o.cmask ? kIdentity2 : o.m), sizeof(o.m));
+}
+// Stores the pair (S where the controls hold, U elsewhere) in its cheapest form; false if the op became the identity.
+bool set_su(LOp& o, double* s, double* u) {
+    snap(s);
+    snap(u);
+    if (o.cmask && memcmp(s, u, sizeof(o.m)) == 0) o.cmask = 0;  // the controls no longer matter
+    o.dual = false;
+    memcpy(o.m, s, sizeof(o.m));
+    memcpy(o.m2, kIdentity2, sizeof(o.m2));
+    if (o.cmask == 0 || is_identity2(u)) return classify_mat(o.m, &o.mtype);
+    o.dual = true;
+    memcpy(o.m2, u, sizeof(o.m2));
+    o.mtype = (is_real2(s) && is_real2(u)) ? OP_MAT_REAL : OP_MAT_GENERAL;
+    return true;
+}
+}  // namespace
+
+void merge_single_qubit_gates(std::vector<LOp>& lops, bool merge_ctrl) {
     std::vector<char> dead(lops.size(), 0);
-    auto classify = [](LOp& o) {  // picks the cheapest op type for the product matrix; returns false if it is the identity
-        const double* m = o.m;
-        auto zero = [](double x) { return fabs(x) < 1e-300; };
-        const bool off_zero = zero(m[2]) && zero(m[3]) && zero(m[4]) && zero(m[5]);
-        const bool diag_zero = zero(m[0]) && zero(m[1]) && zero(m[6]) && zero(m[7]);
-        if (off_zero && m[0] == 1.0 && zero(m[1]) && m[6] == 1.0 && zero(m[7])) return false;
-        if (diag_zero && m[2] == 1.0 && zero(m[3]) && m[4] == 1.0 && zero(m[5])) o.mtype = OP_MAT_XSWAP;
-        else if (diag_zero) o.mtype = OP_MAT_ANTIDIAG;
-        else if (zero(m[1]) && zero(m[3]) && zero(m[5]) && zero(m[7])) o.mtype = OP_MAT_REAL;
-        else o.mtype = OP_MAT_GENERAL;
-        return true;
-    };
     // an uncontrolled one-wire phase gate (Rz, Z, S, T, ...) as the diagonal matrix it is
     auto diag_1q = [](const LOp& o, int* t, double* m) {
         if (o.kind != LOp::DIAG || o.cmask != 0 || o.lin.size() != 1) return false;
@@ -314,58 +358,46 @@ void merge_single_qubit_gates(std::vector<LOp>& lops) {
         double dm[8];
         const bool i_diag = diag_1q(lops[i], &dt, dm);
         if (lops[i].kind != LOp::MAT && !i_diag) continue;
-        const uint64_t tg = i_diag ? 0 : lops[i].targets(), sup = lops[i].support();
         const size_t lo = i > 256 ? i - 256 : 0;
         for (size_t j = i; j-- > lo;) {
             if (dead[j]) continue;
             LOp& p = lops[j];
+            const uint64_t tg = i_diag ? 0 : lops[i].targets(), sup = lops[i].support();
             const bool conflict = (p.targets() & sup) || (tg & p.support());
             if (!conflict) continue;
             int pt = -1;
-            double pm[8];
+            double pm[8], s[8], u[8], rs[8], ru[8];
             if (i_diag) {
-                // a phase gate right after (in commutation order) an uncontrolled 2x2 gate on its wire: fold it into the matrix
-                if (p.kind == LOp::MAT && p.cmask == 0 && p.target == dt) {
-                    double r[8];
-                    auto mul = [](const double* x, const double* y, double* out) { out[0] = x[0] * y[0] - x[1] * y[1]; out[1] = x[0] * y[1] + x[1] * y[0]; };
-                    mul(dm + 0, p.m + 0, r + 0); mul(dm + 0, p.m + 2, r + 2); mul(dm + 6, p.m + 4, r + 4); mul(dm + 6, p.m + 6, r + 6);
-                    memcpy(p.m, r, sizeof(r));
-                    if (p.mtype == OP_MAT_HADAMARD || p.mtype == OP_MAT_REAL || p.mtype == OP_MAT_XSWAP) p.mtype = OP_MAT_GENERAL;
+                // a phase gate right after (in commutation order) a 2x2 gate on its wire: fold it into the matrices
+                if (p.kind == LOp::MAT && p.target == dt && (p.cmask == 0 || merge_ctrl)) {
+                    get_su(p, s, u);
+                    mul2(dm, s, rs);
+                    mul2(dm, u, ru);
                     dead[i] = 1;
+                    if (!set_su(p, rs, ru)) dead[j] = 1;
                 }
                 break;
             }
-            if (lops[i].cmask == 0 && diag_1q(p, &pt, pm) && pt == lops[i].target) {
-                // an uncontrolled 2x2 gate right after a phase gate on its wire: absorb the phase gate and keep looking back
-                double r[8];
-                auto mul = [](const double* x, const double* y, double* out) { out[0] = x[0] * y[0] - x[1] * y[1]; out[1] = x[0] * y[1] + x[1] * y[0]; };
-                const double* a = lops[i].m;
-                mul(a + 0, pm + 0, r + 0); mul(a + 2, pm + 6, r + 2); mul(a + 4, pm + 0, r + 4); mul(a + 6, pm + 6, r + 6);
-                memcpy(lops[i].m, r, sizeof(r));
-                lops[i].mtype = OP_MAT_GENERAL;
+            if ((lops[i].cmask == 0 || merge_ctrl) && diag_1q(p, &pt, pm) && pt == lops[i].target) {
+                // a 2x2 gate right after a phase gate on its wire: absorb the phase gate and keep looking back
+                get_su(lops[i], s, u);
+                mul2(s, pm, rs);
+                mul2(u, pm, ru);
                 dead[j] = 1;
+                if (!set_su(lops[i], rs, ru)) { dead[i] = 1; break; }
                 continue;
             }
-            if (p.kind == LOp::MAT && p.target == lops[i].target && p.cmask == lops[i].cmask) {
-                // product = M_i * M_j (j acts first)
-                const double* a = lops[i].m;
-                double b[8], r[8];
-                memcpy(b, p.m, sizeof(b));
-                auto mul = [](const double* x, const double* y, double* out) { out[0] = x[0] * y[0] - x[1] * y[1]; out[1] = x[0] * y[1] + x[1] * y[0]; };
-                double t0[2], t1[2];
-                mul(a + 0, b + 0, t0); mul(a + 2, b + 4, t1); r[0] = t0[0] + t1[0]; r[1] = t0[1] + t1[1];  // r00 = a00 b00 + a01 b10
-                mul(a + 0, b + 2, t0); mul(a + 2, b + 6, t1); r[2] = t0[0] + t1[0]; r[3] = t0[1] + t1[1];  // r01 = a00 b01 + a01 b11
-                mul(a + 4, b + 0, t0); mul(a + 6, b + 4, t1); r[4] = t0[0] + t1[0]; r[5] = t0[1] + t1[1];  // r10 = a10 b00 + a11 b10
-                mul(a + 4, b + 2, t0); mul(a + 6, b + 6, t1); r[6] = t0[0] + t1[0]; r[7] = t0[1] + t1[1];  // r11 = a10 b01 + a11 b11
-                // H.H and friends: snap products that are the identity up to rounding (|x| < 2^-50) to exact values
-                for (int q = 0; q < 8; ++q) {
-                    if (fabs(r[q]) < 8.9e-16) r[q] = 0.0;
-                    if (fabs(r[q] - 1.0) < 8.9e-16) r[q] = 1.0;
-                    if (fabs(r[q] + 1.0) < 8.9e-16) r[q] = -1.0;
-                }
-                memcpy(p.m, r, sizeof(r));
+            if (p.kind == LOp::MAT && p.target == lops[i].target &&
+                (p.cmask == lops[i].cmask || (merge_ctrl && (p.cmask == 0 || lops[i].cmask == 0)))) {
+                // product = M_i * M_j (j acts first), for the controlled and the uncontrolled half
+                double ps[8], pu[8];
+                get_su(lops[i], s, u);
+                get_su(p, ps, pu);
+                mul2(s, ps, rs);
+                mul2(u, pu, ru);
+                p.cmask |= lops[i].cmask;
                 dead[i] = 1;
-                if (!classify(p)) dead[j] = 1;
+                if (!set_su(p, rs, ru)) dead[j] = 1;
             }
             break;  // the nearest op that does not commute decides
         }
@@ -624,7 +656,11 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
                 const int lp = local_of[lop.target];
                 if (lp < 0 || slot_of[lp] < 0) fail("internal: MAT target not a register bit");
                 d.slot = (uint32_t)slot_of[lp];
-                memcpy(d.m, lop.m, sizeof(d.m));
+                memcpy(d.m, lop.m, sizeof(lop.m));
+                if (lop.dual) {  // second matrix: where the controls do not hold
+                    memcpy(d.m + 8, lop.m2, sizeof(lop.m2));
+                    d.flags |= MAT_DUAL;
+                }
                 if (lop.mtype == OP_MAT_HADAMARD) ++n_hadamard;
             } else {
                 d.type = OP_DIAG;
@@ -782,7 +818,7 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
     plan.lops.clear();
     plan.n_rounds = 0;
     lower_gates(n_qubits, ops, n_ops, plan.lops, &plan.n_gates);
-    if (plan.opt.fuse && plan.opt.merge_1q) merge_single_qubit_gates(plan.lops);
+    if (plan.opt.fuse && plan.opt.merge_1q) merge_single_qubit_gates(plan.lops, plan.opt.merge_ctrl != 0);
     if (plan.opt.fuse) merge_diagonals(plan.lops);
     // tile size: 11 for registers the pipelined kernel serves (measured on B200, DESIGN.md 6: four compute groups of
     // 128 threads overlap better than two of 256), else 12; widened when a Custom gate needs more tile bits
@@ -1131,11 +1167,15 @@ void prefix_amplitudes(const Plan& plan, uint64_t basis_index, std::vector<cplx>
     const uint64_t local = phys & ((1ull << nl) - 1ull), rank_mask = (P - 1ull) << nl;
     for (const LOp& op : plan.prefix) {
         if (op.kind == LOp::MAT) {
-            if ((local & op.cmask & ~rank_mask) != (op.cmask & ~rank_mask)) continue;  // a control on a local bit that is 0
+            const bool local_sat = (local & op.cmask & ~rank_mask) == (op.cmask & ~rank_mask);  // controls on local bits (constants here)
+            if (!local_sat && !op.dual) continue;
             const uint64_t cm = (op.cmask & rank_mask) >> nl, tb = 1ull << (op.target - (int)nl);
-            const cplx m00{op.m[0], op.m[1]}, m01{op.m[2], op.m[3]}, m10{op.m[4], op.m[5]}, m11{op.m[6], op.m[7]};
             for (uint64_t r = 0; r < P; ++r) {
-                if ((r & tb) || (r & cm) != cm) continue;
+                if (r & tb) continue;
+                const bool sat = local_sat && (r & cm) == cm;
+                if (!sat && !op.dual) continue;
+                const double* m = sat ? op.m : op.m2;  // dual ops: m2 where the controls do not hold
+                const cplx m00{m[0], m[1]}, m01{m[2], m[3]}, m10{m[4], m[5]}, m11{m[6], m[7]};
                 const cplx a0 = out[r], a1 = out[r | tb];
                 const cplx p00 = cmul(m00, a0), p01 = cmul(m01, a1), p10 = cmul(m10, a0), p11 = cmul(m11, a1);
                 out[r] = cplx{p00.x + p01.x, p00.y + p01.y};
@@ -1158,7 +1198,10 @@ std::string describe_plan(const Plan& plan) {
     std::ostringstream os;
     os << "{\"n_qubits\":" << plan.n_qubits << ",\"n_local\":" << plan.n_local << ",\"n_alloc\":" << plan.n_alloc
        << ",\"tile_bits\":" << std::min<int>(plan.opt.tile_bits, (int)plan.n_alloc) << ",\"low_bits\":" << plan.opt.low_bits
-       << ",\"n_gates\":" << plan.n_gates << ",\"n_lowered_ops\":" << plan.lops.size() << ",\"prefix_ops\":" << plan.prefix.size() << ",\"passes\":[";
+       << ",\"n_gates\":" << plan.n_gates << ",\"n_lowered_ops\":" << plan.lops.size() << ",\"prefix_ops\":" << plan.prefix.size();
+    size_t n_dual = 0;
+    for (const LOp& lop : plan.lops) n_dual += lop.kind == LOp::MAT && lop.dual;
+    os << ",\"n_dual_ops\":" << n_dual << ",\"passes\":[";
     for (size_t p = 0; p < plan.passes.size(); ++p) {
         const uint8_t* blob = plan.passes[p].data();
         const DevPass* h = reinterpret_cast<const DevPass*>(blob);

@@ -23,6 +23,10 @@ struct LOp {
     uint64_t cmask = 0;
     OpType mtype = OP_MAT_GENERAL;
     double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // MAT, dual: `m` is applied where all bits of cmask are 1 and `m2` everywhere else (a controlled gate multiplied
+    // together with its uncontrolled neighbours on the target: U2.X^c.U1 = U2.U1 or U2.X.U1, merge_single_qubit_gates)
+    bool dual = false;
+    double m2[8] = {1, 0, 0, 0, 0, 0, 1, 0};
     // DIAG: amp *= exp(i*pi*(theta0 + sum coef*bit)) where all bits of cmask are 1 (half-turns)
     double theta0 = 0;
     std::vector<std::pair<int, double>> lin;
@@ -45,6 +49,7 @@ struct PlanOptions {
     int fold_prefix = 1;  // sharded basis states: leading gates on the qubits held in the rank id are applied on the host (build_plan)
     int reorder = 1;      // passes take later ops that commute with the ops they had to leave behind (plan.cpp schedule)
     int merge_1q = 1;     // 2x2 gates on the same target and controls are multiplied together across commuting ops; identities vanish
+    int merge_ctrl = 1;   // ... and a controlled 2x2 gate absorbs its uncontrolled neighbours on the target (dual-matrix ops)
 };
 
 // One step of a plan: a fused pass over the local shard, or a global-qubit remap that swaps the index bits held in
@@ -83,7 +88,7 @@ struct Plan {
 // Throws std::runtime_error with a message on invalid input / unsupported circuits.
 void lower_gates(uint32_t n_qubits, const qsv_op* ops, size_t n_ops, std::vector<LOp>& out, uint64_t* n_gates);
 void merge_diagonals(std::vector<LOp>& lops);
-void merge_single_qubit_gates(std::vector<LOp>& lops);
+void merge_single_qubit_gates(std::vector<LOp>& lops, bool merge_ctrl = true);
 // initial_layout: nullptr = identity; free_layout: let the scheduler choose the initial layout (sharded basis states).
 void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* ops, size_t n_ops, const PlanOptions& opt,
                 const uint8_t* initial_layout = nullptr, bool free_layout = false);

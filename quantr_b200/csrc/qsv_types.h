@@ -76,7 +76,9 @@ constexpr int kDiagTblLen = 64;  // lo[32] (thread-index bits 0-4) + hi[32] (bit
 //         adjacent register bits, highest first, whose register-bit phases are the QFT ones (pi/2, pi/4, pi/8).  The
 //         DevOp carries no constants; the DIAG ops of the (3 or 4, DevOp::slot) stages follow it in the op array outside
 //         the round's op range and supply the tile/thread factors (pass_core.h qft4_apply).
-constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeHdBase = 53, kCodeQft4 = 61, kCodeCount = 62;
+//   DUAL: 62 + general*8 + ctrl*4 + slot: a 2x2 op with two matrices (MatFlags::MAT_DUAL) - m[0..8) where all its controls
+//         hold, m[8..16) everywhere else - of kind REAL (general = 0) or GENERAL; such an op is never skipped
+constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeHdBase = 53, kCodeQft4 = 61, kCodeDualBase = 62, kCodeCount = 78;
 enum PassFlags : uint32_t {
     PASS_DIRECT_STORE = 2,  // the last round writes its registers straight to global memory (coalesced: its register bits
                             // exclude the three lowest tile bits)
@@ -93,6 +95,9 @@ enum DiagFlags : uint32_t {
     // bits 8..22: which entries of the register-constant table are not 1 (see DevOp::m)
     DIAG_NONTRIVIAL_SHIFT = 8
 };
+enum MatFlags : uint32_t {
+    MAT_DUAL = 1  // DevOp::m holds two matrices: m[0..8) where every control holds, m[8..16) elsewhere
+};
 enum RoundType : uint32_t { ROUND_REG = 0, ROUND_DENSE = 1 };
 
 struct DiagExtTerm {
@@ -108,9 +113,9 @@ struct DevOp {
     uint32_t cmask_reg;   // controls among the register slots (4 bits)
     uint32_t cmask_thr;   // controls among the tile-local, non-register bits (tile-local positions)
     uint64_t cmask_ext;   // controls outside the tile (physical bit positions, rank bits included)
-    uint32_t flags;       // DIAG: DiagFlags
+    uint32_t flags;       // DIAG: DiagFlags; MAT: MatFlags
     uint32_t diag_index;  // DIAG: slot in the per-tile external-phase array
-    double m[16];         // MAT: m00 m01 m10 m11 (re, im) in m[0..8).
+    double m[16];         // MAT: m00 m01 m10 m11 (re, im) in m[0..8); MAT_DUAL: the matrix for unsatisfied controls in m[8..16).
                           // DIAG with one register control bit c: m[2(q-1)], m[2(q-1)+1] = exp(i*pi*sum of the coefs of the
                           //   free register bits in q), q = 1..7 over the register bits other than c in ascending order;
                           // DIAG otherwise: m[2k], m[2k+1] = r_k = exp(i*pi*coef of register bit k), k = 0..3.

@@ -200,3 +200,42 @@ def test_peephole_optimiser_merges_and_cancels_single_qubit_gates():
     reg /= np.linalg.norm(reg)
     ref = orc.simulate(n, enc2.ops, enc2.n_ops, reg, mode="dense")
     assert np.max(np.abs(emu_simulate(n, enc2, reg) - ref)) < 1e-13
+
+
+def test_controlled_gates_absorb_their_target_neighbours():
+    """merge_ctrl: U2 . CNot . U1 on the target becomes one dual-matrix op (U2.X.U1 where the control holds, U2.U1
+    elsewhere) - with the control among the register, thread and tile-index bits, for Toffoli, and for phase gates on the
+    target; CNot.CNot vanishes.  Anchor: the reference applies every gate on its own (src/circuit/simulation.rs:37-56)."""
+    emu = __import__("helpers").emu_lib()
+    n = 12
+    c = OracleCircuit.new(n)
+    c.add_gate(G.Ry(0.3), 5).add_gate(G.CNot(2), 5).add_gate(G.Rx(1.2), 5)
+    desc = qb.Plan(n, encode_gates(c.circuit_gates, n), lib=emu).describe()
+    assert desc["n_lowered_ops"] == 1 and desc["n_dual_ops"] == 1
+    c = OracleCircuit.new(n)
+    c.add_gate(G.CNot(2), 5).add_gate(G.H, 7).add_gate(G.CNot(2), 5)  # X.X on the target: nothing left but the H
+    desc = qb.Plan(n, encode_gates(c.circuit_gates, n), lib=emu).describe()
+    assert desc["n_lowered_ops"] == 1 and desc["n_dual_ops"] == 0
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        c = OracleCircuit.new(n)
+        for _ in range(60):
+            w = [int(x) for x in rng.permutation(n)[:3]]
+            k = int(rng.integers(0, 7))
+            th = float(rng.uniform(-3, 3))
+            if k == 0:
+                c.add_gate(G.CNot(w[0]), w[1])
+            elif k == 1:
+                c.add_gate(G.Toffoli(w[0], w[1]), w[2])
+            elif k == 2:
+                c.add_gate(G.CZ(w[0]), w[1])
+            else:
+                c.add_gate([G.H, G.Rx(th), G.Ry(th), G.Rz(th)][k - 3], w[int(rng.integers(0, 3))])
+        enc = encode_gates(c.circuit_gates, n)
+        reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+        reg /= np.linalg.norm(reg)
+        ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense")
+        for tile_bits, low_bits in [(0, 0), (6, 2), (8, 3), (10, 3)]:
+            out, desc = emu_simulate(n, enc, reg, tile_bits=tile_bits, low_bits=low_bits, describe=True)
+            assert desc["n_dual_ops"] > 0
+            assert np.max(np.abs(out - ref)) < 1e-12, (trial, tile_bits, low_bits)

@@ -12,6 +12,7 @@ c = random_layered_circuit(OracleCircuit, qb.Gate, n, d, seed=30)
 enc = encode_gates(list(c.circuit_gates), n)
 s = qb.DeviceState(n)
 s.set_option("timing", 1)
+if os.environ.get("QSV_LOW_BITS"): s.set_option("low_bits", int(os.environ["QSV_LOW_BITS"]))
 for rep in range(2):
     s.init_basis(0)
     st = s.apply(enc)
