@@ -539,8 +539,7 @@ inline uint32_t op_dispatch_code(const DevOp& op) {
         case OP_MAT_ANTIDIAG: kind = 4; break;
         default: break;
     }
-    if (kind >= 0 && (op.flags & MAT_DUAL)) return kCodeDualBase + (op.type == OP_MAT_GENERAL ? 8u : 0u) + (op.cmask_reg ? 4u : 0u) + op.slot;  // REAL or GENERAL
-    if (kind >= 0) return kCodeMatBase + (uint32_t)kind * 8u + (op.cmask_reg ? 4u : 0u) + op.slot;
+    if (kind >= 0) return (kCodeMatBase + (uint32_t)kind * 8u + (op.cmask_reg ? 4u : 0u) + op.slot) | ((op.flags & MAT_DUAL) ? kCodeDualFlag : 0u);  // dual: REAL or GENERAL
     if (op.type == OP_DIAG) {
         uint32_t sel = 5;
         if (op.cmask_reg == 0) sel = 0;
@@ -550,25 +549,31 @@ inline uint32_t op_dispatch_code(const DevOp& op) {
     return kCodeNop;
 }
 
+// c = the op's matrix, already in registers (for a dual op without register controls: the one this thread applies)
 #define QSV_MAT_CASES(KIND, FN)                                                              \
-    case kCodeMatBase + KIND * 8 + 0: FN<0, false>(a, op.m, 0u); break;                      \
-    case kCodeMatBase + KIND * 8 + 1: FN<1, false>(a, op.m, 0u); break;                      \
-    case kCodeMatBase + KIND * 8 + 2: FN<2, false>(a, op.m, 0u); break;                      \
-    case kCodeMatBase + KIND * 8 + 3: FN<3, false>(a, op.m, 0u); break;                      \
-    case kCodeMatBase + KIND * 8 + 4: FN<0, true>(a, op.m, op.cmask_reg); break;             \
-    case kCodeMatBase + KIND * 8 + 5: FN<1, true>(a, op.m, op.cmask_reg); break;             \
-    case kCodeMatBase + KIND * 8 + 6: FN<2, true>(a, op.m, op.cmask_reg); break;             \
-    case kCodeMatBase + KIND * 8 + 7: FN<3, true>(a, op.m, op.cmask_reg); break;
-
-#define QSV_DUAL_CASES(GENERAL, FN)                                                                         \
-    case kCodeDualBase + GENERAL * 8 + 0: FN<0, false, true>(a, op.m, 0u, sat); break;                      \
-    case kCodeDualBase + GENERAL * 8 + 1: FN<1, false, true>(a, op.m, 0u, sat); break;                      \
-    case kCodeDualBase + GENERAL * 8 + 2: FN<2, false, true>(a, op.m, 0u, sat); break;                      \
-    case kCodeDualBase + GENERAL * 8 + 3: FN<3, false, true>(a, op.m, 0u, sat); break;                      \
-    case kCodeDualBase + GENERAL * 8 + 4: FN<0, true, true>(a, op.m, op.cmask_reg, sat); break;             \
-    case kCodeDualBase + GENERAL * 8 + 5: FN<1, true, true>(a, op.m, op.cmask_reg, sat); break;             \
-    case kCodeDualBase + GENERAL * 8 + 6: FN<2, true, true>(a, op.m, op.cmask_reg, sat); break;             \
-    case kCodeDualBase + GENERAL * 8 + 7: FN<3, true, true>(a, op.m, op.cmask_reg, sat); break;
+    case kCodeMatBase + KIND * 8 + 0: FN<0, false>(a, c, 0u); break;                         \
+    case kCodeMatBase + KIND * 8 + 1: FN<1, false>(a, c, 0u); break;                         \
+    case kCodeMatBase + KIND * 8 + 2: FN<2, false>(a, c, 0u); break;                         \
+    case kCodeMatBase + KIND * 8 + 3: FN<3, false>(a, c, 0u); break;                         \
+    case kCodeMatBase + KIND * 8 + 4: FN<0, true>(a, c, op.cmask_reg); break;                \
+    case kCodeMatBase + KIND * 8 + 5: FN<1, true>(a, c, op.cmask_reg); break;                \
+    case kCodeMatBase + KIND * 8 + 6: FN<2, true>(a, c, op.cmask_reg); break;                \
+    case kCodeMatBase + KIND * 8 + 7: FN<3, true>(a, c, op.cmask_reg); break;
+// REAL and GENERAL may be dual: with register controls the choice of matrix is per pair
+#define QSV_MAT2_CTRL_CASE(KIND, FN, J)                                                      \
+    case kCodeMatBase + KIND * 8 + 4 + J:                                                    \
+        if (dual) FN<J, true, true>(a, op.m, op.cmask_reg, sat);                             \
+        else FN<J, true>(a, c, op.cmask_reg);                                                \
+        break;
+#define QSV_MAT2_CASES(KIND, FN)                                                             \
+    case kCodeMatBase + KIND * 8 + 0: FN<0, false>(a, c, 0u); break;                         \
+    case kCodeMatBase + KIND * 8 + 1: FN<1, false>(a, c, 0u); break;                         \
+    case kCodeMatBase + KIND * 8 + 2: FN<2, false>(a, c, 0u); break;                         \
+    case kCodeMatBase + KIND * 8 + 3: FN<3, false>(a, c, 0u); break;                         \
+    QSV_MAT2_CTRL_CASE(KIND, FN, 0)                                                          \
+    QSV_MAT2_CTRL_CASE(KIND, FN, 1)                                                          \
+    QSV_MAT2_CTRL_CASE(KIND, FN, 2)                                                          \
+    QSV_MAT2_CTRL_CASE(KIND, FN, 3)
 
 #define QSV_HD_CASES(HAS_REG)                                                                   \
     case kCodeHdBase + (HAS_REG ? 4 : 0) + 0: hd_apply<0, HAS_REG, FAST>(a, op, ctx, e); break;       \
@@ -647,106 +652,70 @@ QSV_HD void round_store_tile_scaled(const DevRound& R, uint32_t lb, cplx* tile, 
 }
 
 //   act : bit o set = every control of op o outside the registers holds for this thread-group and tile (W words).  A plain
-//         op whose bit is clear is skipped; a dual op (kCodeDualBase..) runs either way and picks its matrix by the bit.
+//         op whose bit is clear is skipped; a dual op (kCodeDualFlag) runs either way and picks its matrix by the bit.
 //   FAST: the uniform fast path (pass_is_fast): act is ignored, every control holds
-// The op list is walked with a counted loop: op index, dispatch code and the ops' constants are uniform over the CTA
-// (scalar registers / constant-bank operands); only the test of the thread's act bit diverges.
-#ifndef QSV_UNIFORM_OPS
-#define QSV_UNIFORM_OPS 1  // 0: the round-1 walk over the set bits of the thread's act mask (developer A/B switch)
+// The op list is walked with a counted loop: op index, dispatch code and the ops' constants are uniform over the CTA;
+// only the test of the thread's act bit diverges.  The op's matrix is fetched ahead of the dispatch tree so that the
+// constant-bank latency overlaps it (fetching the next op's dispatch code ahead as well costs a register the kernel
+// does not have: it spills inside this loop).
+#ifndef QSV_PRELOAD
+#define QSV_PRELOAD 0  // 1: the 2x2 routines get their constants loaded ahead of the dispatch tree - measured slower on B200 (2.60 s vs 2.01 s on config 3: the 16 extra live registers spill inside the op loop)
 #endif
 template <int W, bool FAST = false>
 QSV_HD void round_ops(const DevRound& R, const DevOp* ops, const DiagCtx& ctx, const uint32_t (&act)[W], uint32_t e, cplx (&a)[kSlots]) {
     const uint32_t first = R.first_op, n = R.n_ops;  // n <= kMaxRoundOps
     if (n == 0) return;
-    if constexpr (FAST || QSV_UNIFORM_OPS) {
-        for (uint32_t o = first; o < first + n; ++o) {
-            const DevOp& op = ops[o];
-            const uint32_t code = op.code;
-            bool sat = true;
-            if constexpr (!FAST) {
-                uint32_t word = act[0];
+    for (uint32_t o = first; o < first + n; ++o) {
+        const DevOp& op = ops[o];
+        const uint32_t full_code = op.code;
+        const bool dual = (full_code & kCodeDualFlag) != 0;
+        const uint32_t code = full_code & (kCodeDualFlag - 1u);
+        bool sat = true;
+        if constexpr (!FAST) {
+            uint32_t word = act[0];
 #pragma unroll
-                for (int w = 1; w < W; ++w)
-                    if ((int)(o >> 5) == w) word = act[w];
-                sat = ((word >> (o & 31u)) & 1u) != 0;
-                if (!sat && code < kCodeDualBase) continue;
-            }
-            if constexpr (FAST) {
-                if (code == kCodeQft4) {  // the hot case of QFT passes: tested ahead of the dispatch tree
-                    qft4_apply<true>(a, &op + 1, op.slot, op.cmask_reg, ctx, e);
-                    continue;
-                }
-            }
-            // two dispatch trees: the 2x2 routines need nothing but the op's constants; the phase routines share the
-            // DiagCtx address arithmetic, which the compiler would otherwise hoist in front of every op
-            if (code < kCodeDiagBase || code >= kCodeDualBase) {
-                switch (code) {
-                    QSV_MAT_CASES(0, mat_hadamard)
-                    QSV_MAT_CASES(1, mat_xswap)
-                    QSV_MAT_CASES(2, mat_real)
-                    QSV_MAT_CASES(3, mat_general)
-                    QSV_MAT_CASES(4, mat_antidiag)
-                    QSV_DUAL_CASES(0, mat_real)
-                    QSV_DUAL_CASES(1, mat_general)
-                    default: break;
-                }
-            } else {
-                switch (code) {
-                    QSV_QFT4_CASE
-                    QSV_DIAG_CASES(false)
-                    QSV_DIAG_CASES(true)
-                    QSV_HD_CASES(false)
-                    QSV_HD_CASES(true)
-                    default: break;
-                }
+            for (int w = 1; w < W; ++w)
+                if ((int)(o >> 5) == w) word = act[w];
+            sat = ((word >> (o & 31u)) & 1u) != 0;
+            if (!sat && !dual) continue;
+        }
+        if constexpr (FAST) {
+            if (code == kCodeQft4) {  // the hot case of QFT passes: tested ahead of the dispatch tree
+                qft4_apply<true>(a, &op + 1, op.slot, op.cmask_reg, ctx, e);
+                continue;
             }
         }
-        return;
-    } else {
-    // the round's slice of the active mask, bit j = op first + j; dual ops always run
-    uint32_t lo = act[0], hi = 0;
+        // two dispatch trees: the 2x2 routines need nothing but the op's constants; the phase routines share the
+        // DiagCtx address arithmetic, which the compiler would otherwise hoist in front of every op
+        if (code < kCodeDiagBase) {
+#if QSV_PRELOAD
+            double c[8];
+            {
+                const double* src = op.m + ((dual && !sat) ? 8 : 0);
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
-        if ((int)(first >> 5) == w) lo = act[w];
-        if ((int)(first >> 5) + 1 == w) hi = act[w];
-    }
-    const uint32_t sh = first & 31u;
-    const uint32_t sat_m = sh ? ((lo >> sh) | (hi << (32u - sh))) : lo;
-    uint32_t m = sat_m;
-    for (uint32_t j = 0; j < n; ++j)
-        if (ops[first + j].code >= kCodeDualBase) m |= 1u << j;
-    if (n < 32u) m &= (1u << n) - 1u;
-    if (!m) return;
-    uint32_t j = ctz32(m);
-    uint32_t code = ops[first + j].code;
-    while (true) {
-        const DevOp& op = ops[first + j];
-        const bool sat = ((sat_m >> j) & 1u) != 0;
-        m &= m - 1;
-        uint32_t jn = 0, next_code = kCodeNop;
-        if (m) {  // fetch the next op's dispatch code before running this one
-            jn = ctz32(m);
-            next_code = ops[first + jn].code;
+                for (int i = 0; i < 8; ++i) c[i] = src[i];
+            }
+#else
+            const double* c = op.m + ((dual && !sat) ? 8 : 0);
+#endif
+            switch (code) {
+                QSV_MAT_CASES(0, mat_hadamard)
+                QSV_MAT_CASES(1, mat_xswap)
+                QSV_MAT2_CASES(2, mat_real)
+                QSV_MAT2_CASES(3, mat_general)
+                QSV_MAT_CASES(4, mat_antidiag)
+                default: break;
+            }
+        } else {
+            switch (code) {
+                QSV_QFT4_CASE
+                QSV_DIAG_CASES(false)
+                QSV_DIAG_CASES(true)
+                QSV_HD_CASES(false)
+                QSV_HD_CASES(true)
+                default: break;
+            }
         }
-        switch (code) {
-            QSV_MAT_CASES(0, mat_hadamard)
-            QSV_MAT_CASES(1, mat_xswap)
-            QSV_MAT_CASES(2, mat_real)
-            QSV_MAT_CASES(3, mat_general)
-            QSV_MAT_CASES(4, mat_antidiag)
-            QSV_DIAG_CASES(false)
-            QSV_DIAG_CASES(true)
-            QSV_HD_CASES(false)
-            QSV_HD_CASES(true)
-            QSV_QFT4_CASE
-            QSV_DUAL_CASES(0, mat_real)
-            QSV_DUAL_CASES(1, mat_general)
-            default: break;
-        }
-        if (!m) break;
-        j = jn;
-        code = next_code;
-    }
     }
 }
 

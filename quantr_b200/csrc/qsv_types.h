@@ -76,14 +76,17 @@ constexpr int kDiagTblLen = 64;  // lo[32] (thread-index bits 0-4) + hi[32] (bit
 //         adjacent register bits, highest first, whose register-bit phases are the QFT ones (pi/2, pi/4, pi/8).  The
 //         DevOp carries no constants; the DIAG ops of the (3 or 4, DevOp::slot) stages follow it in the op array outside
 //         the round's op range and supply the tile/thread factors (pass_core.h qft4_apply).
-//   DUAL: 62 + general*8 + ctrl*4 + slot: a 2x2 op with two matrices (MatFlags::MAT_DUAL) - m[0..8) where all its controls
-//         hold, m[8..16) everywhere else - of kind REAL (general = 0) or GENERAL; such an op is never skipped
-constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeHdBase = 53, kCodeQft4 = 61, kCodeDualBase = 62, kCodeCount = 78;
+//   DUAL: a REAL or GENERAL MAT code | kCodeDualFlag: a 2x2 op with two matrices (MatFlags::MAT_DUAL) - m[0..8) where all
+//         its controls hold, m[8..16) everywhere else; such an op is never skipped
+constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeHdBase = 53, kCodeQft4 = 61, kCodeCount = 62, kCodeDualFlag = 128;
 enum PassFlags : uint32_t {
     PASS_DIRECT_STORE = 2,  // the last round writes its registers straight to global memory (coalesced: its register bits
                             // exclude the three lowest tile bits)
-    PASS_UNCONDITIONAL = 4  // no op of the pass has a control among the thread or tile-index bits: every thread of every
+    PASS_UNCONDITIONAL = 4, // no op of the pass has a control among the thread or tile-index bits: every thread of every
                             // tile runs the whole op list, so the kernel walks it with uniform (scalar) control flow
+    PASS_WARP_LOCAL = 8     // thread-index bits 5 and 6 map to the same two tile bits in every round and those are
+                            // register bits in none (2^11 tiles, 128-thread groups): between rounds a warp only reads
+                            // what it wrote itself, so a warp barrier replaces the group barrier (plan.cpp emit_pass)
 };
 constexpr int kMaxRoundOps = 32;  // ops per register round (one 32-bit active mask)
 
