@@ -173,7 +173,12 @@ const char* qsv_last_error(const qsv_state* s);
 
 /* key: "tile_bits" (4..13), "low_bits" (contiguous low index bits kept in every
  * tile; 0 = chosen per circuit by the scheduler's cost model), "timing" (0/1: record CUDA-event times in qsv_stats),
- * "fuse" (0: one pass per gate, 1: fused passes). */
+ * "fuse" (0: one pass per gate, 1: fused passes).
+ * Sharded handles with peer-mapped shards (qsv_peer_import): "overlap" (default 1: a global-qubit remap runs slice by
+ * slice on a second stream while the passes before and after it work on the other slices; 0: every remap on its own),
+ * "exchange_slices_log2" (1..3, default 2: 2^k slices), "exchange_sms" (SMs left to the swap kernels while a pass runs
+ * next to them, default 32).  With "timing" set, remaps run on their own so that every step can be timed.
+ * qsv_get_info also answers "overlapped_exchanges": the remaps of the last plan run that were pipelined. */
 int qsv_set_option(qsv_state* s, const char* key, int64_t value);
 int qsv_get_info(const qsv_state* s, const char* key, int64_t* value);
 

@@ -48,15 +48,16 @@ bool pass_uses_tma(const uint8_t* host_blob, uint32_t n_alloc, int sm_count) {
 bool pass_init_supported(const uint8_t* host_blob, uint32_t n_alloc, int sm_count) { return pass_uses_tma(host_blob, n_alloc, sm_count); }
 
 cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, const cplx* ext_tbl, uint64_t rank_hi, uint32_t n_alloc, int sm_count,
-                        const PassInit* init, cudaStream_t stream) {
+                        const PassInit* init, cudaStream_t stream, const PassSlice* slice, int grid_sms) {
     const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
     const uint32_t tile_bits = hdr.tile_bits;
     if (pass_uses_tma(host_blob, n_alloc, sm_count)) {
         const PassInit none{0, 0, 0, 0, 0, 0, 1.0, 0.0};
-        if (tile_bits == 12) return launch_pass_tma_tile<12>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init ? *init : none, stream);
-        return launch_pass_tma_tile<11>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init ? *init : none, stream);
+        if (init && slice && slice->n) return cudaErrorNotSupported;
+        if (tile_bits == 12) return launch_pass_tma_tile<12>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init ? *init : none, stream, slice, grid_sms);
+        return launch_pass_tma_tile<11>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init ? *init : none, stream, slice, grid_sms);
     }
-    if (init) return cudaErrorNotSupported;
+    if (init || (slice && slice->n)) return cudaErrorNotSupported;
     switch (tile_bits) {
         case 10: return launch_pass_tile<10>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
         case 11: return launch_pass_tile<11>(state, dev_blob, host_blob, rank_hi, sm_count, stream);
@@ -151,7 +152,8 @@ cudaError_t launch_gather(const cplx* state, const uint64_t* idx, cplx* out, uin
 // each rank of the pair moves one half of the block, reading the remote half over NVLink and writing its own
 // amplitudes back into the peer's memory with 128-bit loads/stores.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) peer_swap_kernel(cplx* __restrict__ local, cplx* __restrict__ remote, SwapArgs a) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) peer_swap_kernel(cplx* __restrict__ local, cplx* __restrict__ remote, SwapArgs a) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j0 < a.count; j0 += 4 * stride) {
         double2 mine[4], theirs[4];
@@ -172,13 +174,54 @@ __global__ void __launch_bounds__(256) peer_swap_kernel(cplx* __restrict__ local
     }
 }
 
-cudaError_t launch_peer_swap(cplx* local, cplx* remote, uint32_t n_local, const uint8_t* partner, uint32_t g, int rank, int peer, int sm_count, cudaStream_t stream) {
-    const SwapArgs a = make_swap_args(n_local, partner, g, rank, peer);
+// slice != null: the pipelined exchange - one 1024-thread CTA per SM on `sm_count` SMs (a persistent pass kernel owns the
+// others; fat CTAs keep the two grids from sharing an SM, which the pass kernel's register file does not allow anyway)
+cudaError_t launch_peer_swap(cplx* local, cplx* remote, uint32_t n_local, const uint8_t* partner, uint32_t g, int rank, int peer, int sm_count, cudaStream_t stream,
+                             const PassSlice* slice) {
+    const SwapArgs a = make_swap_args(n_local, partner, g, rank, peer, slice ? slice->n : 0u, slice ? slice->bit : nullptr, slice ? slice->value : 0u);
     if (a.count == 0) return cudaSuccess;
+    if (slice && slice->n) {
+        uint64_t grid = (a.count + 1024 * 4 - 1) / (1024 * 4);
+        if (grid > (uint64_t)sm_count) grid = (uint64_t)sm_count;
+        peer_swap_kernel<1024><<<(unsigned)grid, 1024, 0, stream>>>(local, remote, a);
+        return cudaGetLastError();
+    }
     uint64_t grid = (a.count + 256 * 4 - 1) / (256 * 4);
     const uint64_t cap = (uint64_t)sm_count * 8;
     if (grid > cap) grid = cap;
-    peer_swap_kernel<<<(unsigned)grid, 256, 0, stream>>>(local, remote, a);
+    peer_swap_kernel<256><<<(unsigned)grid, 256, 0, stream>>>(local, remote, a);
+    return cudaGetLastError();
+}
+
+// Cross-GPU flags of the pipelined exchange.  A wait that outlasts any legitimate exchange (seconds) traps so that a
+// protocol error surfaces as a launch failure instead of a hung device.
+__global__ void flag_signal_kernel(FlagPeers peers, int world, uint32_t index, uint32_t value) {
+    const int r = (int)threadIdx.x;
+    if (r < world && peers.flags[r]) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.flags[r] + index), "r"(value) : "memory");
+    }
+}
+__global__ void flag_wait_kernel(const uint32_t* __restrict__ local_flags, int world, int rank, uint32_t index, uint32_t value) {
+    const int r = (int)threadIdx.x;
+    if (r < world && r != rank) {
+        const uint32_t* p = local_flags + index + r;
+        for (uint64_t spins = 0;; ++spins) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+            if ((int32_t)(v - value) >= 0) break;
+            __nanosleep(200);
+            if (spins > (1ull << 24)) __trap();
+        }
+    }
+    __threadfence_system();
+}
+cudaError_t launch_flag_signal(const FlagPeers& peers, int world, uint32_t index, uint32_t value, cudaStream_t stream) {
+    flag_signal_kernel<<<1, 32, 0, stream>>>(peers, world, index, value);
+    return cudaGetLastError();
+}
+cudaError_t launch_flag_wait(const uint32_t* local_flags, int world, int rank, uint32_t index, uint32_t value, cudaStream_t stream) {
+    flag_wait_kernel<<<1, 32, 0, stream>>>(local_flags, world, rank, index, value);
     return cudaGetLastError();
 }
 

@@ -6,6 +6,7 @@
 #include <atomic>
 
 #include "qsv_types.h"
+#include "tma_tile.h"
 
 namespace qsv { struct PassInit; }
 
@@ -31,9 +32,11 @@ namespace qsv {
 // host_blob: the pass blob in host memory (its header/rounds/ops travel as kernel parameters);
 // dev_blob: the same blob in device memory (tables, external phase terms, Custom matrices);
 // ext_tbl: the pass's external-phase tables in device memory (launch_build_ext_tables), may be null for passes without;
-// init: null, or the basis state whose initialisation is fused into this pass (the register is not read).
+// init: null, or the basis state whose initialisation is fused into this pass (the register is not read);
+// slice: null, or the part of the register this launch covers (pipelined kernel only, tma_tile.h PassSlice);
+// grid_sms: 0, or the number of SMs the persistent kernel may occupy (the rest is left to a concurrent exchange).
 cudaError_t launch_pass(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, const cplx* ext_tbl, uint64_t rank_hi, uint32_t n_alloc, int sm_count,
-                        const PassInit* init, cudaStream_t stream);
+                        const PassInit* init, cudaStream_t stream, const PassSlice* slice = nullptr, int grid_sms = 0);
 // true when launch_pass sends this pass to the pipelined TMA kernel (large registers whose tile is a tensor-map box)
 bool pass_uses_tma(const uint8_t* host_blob, uint32_t n_alloc, int sm_count);
 // true when launch_pass accepts `init` for this pass
@@ -48,13 +51,22 @@ cudaError_t launch_pass_tile(cplx* state, const uint8_t* dev_blob, const uint8_t
 // defined in pass_kernel_tma.cu for TILE_BITS = 11 and 12: the software-pipelined TMA kernel
 template <int TILE_BITS>
 cudaError_t launch_pass_tma_tile(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, const cplx* ext_tbl, uint64_t rank_hi, uint32_t n_alloc, int sm_count,
-                                 const PassInit& init, cudaStream_t stream);
+                                 const PassInit& init, cudaStream_t stream, const PassSlice* slice, int grid_sms);
 template <int TILE_BITS>
 bool pass_tma_supported_tile(const uint8_t* host_blob, uint32_t n_alloc);
 
 cudaError_t launch_set_amp(cplx* state, uint64_t index, double re, double im, cudaStream_t stream);
 // in-place swap of this rank's block 'spelled' peer with the peer's block 'spelled' rank (peer-mapped memory, NVLink)
-cudaError_t launch_peer_swap(cplx* local, cplx* remote, uint32_t n_local, const uint8_t* partner, uint32_t g, int rank, int peer, int sm_count, cudaStream_t stream);
+// slice: null, or the part of the shard to swap (the blocks' amplitudes whose index bits slice->bit[] spell slice->value)
+cudaError_t launch_peer_swap(cplx* local, cplx* remote, uint32_t n_local, const uint8_t* partner, uint32_t g, int rank, int peer, int sm_count, cudaStream_t stream,
+                             const PassSlice* slice = nullptr);
+// Cross-GPU flags of the pipelined exchange (words in peer-mapped memory): every peer's word `index` is set to `value`
+// (system-scope release) / the kernel returns once the local words index + r, r != rank, are all >= value (acquire).
+struct FlagPeers {
+    uint32_t* flags[16];  // flags[r] = rank r's flag words as mapped here (null for this rank and beyond the world size)
+};
+cudaError_t launch_flag_signal(const FlagPeers& peers, int world, uint32_t index, uint32_t value, cudaStream_t stream);
+cudaError_t launch_flag_wait(const uint32_t* local_flags, int world, int rank, uint32_t index, uint32_t value, cudaStream_t stream);
 cudaError_t launch_gather(const cplx* state, const uint64_t* idx, cplx* out, uint64_t count, cudaStream_t stream);
 // canonical range of a register in a permuted qubit layout; entries held by other ranks come back as zero
 cudaError_t launch_gather_range(const cplx* state, cplx* out, uint64_t first, uint64_t count, const uint8_t* layout, uint32_t n_qubits, uint32_t n_local, uint64_t rank,

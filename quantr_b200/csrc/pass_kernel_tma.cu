@@ -157,13 +157,15 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
     // the index bits right above the tile's 128-byte rows, so the CTA's loads and stores cover kG adjacent rows (512
     // contiguous bytes) at every row position instead of one - measured, DRAM streams 128-byte runs at ~58 % of the
     // copy peak and 256-byte runs at ~90 % (profiles/r02_stream_probe.txt).
-    const uint32_t n_tiles = (uint32_t)P.hdr.n_tiles;
+    // A launch over a slice of the register (tt.slice_n fixed tile-id bits) enumerates the slice's tiles and spreads their
+    // ids around the fixed bits.
+    const uint32_t n_tiles_all = (uint32_t)P.hdr.n_tiles, n_tiles = n_tiles_all >> tt.slice_n;
     const uint32_t ilog = ((uint32_t)diag_mode >> 8) & 7u, imask = (1u << ilog) - 1u;
     const uint32_t n_super = n_tiles >> ilog;
     const uint32_t n_my = (n_super > blockIdx.x ? (n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0) << ilog;
-    auto tile_of = [&](uint32_t k) { return ((blockIdx.x + (k >> ilog) * gridDim.x) << ilog) | (k & imask); };
+    auto tile_of = [&](uint32_t k) { return slice_tile_id(tt, ((blockIdx.x + (k >> ilog) * gridDim.x) << ilog) | (k & imask)); };
     const uint32_t tbl_a_mask = (1u << tt.tbl_a_bits) - 1u;
-    const uint32_t tbl_stride = (tbl_a_mask + 1u) + ((n_tiles + tbl_a_mask) >> tt.tbl_a_bits);  // entries per op: table A then table B
+    const uint32_t tbl_stride = (tbl_a_mask + 1u) + ((n_tiles_all + tbl_a_mask) >> tt.tbl_a_bits);  // entries per op: table A then table B
 
     // warp 0 of the calling group: tile t_id -> buffer `slot` (its use number `use`), its table entries -> the buffer's
     // slot of ext_raw
@@ -430,7 +432,7 @@ constexpr size_t kSmemLimit = (size_t)227 * 1024;
 
 template <int T, int NR, int NO, bool FAST>
 static cudaError_t launch_tma_t(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, const cplx* ext_tbl, uint64_t rank_hi, uint32_t n_alloc, int sm_count,
-                                const PassInit& init, cudaStream_t stream) {
+                                const PassInit& init, cudaStream_t stream, const PassSlice* slice, int grid_sms) {
     using Cfg = TmaCfg<T>;
     static thread_local PassParams<NR, NO> params;  // one staging buffer per host thread (include/qsv.h threading contract)
     if (!fill_params(host_blob, params)) return cudaErrorInvalidValue;
@@ -438,6 +440,7 @@ static cudaError_t launch_tma_t(cplx* state, const uint8_t* dev_blob, const uint
     if (hdr.tile_bits != (uint32_t)T) return cudaErrorInvalidValue;
     TmaTileDesc desc;
     if (!make_tma_tile(hdr, n_alloc, desc)) return cudaErrorInvalidValue;
+    if (!set_tma_slice(hdr, slice, desc.tile) || (desc.tile.slice_n && init.mode)) return cudaErrorInvalidValue;
     desc.tile.n_ext_ops = hdr.n_ext_ops;
     desc.tile.tbl_a_bits = ext_table_low_bits(hdr.n_tiles);
     for (uint32_t o = 0; o < hdr.n_ops; ++o)
@@ -457,11 +460,14 @@ static cudaError_t launch_tma_t(cplx* state, const uint8_t* dev_blob, const uint
     if (err != cudaSuccess) return err;
     // tile interleave (see the kernel): the groups of a CTA take tiles with consecutive ids; QSV_TILE_INTERLEAVE=0 turns it off
     static const int interleave = getenv("QSV_TILE_INTERLEAVE") ? atoi(getenv("QSV_TILE_INTERLEAVE")) : 1;
+    const uint64_t n_tiles = hdr.n_tiles >> desc.tile.slice_n;  // tiles of this launch
     uint32_t ilog = 0;
     if (interleave)
-        while ((1u << (ilog + 1)) <= Cfg::kGroups && (hdr.n_tiles >> (ilog + 1)) >= 1) ++ilog;
-    uint64_t grid = (uint64_t)sm_count;
-    if (grid > (hdr.n_tiles >> ilog)) grid = hdr.n_tiles >> ilog;
+        while ((1u << (ilog + 1)) <= Cfg::kGroups && (n_tiles >> (ilog + 1)) >= 1) ++ilog;
+    for (uint32_t i = 0; i < desc.tile.slice_n; ++i)
+        if (desc.tile.slice_pos[i] < ilog) return cudaErrorInvalidValue;  // the groups' consecutive tile ids must stay inside the slice
+    uint64_t grid = (uint64_t)(grid_sms > 0 && grid_sms < sm_count ? grid_sms : sm_count);
+    if (grid > (n_tiles >> ilog)) grid = n_tiles >> ilog;
     static const int tma_store = getenv("QSV_TMA_STORE") ? atoi(getenv("QSV_TMA_STORE")) : 0;  // developer A/B switch: 1 = no register->global stores
     pass_kernel_tma<T, NR, NO, FAST><<<(unsigned)grid, Cfg::kThreads, smem, stream>>>(map, state, dev_blob, ext_tbl, rank_hi, mode | (tma_store ? 4 : 0) | (int)(ilog << 8), init, desc.tile, params);
     return cudaGetLastError();
@@ -477,16 +483,16 @@ bool pass_tma_supported_tile<QSV_TILE_BITS>(const uint8_t* host_blob, uint32_t n
 
 template <>
 cudaError_t launch_pass_tma_tile<QSV_TILE_BITS>(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, const cplx* ext_tbl, uint64_t rank_hi, uint32_t n_alloc,
-                                                int sm_count, const PassInit& init, cudaStream_t stream) {
+                                                int sm_count, const PassInit& init, cudaStream_t stream, const PassSlice* slice, int grid_sms) {
     const DevPass& hdr = *reinterpret_cast<const DevPass*>(host_blob);
     using Cfg = TmaCfg<QSV_TILE_BITS>;
     const bool small = hdr.n_rounds <= (uint32_t)kSmallRounds && hdr.n_ops <= (uint32_t)kSmallOps;
     const size_t fast_smem = tma_fixed_smem<QSV_TILE_BITS>(hdr) + sizeof(cplx) * Cfg::kGroupThreads * hdr.n_diag;
     static const bool no_fast = getenv("QSV_NO_FAST") != nullptr;  // developer A/B switch
     if (!no_fast && small && (hdr.flags & PASS_UNCONDITIONAL) && fast_smem <= kSmemLimit)
-        return launch_tma_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, true>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream);
-    if (small) return launch_tma_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, false>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream);
-    return launch_tma_t<QSV_TILE_BITS, kMaxRounds, kMaxOps, false>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream);
+        return launch_tma_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, true>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream, slice, grid_sms);
+    if (small) return launch_tma_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, false>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream, slice, grid_sms);
+    return launch_tma_t<QSV_TILE_BITS, kMaxRounds, kMaxOps, false>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream, slice, grid_sms);
 }
 
 }  // namespace qsv

@@ -1246,6 +1246,48 @@ void prefix_amplitudes(const Plan& plan, uint64_t basis_index, std::vector<cplx>
     }
 }
 
+bool plan_overlap_group(const Plan& plan, size_t step, const std::vector<char>& sliceable, uint32_t log2_slices, OverlapGroup& out) {
+    out = OverlapGroup();
+    if (step >= plan.steps.size() || plan.steps[step].kind != PlanStep::EXCHANGE || log2_slices == 0) return false;
+    if (log2_slices > 3) log2_slices = 3;
+    const uint64_t local_mask = (1ull << plan.n_local) - 1ull;
+    auto tile_mask_of = [&](size_t st) {
+        const DevPass& h = *reinterpret_cast<const DevPass*>(plan.passes[plan.steps[st].pass_index].data());
+        uint64_t m = 0;
+        for (uint32_t sgi = 0; sgi < h.n_tile_segs; ++sgi) m |= ((1ull << h.tile_segs[sgi].width) - 1ull) << h.tile_segs[sgi].dst_lo;
+        return m;
+    };
+    uint64_t partners = 0;
+    for (uint8_t b : plan.steps[step].partner_bits) partners |= 1ull << b;
+    const bool has_prev = step > 0 && plan.steps[step - 1].kind == PlanStep::PASS && sliceable[step - 1];
+    const bool has_next = step + 1 < plan.steps.size() && plan.steps[step + 1].kind == PlanStep::PASS && sliceable[step + 1];
+    // candidates, best first: both neighbours sliced, then the one after, then the one before
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const bool use_prev = has_prev && attempt != 1, use_next = has_next && attempt != 2;
+        if ((attempt == 0 && !(has_prev && has_next)) || (!use_prev && !use_next)) continue;
+        uint64_t blocked = partners;
+        if (use_prev) blocked |= tile_mask_of(step - 1);
+        if (use_next) blocked |= tile_mask_of(step + 1);
+        const uint64_t free_bits = local_mask & ~blocked;
+        if ((uint32_t)popcnt(free_bits) < log2_slices) continue;
+        // the highest free bits: slices are as contiguous as the passes allow, and far above the groups' tile interleave
+        uint32_t n = 0;
+        uint8_t picked[3];
+        auto id_pos_ok = [&](size_t st, int b) {  // at least three tile-id bits below the slice bit (kernel: the groups' interleaved tile ids)
+            return popcnt(~tile_mask_of(st) & ((1ull << b) - 1ull)) >= 3;
+        };
+        for (int b = (int)plan.n_local - 1; b >= 6 && n < log2_slices; --b)
+            if (((free_bits >> b) & 1ull) && (!use_prev || id_pos_ok(step - 1, b)) && (!use_next || id_pos_ok(step + 1, b))) picked[n++] = (uint8_t)b;
+        if (n < log2_slices) continue;
+        out.slice_prev = use_prev;
+        out.slice_next = use_next;
+        out.n_bits = n;
+        for (uint32_t i = 0; i < n; ++i) out.bits[i] = picked[n - 1 - i];  // ascending
+        return true;
+    }
+    return false;
+}
+
 std::string describe_plan(const Plan& plan) {
     std::ostringstream os;
     os << "{\"n_qubits\":" << plan.n_qubits << ",\"n_local\":" << plan.n_local << ",\"n_alloc\":" << plan.n_alloc

@@ -99,6 +99,19 @@ std::string describe_plan(const Plan& plan);
 // Without a prefix: 1 on the rank that holds the basis state.
 void prefix_amplitudes(const Plan& plan, uint64_t basis_index, std::vector<cplx>& out);
 
+// Pipelined exchange (state_api.cu run_overlapped): an EXCHANGE step can run slice by slice against the pass before it
+// and the pass after it when some local index bits are neither partner bits of the exchange nor tile bits of those
+// passes: the passes then run once per slice (the amplitudes whose slice bits spell v) and slice v is exchanged while the
+// passes work on other slices.
+struct OverlapGroup {
+    bool slice_prev = false, slice_next = false;  // the neighbouring PASS steps that run slice by slice
+    uint32_t n_bits = 0;                          // log2 of the number of slices
+    uint8_t bits[3] = {0, 0, 0};                  // slice bits (local physical index bits), ascending
+};
+// step: index of an EXCHANGE step; sliceable[i] != 0: the PASS of step i may run over a slice (pipelined kernel, not the
+// fused initialisation, not already part of another group).  log2_slices: 1..3.  False when nothing can overlap.
+bool plan_overlap_group(const Plan& plan, size_t step, const std::vector<char>& sliceable, uint32_t log2_slices, OverlapGroup& out);
+
 void host_sincospi(double x, double* s, double* c);
 
 }  // namespace qsv

@@ -66,6 +66,17 @@ struct qsv_state {
     uint64_t plan_stamp = 0;
     std::vector<double> last_step_ms;  // "timing" option: device time of every step of the last plan run
     std::vector<cplx*> peer_ptr;  // peer-mapped shards (qsv_peer_import); empty = NCCL send/recv exchange
+    // Pipelined exchange (run_overlapped): the remap runs slice by slice on a second stream while the passes next to it
+    // work on the other slices.  Cross-GPU hand-shakes are flag words behind the shard (kFlagBytes after the amplitudes,
+    // so the peers reach them through the same mapping): ready[v][r] = rank r has finished the pass before the remap on
+    // slice v, done[v][r] = rank r has finished writing slice v of this shard; values are the running exchange number.
+    cudaStream_t xstream = nullptr;
+    std::vector<cudaEvent_t> xev;
+    uint32_t xchg_epoch = 0;
+    int overlap = 1;         // option "overlap": 0 = every remap runs on its own between the passes
+    int xchg_sms = 32;       // SMs left to the swap kernels while a pass runs next to them (option "exchange_sms")
+    int xchg_slices_log2 = 2;  // option "exchange_slices_log2": 2^k slices per remap
+    uint64_t n_overlapped = 0;   // remaps of the last plan run that were pipelined
     std::string error;
 };
 
@@ -94,6 +105,9 @@ int set_error(qsv_state* s, int code, const char* fmt, ...) {
         }                                                                                                            \
     } while (0)
 
+constexpr size_t kFlagBytes = 4096;     // 2 x 8 slices x 16 ranks x 4 bytes, rounded up
+constexpr uint32_t kFlagRanks = 16, kFlagDone = 8 * kFlagRanks;
+uint32_t* flag_words(const qsv_state* s, cplx* shard) { return reinterpret_cast<uint32_t*>(shard + (1ull << s->n_alloc)); }
 uint64_t local_len(const qsv_state* s) { return 1ull << s->n_local; }
 uint64_t rank_base(const qsv_state* s) { return (uint64_t)s->rank << s->n_local; }
 
@@ -181,7 +195,7 @@ int create_common(qsv_state** out, uint32_t n_qubits, int device, int rank, int 
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(set_error(nullptr, QSV_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)));
     s->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(set_error(nullptr, QSV_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)));
-    const size_t bytes = sizeof(cplx) << s->n_alloc;
+    const size_t bytes = (sizeof(cplx) << s->n_alloc) + kFlagBytes;  // amplitudes + the exchange flags behind them
     if ((e = cudaMalloc(&s->d_state, bytes)) != cudaSuccess) {
         cudaGetLastError();
         return fail(set_error(nullptr, e == cudaErrorMemoryAllocation ? QSV_ERR_OUT_OF_MEMORY : QSV_ERR_CUDA, "cudaMalloc of %zu bytes for a %u-qubit register: %s", bytes, s->n_local, cudaGetErrorString(e)));
@@ -192,6 +206,11 @@ int create_common(qsv_state** out, uint32_t n_qubits, int device, int rank, int 
         cudaGetLastError();
         return fail(set_error(nullptr, QSV_ERR_OUT_OF_MEMORY, "cudaMalloc of the measurement scratch: %s", cudaGetErrorString(e)));
     }
+    if ((e = cudaMemset(reinterpret_cast<uint8_t*>(s->d_state) + (sizeof(cplx) << s->n_alloc), 0, kFlagBytes)) != cudaSuccess)
+        return fail(set_error(nullptr, QSV_ERR_CUDA, "cudaMemset of the exchange flags: %s", cudaGetErrorString(e)));
+    if (const char* env = getenv("QSV_OVERLAP")) s->overlap = atoi(env) != 0;
+    if (const char* env = getenv("QSV_XCHG_SMS")) s->xchg_sms = atoi(env);
+    if (const char* env = getenv("QSV_XCHG_SLICES_LOG2")) s->xchg_slices_log2 = atoi(env);
     cudaEventCreate(&s->ev0);
     cudaEventCreate(&s->ev1);
     set_layout(s, nullptr);
@@ -271,12 +290,28 @@ int run_exchange(qsv_state* s, const PlanStep& st, double* ms_out) {
     if (!s->peer_ptr.empty()) {
         // peer-memory path: barrier (every rank has finished the passes before the remap), one in-place swap kernel
         // per peer (round-robin pairing), barrier (every peer has finished writing into this shard)
+        static const bool trace_exchange = getenv("QSV_TRACE_EXCHANGE") != nullptr;  // developer aid: barrier / swap / barrier times on stderr
+        cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (trace_exchange) for (auto& e : te) cudaEventCreate(&e);
+        if (trace_exchange) cudaEventRecord(te[0], s->stream);
         if (!shard_barrier(s->comm, err)) return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
+        if (trace_exchange) cudaEventRecord(te[1], s->stream);
         for (int step = 1; step < s->world; ++step) {
             const int peer = s->rank ^ step;
             QSV_CUDA(s, launch_peer_swap(s->d_state, s->peer_ptr[peer], s->n_local, st.partner_bits.data(), g, s->rank, peer, s->sm_count, s->stream));
         }
+        if (trace_exchange) cudaEventRecord(te[2], s->stream);
         if (!shard_barrier(s->comm, err)) return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
+        if (trace_exchange) {
+            cudaEventRecord(te[3], s->stream);
+            cudaEventSynchronize(te[3]);
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, te[0], te[1]);
+            cudaEventElapsedTime(&b, te[1], te[2]);
+            cudaEventElapsedTime(&c, te[2], te[3]);
+            fprintf(stderr, "[qsv] rank %d remap: barrier %.3f ms, swap %.3f ms, barrier %.3f ms\n", s->rank, a, b, c);
+            for (auto& e : te) cudaEventDestroy(e);
+        }
     } else if (!shard_exchange_bits(s->comm, s->d_state, s->n_local, st.partner_bits.data(), g, s->d_staging, s->staging_bytes, err)) {
         return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
     }
@@ -286,6 +321,69 @@ int run_exchange(qsv_state* s, const PlanStep& st, double* ms_out) {
         float ms = 0.f;
         QSV_CUDA(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         if (ms_out) *ms_out += ms;
+    }
+    return QSV_OK;
+}
+
+// One pass step on the handle's stream, whole or over a slice.
+int launch_pass_step(qsv_state* s, const Plan& plan, uint32_t pass_index, const PassInit* init, const PassSlice* slice, int grid_sms) {
+    const uint8_t* dev_pass = static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[pass_index];
+    const cplx* ext_tbl = plan.dev_tbl_offsets[pass_index] == SIZE_MAX
+                              ? nullptr
+                              : reinterpret_cast<const cplx*>(static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_tbl_offsets[pass_index]);
+    QSV_CUDA(s, launch_pass(s->d_state, dev_pass, plan.passes[pass_index].data(), ext_tbl, rank_base(s), s->n_alloc, s->sm_count, init, s->stream, slice, grid_sms));
+    return QSV_OK;
+}
+
+// Pipelined global-qubit remap (peer-memory transport): the shard is cut into 2^k slices along index bits that neither the
+// remap nor the passes next to it touch.  The pass before the remap runs slice by slice on the handle's stream; slice v
+// is exchanged on the second stream as soon as every rank has finished it (flag words in peer memory, no host round
+// trip, no NCCL call); the pass after the remap starts on slice v as soon as every peer has finished writing it.  While
+// both kinds of kernels are in flight the persistent pass kernel leaves `xchg_sms` SMs to the swap kernels (one fat
+// CTA per SM each, so the two grids fit next to each other whatever the launch order).
+//   step: index of the EXCHANGE step; grp: what plan_overlap_group decided.
+int run_overlapped(qsv_state* s, const Plan& plan, size_t step, const OverlapGroup& grp) {
+    const PlanStep& st = plan.steps[step];
+    const uint32_t g = s->n_qubits - s->n_local, n_slices = 1u << grp.n_bits;
+    if (!s->xstream) QSV_CUDA(s, cudaStreamCreateWithFlags(&s->xstream, cudaStreamNonBlocking));
+    while (s->xev.size() < 2 * (size_t)n_slices) {
+        cudaEvent_t ev;
+        QSV_CUDA(s, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        s->xev.push_back(ev);
+    }
+    FlagPeers peers{};
+    for (int r = 0; r < s->world && r < (int)kFlagRanks; ++r) peers.flags[r] = r == s->rank ? nullptr : flag_words(s, s->peer_ptr[r]);
+    const uint32_t* my_flags = flag_words(s, s->d_state);
+    const uint32_t epoch = ++s->xchg_epoch;
+    const int pass_sms = s->sm_count - s->xchg_sms, swap_sms = s->xchg_sms > 4 ? s->xchg_sms - 2 : s->xchg_sms;  // two SMs stay free for the flag kernels
+    PassSlice sl{};
+    sl.n = grp.n_bits;
+    for (uint32_t i = 0; i < grp.n_bits; ++i) sl.bit[i] = grp.bits[i];
+    for (uint32_t v = 0; v < n_slices; ++v) {
+        sl.value = v;
+        if (grp.slice_prev) {
+            int rc = launch_pass_step(s, plan, plan.steps[step - 1].pass_index, nullptr, &sl, v == 0 ? 0 : pass_sms);  // nothing else runs next to slice 0
+            if (rc != QSV_OK) return rc;
+        }
+        if (grp.slice_prev || v == 0) QSV_CUDA(s, cudaEventRecord(s->xev[v], s->stream));
+        QSV_CUDA(s, cudaStreamWaitEvent(s->xstream, s->xev[grp.slice_prev ? v : 0], 0));
+        QSV_CUDA(s, launch_flag_signal(peers, s->world, v * kFlagRanks + (uint32_t)s->rank, epoch, s->xstream));
+        QSV_CUDA(s, launch_flag_wait(my_flags, s->world, s->rank, v * kFlagRanks, epoch, s->xstream));
+        for (int k = 1; k < s->world; ++k) {
+            const int peer = s->rank ^ k;
+            QSV_CUDA(s, launch_peer_swap(s->d_state, s->peer_ptr[peer], s->n_local, st.partner_bits.data(), g, s->rank, peer, swap_sms, s->xstream, &sl));
+        }
+        QSV_CUDA(s, launch_flag_signal(peers, s->world, kFlagDone + v * kFlagRanks + (uint32_t)s->rank, epoch, s->xstream));
+        QSV_CUDA(s, cudaEventRecord(s->xev[n_slices + v], s->xstream));
+    }
+    for (uint32_t v = 0; v < n_slices; ++v) {
+        sl.value = v;
+        QSV_CUDA(s, cudaStreamWaitEvent(s->stream, s->xev[n_slices + v], 0));
+        QSV_CUDA(s, launch_flag_wait(my_flags, s->world, s->rank, kFlagDone + v * kFlagRanks, epoch, s->stream));
+        if (grp.slice_next) {
+            int rc = launch_pass_step(s, plan, plan.steps[step + 1].pass_index, nullptr, &sl, v + 1 == n_slices ? 0 : pass_sms);  // the last slice has the GPU to itself
+            if (rc != QSV_OK) return rc;
+        }
     }
     return QSV_OK;
 }
@@ -337,8 +435,35 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     double pass_ms = 0.0, exch_ms = 0.0;
     uint64_t n_exch = 0;
     s->last_step_ms.clear();
+    // Which remaps run pipelined against their neighbouring passes (peer-memory transport, no per-step timing): decided
+    // left to right; a pass belongs to at most one group.
+    std::vector<OverlapGroup> groups(plan.steps.size());
+    std::vector<char> in_group(plan.steps.size(), 0);  // PASS steps that run inside run_overlapped
+    s->n_overlapped = 0;
+    if (s->overlap && !s->peer_ptr.empty() && !s->timing && !trace_passes && s->world <= (int)kFlagRanks && s->n_alloc == s->n_local) {
+        std::vector<char> sliceable(plan.steps.size(), 0);
+        for (size_t i = 0; i < plan.steps.size(); ++i)
+            sliceable[i] = plan.steps[i].kind == PlanStep::PASS && !(i == 0 && fused_init) &&
+                           pass_uses_tma(plan.passes[plan.steps[i].pass_index].data(), s->n_alloc, s->sm_count);
+        for (size_t i = 0; i < plan.steps.size(); ++i) {
+            if (plan.steps[i].kind != PlanStep::EXCHANGE) continue;
+            OverlapGroup grp;
+            if (!plan_overlap_group(plan, i, sliceable, (uint32_t)s->xchg_slices_log2, grp)) continue;
+            groups[i] = grp;
+            if (grp.slice_prev) in_group[i - 1] = 1, sliceable[i - 1] = 0;
+            if (grp.slice_next) in_group[i + 1] = 1, sliceable[i + 1] = 0;
+        }
+    }
     for (size_t i = 0; i < plan.steps.size(); ++i) {
         const PlanStep& st = plan.steps[i];
+        if (in_group[i]) continue;  // runs slice by slice inside its remap's group
+        if (st.kind == PlanStep::EXCHANGE && groups[i].n_bits) {
+            rc = run_overlapped(s, plan, i, groups[i]);
+            if (rc != QSV_OK) return rc;
+            ++n_exch;
+            ++s->n_overlapped;
+            continue;
+        }
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         const bool timed = (s->timing || trace_passes) && st.kind == PlanStep::PASS;
         if (timed) {
@@ -501,6 +626,14 @@ int qsv_create_sharded(qsv_state** out, uint32_t n_qubits, int device, int rank,
             *out = nullptr;
             return QSV_ERR_NCCL;
         }
+        // NCCL sets its connections up lazily inside the first collective (hundreds of ms): pay for it here, collectively,
+        // instead of inside whichever remap, norm or sample happens to come first
+        if (!shard_barrier(s->comm, err) || cudaStreamSynchronize(s->stream) != cudaSuccess) {
+            set_error(nullptr, QSV_ERR_NCCL, "first collective on the new communicator failed: %s", err.c_str());
+            qsv_destroy(s);
+            *out = nullptr;
+            return QSV_ERR_NCCL;
+        }
         return qsv_init_basis(s, 0);
     } catch (...) {
         return set_error(nullptr, QSV_ERR_INTERNAL, "unexpected exception in qsv_create_sharded");
@@ -565,6 +698,8 @@ int qsv_destroy(qsv_state* s) {
     if (s->d_staging) cudaFree(s->d_staging);
     if (s->d_scratch) cudaFree(s->d_scratch);
     for (auto& e : s->plan_cache) qsv_plan_destroy(e.plan);
+    for (cudaEvent_t ev : s->xev) cudaEventDestroy(ev);
+    if (s->xstream) cudaStreamDestroy(s->xstream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -587,6 +722,14 @@ int qsv_set_option(qsv_state* s, const char* key, int64_t value) {
         s->opt.fuse = value ? 1 : 0;
     } else if (k == "timing") {
         s->timing = value ? 1 : 0;
+    } else if (k == "overlap") {
+        s->overlap = value ? 1 : 0;
+    } else if (k == "exchange_sms") {
+        if (value < 4 || value > s->sm_count / 2) return set_error(s, QSV_ERR_INVALID_ARG, "exchange_sms must be in 4..%d", s->sm_count / 2);
+        s->xchg_sms = (int)value;
+    } else if (k == "exchange_slices_log2") {
+        if (value < 1 || value > 3) return set_error(s, QSV_ERR_INVALID_ARG, "exchange_slices_log2 must be in 1..3");
+        s->xchg_slices_log2 = (int)value;
     } else {
         return set_error(s, QSV_ERR_INVALID_ARG, "unknown option '%s'", key);
     }
@@ -605,6 +748,10 @@ int qsv_get_info(const qsv_state* s, const char* key, int64_t* value) {
     else if (k == "device") *value = s->device;
     else if (k == "rank") *value = s->rank;
     else if (k == "world") *value = s->world;
+    else if (k == "overlap") *value = s->overlap;
+    else if (k == "exchange_sms") *value = s->xchg_sms;
+    else if (k == "exchange_slices_log2") *value = s->xchg_slices_log2;
+    else if (k == "overlapped_exchanges") *value = (int64_t)s->n_overlapped;  // remaps of the last plan run that were pipelined against their neighbouring passes
     else return QSV_ERR_INVALID_ARG;
     return QSV_OK;
 }

@@ -42,7 +42,46 @@ struct TmaTile {
     int32_t box_add[kTmaMaxBoxes]; // added to coordinate last_dim for box j
     uint64_t box_off[kTmaMaxBoxes];// element offset of box j relative to the tile base (host emulation, checks)
     uint8_t ext_diag[kMaxOps];     // DevOp::diag_index of external-phase slot j
+    // A launch may cover only a *slice* of the register: the tiles whose tile-id bits slice_pos[] (ascending) spell
+    // slice_val.  Used to pipeline a pass, slice by slice, against a global-qubit exchange (state_api.cu run_overlapped).
+    uint32_t slice_n;              // 0 = the whole register
+    uint32_t slice_pos[3];
+    uint32_t slice_val;            // the fixed bits, in place
 };
+
+// k-th tile id of a slice: k's bits spread around the fixed positions
+QSV_HD uint32_t slice_tile_id(const TmaTile& t, uint32_t k) {
+    for (uint32_t i = 0; i < t.slice_n; ++i) {
+        const uint32_t p = t.slice_pos[i];
+        k = ((k >> p) << (p + 1u)) | (k & ((1u << p) - 1u));
+    }
+    return k | t.slice_val;
+}
+
+// A slice of the local register: the amplitudes whose index bits `bit[]` (ascending, none of them a tile bit of the
+// pass) spell `value` (bit i of value <-> bit[i]).
+struct PassSlice {
+    uint32_t n;
+    uint8_t bit[3];
+    uint32_t value;
+};
+
+// Fills the slice fields of a TmaTile; false if a slice bit is a tile bit of the pass.
+inline bool set_tma_slice(const DevPass& hdr, const PassSlice* sl, TmaTile& t) {
+    t.slice_n = 0;
+    t.slice_val = 0;
+    if (!sl || sl->n == 0) return true;
+    if (sl->n > 3) return false;
+    for (uint32_t i = 0; i < sl->n; ++i) {
+        const uint64_t id_bit = extract(1ull << sl->bit[i], hdr.ext_segs, hdr.n_ext_segs);  // the tile-id bit this index bit feeds
+        if (id_bit == 0 || (id_bit & (id_bit - 1)) != 0 || (i && sl->bit[i] <= sl->bit[i - 1])) return false;
+        const uint32_t pos = (uint32_t)__builtin_ctzll(id_bit);
+        t.slice_pos[i] = pos;
+        if ((sl->value >> i) & 1u) t.slice_val |= 1u << pos;
+    }
+    t.slice_n = sl->n;
+    return true;
+}
 
 // Host side of the tensor map (arguments of cuTensorMapEncodeTiled, f64 elements).
 struct TmaTileDesc {

@@ -28,7 +28,7 @@ static uint32_t g_tma_passes = 0, g_tma_max_boxes = 0;
 extern "C" uint32_t qsv_emu_tma_passes(void) { return g_tma_passes; }
 extern "C" uint32_t qsv_emu_tma_max_boxes(void) { return g_tma_max_boxes; }
 
-static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const PassInit* init = nullptr, uint32_t n_alloc = 0) {
+static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const PassInit* init = nullptr, uint32_t n_alloc = 0, const PassSlice* slice = nullptr) {
     static PassParams<kMaxRounds, kMaxOps> P;  // what the kernel receives by value
     if (!fill_params(blob, P)) return;
     constexpr int W = kMaxOps / 32;
@@ -91,7 +91,11 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
             });
         }
     };
-    for (uint64_t t = 0; t < P.hdr.n_tiles; ++t) {
+    // a launch over a slice of the register enumerates the slice's tiles exactly as the kernel does (tma_tile.h slice_tile_id)
+    TmaTile slice_tile{};
+    if (!set_tma_slice(P.hdr, slice, slice_tile)) __builtin_trap();
+    for (uint64_t k = 0; k < (P.hdr.n_tiles >> slice_tile.slice_n); ++k) {
+        const uint64_t t = slice_tile_id(slice_tile, (uint32_t)k);
         const uint64_t base = deposit(t, P.hdr.ext_segs, P.hdr.n_ext_segs);
         if (tma && tma_tile_base(desc.tile, (uint32_t)t) != base) __builtin_trap();  // the kernel derives the tile base from the tile id fields
         const uint64_t base_full = base | rank_hi;
@@ -213,14 +217,45 @@ extern "C" int qsv_emu_run_pass(const qsv_plan* p, uint32_t pass_index, double* 
 
 extern "C" uint32_t qsv_emu_alloc_qubits(const qsv_plan* p) { return p ? p->plan.n_alloc : 0; }
 
+// The pipelined exchange (state_api.cu run_overlapped), piece by piece: one pass over one slice of the shard ...
+extern "C" int qsv_emu_run_pass_slice(const qsv_plan* p, uint32_t pass_index, double* amps, uint64_t rank, uint32_t n_slice, const uint8_t* slice_bits, uint32_t value) {
+    if (!p || !amps || pass_index >= p->plan.passes.size() || n_slice > 3) return 1;
+    PassSlice sl{};
+    sl.n = n_slice;
+    for (uint32_t i = 0; i < n_slice; ++i) sl.bit[i] = slice_bits[i];
+    sl.value = value;
+    TmaTile probe{};
+    if (!set_tma_slice(*reinterpret_cast<const DevPass*>(p->plan.passes[pass_index].data()), &sl, probe)) return 2;
+    run_pass(p->plan.passes[pass_index].data(), reinterpret_cast<cplx*>(amps), rank << p->plan.n_local, nullptr, p->plan.n_alloc, &sl);
+    return 0;
+}
+// ... and what plan_overlap_group decides for an EXCHANGE step: out = {slice_prev, slice_next, n_bits, bits[0..2]}; returns 1 if it overlaps
+extern "C" int qsv_emu_overlap_group(const qsv_plan* p, uint32_t step, const uint8_t* sliceable, uint32_t log2_slices, uint32_t* out) {
+    if (!p || !sliceable || !out) return -1;
+    std::vector<char> sl(p->plan.steps.size());
+    for (size_t i = 0; i < sl.size(); ++i) sl[i] = (char)sliceable[i];
+    OverlapGroup g;
+    const bool ok = plan_overlap_group(p->plan, step, sl, log2_slices, g);
+    out[0] = g.slice_prev; out[1] = g.slice_next; out[2] = g.n_bits; out[3] = g.bits[0]; out[4] = g.bits[1]; out[5] = g.bits[2];
+    return ok ? 1 : 0;
+}
+
 // One EXCHANGE step the way the peer-memory path runs it (state_api.cu run_exchange + peer_swap_kernel): every rank,
 // for every step of the round-robin pairing, swaps its half of the pair's blocks in place.  shards[r] = rank r's amplitudes.
+static int peer_exchange(double** shards, uint32_t n_local, const uint8_t* partner, uint32_t g, uint32_t n_slice, const uint8_t* slice_bits, uint32_t value);
 extern "C" int qsv_emu_peer_exchange(double** shards, uint32_t n_local, const uint8_t* partner, uint32_t g) {
+    return peer_exchange(shards, n_local, partner, g, 0, nullptr, 0);
+}
+// one slice of it (the amplitudes whose index bits slice_bits[] spell value)
+extern "C" int qsv_emu_peer_exchange_slice(double** shards, uint32_t n_local, const uint8_t* partner, uint32_t g, uint32_t n_slice, const uint8_t* slice_bits, uint32_t value) {
+    return peer_exchange(shards, n_local, partner, g, n_slice, slice_bits, value);
+}
+static int peer_exchange(double** shards, uint32_t n_local, const uint8_t* partner, uint32_t g, uint32_t n_slice, const uint8_t* slice_bits, uint32_t value) {
     const int world = 1 << g;
     for (int step = 1; step < world; ++step)
         for (int rank = 0; rank < world; ++rank) {
             const int peer = rank ^ step;
-            const SwapArgs a = make_swap_args(n_local, partner, g, rank, peer);
+            const SwapArgs a = make_swap_args(n_local, partner, g, rank, peer, n_slice, slice_bits, value);
             cplx* local = reinterpret_cast<cplx*>(shards[rank]);
             cplx* remote = reinterpret_cast<cplx*>(shards[peer]);
             for (uint64_t j = 0; j < a.count; ++j) {

@@ -313,3 +313,59 @@ def emu_simulate_sharded(n, enc, world, *, basis_index=0, register=None, tile_bi
     phys = physical_index_table(n, lay1)
     out = np.concatenate(shards)[phys]
     return out, plan, n_exchanges
+
+
+def emu_simulate_sharded_overlapped(n, enc, world, *, register, tile_bits=0, low_bits=0, log2_slices=2, rng=None):
+    """emu_simulate_sharded with every EXCHANGE step run the way state_api.cu run_overlapped pipelines it: the shard is cut
+    into slices along bits that neither the remap nor its neighbouring passes touch (plan_overlap_group); the pass
+    before the remap, the remap and the pass after it each run slice by slice - here in a scrambled order that only
+    respects 'a slice is exchanged after every rank has passed it and before any rank passes it again'.
+    Returns (canonical state vector, number of remaps, number of remaps that were pipelined)."""
+    lib = emu_lib()
+    rng = rng or np.random.default_rng(0)
+    g = world.bit_length() - 1
+    nl = n - g
+    plan = qb.Plan(n, enc, n_local=nl, tile_bits=tile_bits, low_bits=low_bits, lib=lib)
+    assert plan.layout(False) == list(range(n))
+    shards = [np.array(register[r << nl:(r + 1) << nl], dtype=np.complex128) for r in range(world)]
+    steps = plan.steps()
+    sliceable = (C.c_uint8 * len(steps))(*[1 if k == "pass" else 0 for k, _ in steps])
+    ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    done = [False] * len(steps)
+    n_exchanges = n_overlapped = 0
+    for i, (kind, arg) in enumerate(steps):
+        if kind == "pass":
+            continue
+        n_exchanges += 1
+        out = (C.c_uint32 * 6)()
+        if lib.qsv_emu_overlap_group(plan.handle, i, sliceable, log2_slices, out) != 1:
+            continue
+        n_overlapped += 1
+        steps[i] = ("group", (arg, bool(out[0]), bool(out[1]), int(out[2]), [int(out[3 + k]) for k in range(out[2])]))
+        if out[0]:
+            done[i - 1], sliceable[i - 1] = True, 0
+        if out[1]:
+            done[i + 1], sliceable[i + 1] = True, 0
+    for i, (kind, arg) in enumerate(steps):
+        if kind == "pass":
+            if not done[i]:
+                for r in range(world):
+                    assert lib.qsv_emu_run_pass(plan.handle, arg, ptr(shards[r]), r) == 0
+        elif kind == "exchange":
+            shards = exchange_bits_global(shards, nl, arg)
+        else:
+            partners, slice_prev, slice_next, nb, bits = arg
+            cbits = (C.c_uint8 * 3)(*(bits + [0] * (3 - nb)))
+            cpart = (C.c_uint8 * len(partners))(*partners)
+            order = [int(v) for v in rng.permutation(1 << nb)]
+            for v in order:  # a fast slice may be exchanged and even passed again before a slow one has been touched
+                if slice_prev:
+                    for r in range(world):
+                        assert lib.qsv_emu_run_pass_slice(plan.handle, steps[i - 1][1], ptr(shards[r]), r, nb, cbits, v) == 0
+                arr = (C.POINTER(C.c_double) * world)(*[ptr(s) for s in shards])
+                assert lib.qsv_emu_peer_exchange_slice(arr, nl, cpart, g, nb, cbits, v) == 0
+                if slice_next:
+                    for r in range(world):
+                        assert lib.qsv_emu_run_pass_slice(plan.handle, steps[i + 1][1], ptr(shards[r]), r, nb, cbits, v) == 0
+    phys = physical_index_table(n, plan.layout(True))
+    return np.concatenate(shards)[phys], n_exchanges, n_overlapped

@@ -84,7 +84,12 @@ def _worker(rank, world, port, result_dir):
     results["rand"] = s2.gather(np.arange(1 << n2, dtype=np.uint64))
     results["rand_exchanges"] = st2["n_exchanges"]
     results["rand_layout_identity"] = s2.layout() == list(range(n2))
-    results["rand_download"] = s2.download(0, 1 << n2)  # remapped layout: collective, un-permuted on the device
+    # remapped layout: qsv_download is collective and un-permutes on the device; canonical layout: every rank reads its shard
+    if results["rand_layout_identity"]:
+        results["rand_download"] = results["rand"]
+        results["rand_download_shard"] = s2.download(rank << nl, 1 << nl) if rank == 0 else np.zeros(1)
+    else:
+        results["rand_download"] = s2.download(0, 1 << n2)
     s2.peer_import([])  # importers unmap their peers before any exporter frees its shard (CUDA IPC teardown order)
     dist.barrier()
     s2.close()
@@ -119,3 +124,77 @@ def test_two_gpu_sharded_register_matches_oracle(tmp_path):
     assert int(out["rand_exchanges"]) >= 1
     assert np.max(np.abs(out["rand"] - ref)) < 1e-12
     assert np.max(np.abs(out["rand_download"] - ref)) < 1e-12
+    if bool(out["rand_layout_identity"]):
+        assert np.max(np.abs(out["rand_download_shard"] - ref[:1 << (n2 - 1)])) < 1e-12
+
+
+def _worker_pipelined(rank, world, port, result_dir):
+    """Random circuit on an uploaded register through peer memory, pipelined TMA kernel forced onto a small register
+    (QSV_ASYNC=2, set by the parent): the remaps run slice by slice against their neighbouring passes."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ctypes as C
+    from quantr_b200 import _ffi as F
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = F.load_library()
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        F.check(lib.qsv_nccl_unique_id(buf, 128))
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    dist.broadcast(t, 0)
+    n = 19
+    rng = np.random.default_rng(4242)
+    c = random_any_gate_circuit(OracleCircuit, G, n, 150, rng)
+    enc = encode_gates(c.circuit_gates, n)
+    reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    reg /= np.linalg.norm(reg)
+    s = qb.DeviceState(n, rank, rank=rank, world=world, nccl_id=bytes(t.numpy().tobytes()))
+    s.set_option("tile_bits", 11)
+    mine = torch.frombuffer(bytearray(s.peer_export()), dtype=torch.uint8).clone()
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    s.peer_import([bytes(h.numpy().tobytes()) for h in allh])
+    nl = n - (world.bit_length() - 1)
+    results = {}
+    for label, overlap, k in (("serial", 0, 2), ("pipelined2", 1, 1), ("pipelined4", 1, 2), ("pipelined8", 1, 3)):
+        s.set_option("overlap", overlap)
+        s.set_option("exchange_slices_log2", k)
+        s.init_basis(0)  # back to the canonical layout: the previous run left the qubits remapped
+        s.upload(reg[rank << nl:(rank + 1) << nl], first=rank << nl)
+        st = s.apply(enc)
+        results[label] = s.gather(np.arange(1 << n, dtype=np.uint64))
+        results[label + "_exchanges"] = st["n_exchanges"]
+        results[label + "_overlapped"] = s.get_info("overlapped_exchanges")
+    s.peer_import([])
+    dist.barrier()
+    s.close()
+    if rank == 0:
+        np.savez(os.path.join(result_dir, "out.npz"), **results)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs")
+def test_two_gpu_pipelined_exchange_matches_oracle(tmp_path, monkeypatch):
+    """north_star: global-qubit swaps over NVLink overlapped with local fused passes (state_api.cu run_overlapped)."""
+    import torch.multiprocessing as mp
+    monkeypatch.setenv("QSV_ASYNC", "2")
+    world = 2
+    port = 31700 + (os.getpid() % 2000)
+    mp.spawn(_worker_pipelined, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    out = np.load(tmp_path / "out.npz")
+    n = 19
+    rng = np.random.default_rng(4242)
+    c = random_any_gate_circuit(OracleCircuit, G, n, 150, rng)
+    enc = encode_gates(c.circuit_gates, n)
+    reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    reg /= np.linalg.norm(reg)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense", threads=4)
+    assert int(out["serial_exchanges"]) >= 1 and int(out["serial_overlapped"]) == 0
+    assert np.max(np.abs(out["serial"] - ref)) < 1e-12
+    for label in ("pipelined2", "pipelined4", "pipelined8"):
+        assert int(out[label + "_overlapped"]) >= 1, label
+        assert np.max(np.abs(out[label] - ref)) < 1e-12, label

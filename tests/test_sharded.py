@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import pytest
 
-from helpers import (OracleCircuit, emu_lib, emu_simulate_sharded, encode_gates, orc, qb, qft_circuit, qft_expected,
+from helpers import (OracleCircuit, emu_lib, emu_simulate_sharded, emu_simulate_sharded_overlapped, encode_gates, orc, qb, qft_circuit, qft_expected,
                      random_any_gate_circuit, random_layered_circuit)
 from quantr_b200 import _ffi as F
 
@@ -229,3 +229,27 @@ def test_grover_from_native_gates_sharded(n, world, iterations):
     out, plan, n_exchanges = emu_simulate_sharded(n, enc, world, tile_bits=6, low_bits=3)
     assert np.max(np.abs(out - ref)) < 1e-12
     assert n_exchanges >= 2
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_pipelined_exchange_slices_match_oracle(seed):
+    """The pipelined remap (state_api.cu run_overlapped; north_star: global-qubit swaps overlapped with local fused
+    passes): the pass before a remap, the remap and the pass after it run slice by slice along index bits none of the three
+    touches.  Emulated here with the product's own slice enumeration (tma_tile.h slice_tile_id), swap index arithmetic
+    (peer_swap.h) and group decision (plan.cpp plan_overlap_group), slices in a scrambled order."""
+    rng = np.random.default_rng(100 + seed)
+    world = [2, 4, 8][seed % 3]
+    g = world.bit_length() - 1
+    n = 13 + g + seed % 2
+    c = random_any_gate_circuit(OracleCircuit, G, n, 90, rng)
+    enc = encode_gates(c.circuit_gates, n)
+    reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    reg /= np.linalg.norm(reg)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense", threads=4)
+    total = pipelined = 0
+    for tile_bits, low_bits, k in [(6, 2, 1), (7, 3, 2), (6, 3, 3)]:
+        out, n_exch, n_over = emu_simulate_sharded_overlapped(n, enc, world, register=reg, tile_bits=tile_bits, low_bits=low_bits, log2_slices=k, rng=rng)
+        assert np.max(np.abs(out - ref)) < 1e-12, (world, n, tile_bits, low_bits, k)
+        total += n_exch
+        pipelined += n_over
+    assert total > 0 and pipelined > 0
