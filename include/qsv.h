@@ -151,6 +151,17 @@ int qsv_create_sharded(qsv_state** out, uint32_t n_qubits, int device, int rank,
                        const void* nccl_unique_id, size_t nccl_unique_id_bytes);
 int qsv_nccl_unique_id(void* out, size_t out_bytes);
 
+/* In-library multi-GPU ("single-process, multi-device inside the library, invisible to the caller"; the
+ * reference's Circuit::simulate has no notion of devices, src/circuit.rs:364-388): ONE handle for a register sharded
+ * over n_devices GPUs of this process (a power of two, at most 16; the devices must reach each other's memory).  Every
+ * call below works on it as on a single-GPU handle - qsv_upload / qsv_download / qsv_gather take any range of the
+ * register, qsv_apply runs the circuit on all devices with the global-qubit remaps going over NVLink peer memory,
+ * qsv_sample / qsv_norm_sqr see the whole register, qsv_save / qsv_load use one file per shard (<path>.r<k>).  Not
+ * available on it: qsv_run_plan (a plan object lives on one device; qsv_apply caches its plans per shard),
+ * qsv_device_pointer, qsv_peer_export / qsv_peer_import.  Inside, the library keeps one sharded handle and one host thread
+ * per device.  n_devices = 1 is qsv_create.  qsv_get_info "devices" returns the number of GPUs behind a handle. */
+int qsv_create_multi(qsv_state** out, uint32_t n_qubits, const int* devices, int n_devices);
+
 /* Optional, sharded handles: direct NVLink exchange.  Every rank exports an opaque 64-byte handle of its shard
  * (qsv_peer_export), the caller all-gathers them, and every rank imports the table (qsv_peer_import: `handles` holds
  * world x 64 bytes, entry r = rank r's export).  Afterwards global-qubit remaps swap amplitudes in place through

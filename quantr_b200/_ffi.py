@@ -83,6 +83,7 @@ def load_library():
     sigs = {
         "qsv_create": [C.POINTER(vp), u32, i32],
         "qsv_create_sharded": [C.POINTER(vp), u32, i32, i32, i32, vp, sz],
+        "qsv_create_multi": [C.POINTER(vp), u32, C.POINTER(i32), i32],
         "qsv_nccl_unique_id": [vp, sz],
         "qsv_peer_export": [vp, vp, sz],
         "qsv_peer_import": [vp, vp, sz],
@@ -126,7 +127,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "qsv_create", "qsv_create_sharded", "qsv_nccl_unique_id", "qsv_peer_export", "qsv_peer_import", "qsv_destroy", "qsv_last_error", "qsv_set_option",
+    "qsv_create", "qsv_create_sharded", "qsv_create_multi", "qsv_nccl_unique_id", "qsv_peer_export", "qsv_peer_import", "qsv_destroy", "qsv_last_error", "qsv_set_option",
     "qsv_get_info", "qsv_init_basis", "qsv_upload", "qsv_download", "qsv_gather", "qsv_apply", "qsv_plan_create",
     "qsv_plan_create_ex", "qsv_plan_num_steps", "qsv_plan_get_step", "qsv_plan_get_layout", "qsv_get_layout",
     "qsv_plan_destroy", "qsv_plan_initial_amplitudes", "qsv_plan_stats", "qsv_plan_serialize", "qsv_plan_last_error", "qsv_run_plan", "qsv_sample",

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import struct
 import sys
 
 import numpy as np
@@ -63,6 +64,17 @@ class EncodedOps:
     @property
     def nbytes(self) -> int:
         return C.sizeof(self.ops) + sum(getattr(k, "nbytes", 0) for k in self.keep)
+
+    def signature(self) -> bytes:
+        """Everything the device will see, as bytes: two encodings with equal signatures give the same register."""
+        parts = []
+        for i in range(self.n_ops):
+            op = self.ops[i]
+            parts.append(struct.pack("<IIIdq", op.kind, op.target, op.n_controls, op.param, op.iparam))
+            if op.n_controls:
+                parts.append(bytes(C.cast(op.controls, C.POINTER(C.c_uint32 * op.n_controls)).contents))
+        parts.extend(k.tobytes() for k in self.keep if isinstance(k, np.ndarray))
+        return b"".join(parts)
 
 
 COMPACT_CUSTOM_WIRES = 11  # Custom gates on more wires are passed as the columns of their non-None sub-states only
@@ -160,15 +172,34 @@ def default_device() -> int:
     return int(os.environ.get("QSV_DEVICE", os.environ.get("LOCAL_RANK", "0")))
 
 
+def default_devices(n_qubits: int):
+    """QSV_DEVICES=0,1,2,3 spreads every register of a Circuit::simulate over these GPUs of the process (a power of two;
+    registers too small to shard - fewer than 4 qubits per device - stay on the first one).  Unset: one GPU."""
+    env = os.environ.get("QSV_DEVICES")
+    if not env:
+        return None
+    devs = [int(x) for x in env.split(",") if x.strip() != ""]
+    while len(devs) > 1 and n_qubits - (len(devs).bit_length() - 1) < 4:
+        devs = devs[:len(devs) // 2]
+    return devs if len(devs) > 1 else None
+
+
 class DeviceState:
     """Owns a `qsv_state*` (freed on drop, like the Rust shim's `Drop`)."""
 
-    def __init__(self, n_qubits: int, device: int | None = None, *, rank: int = 0, world: int = 1, nccl_id: bytes | None = None):
+    def __init__(self, n_qubits: int, device: int | None = None, *, rank: int = 0, world: int = 1, nccl_id: bytes | None = None,
+                 devices: list | None = None):
         self.lib = F.load_library()
         self.n_qubits = n_qubits
         self.handle = C.c_void_p()
+        if devices is None and device is None and world == 1:
+            devices = default_devices(n_qubits)
         dev = default_device() if device is None else device
-        if world > 1:
+        if devices is not None and len(devices) > 1:
+            # in-library multi-GPU: one handle, the register sharded over `devices` inside libqsv.so (include/qsv.h qsv_create_multi)
+            arr = (C.c_int32 * len(devices))(*devices)
+            code = self.lib.qsv_create_multi(C.byref(self.handle), n_qubits, arr, len(devices))
+        elif world > 1:
             buf = C.create_string_buffer(nccl_id, len(nccl_id))
             code = self.lib.qsv_create_sharded(C.byref(self.handle), n_qubits, dev, rank, world, buf, len(nccl_id))
         else:
@@ -466,7 +497,9 @@ class Circuit:
         else:
             state.upload(register.get_amplitudes())
         stats = state.apply(enc)
-        return SimulatedCircuit(gates, self.num_qubits, state, self.config_progress, stats)
+        sim = SimulatedCircuit(gates, self.num_qubits, state, self.config_progress, stats)
+        sim._register_origin = (register is None, enc.signature())
+        return sim
 
     def simulate(self) -> "SimulatedCircuit":  # circuit.rs:364-388 (consumes the circuit)
         register, self.register = self.register, None
@@ -488,6 +521,8 @@ class SimulatedCircuit:
         self.stats = stats or {}
         self._state = state
         self._host: SuperPosition | None = None
+        self._register_origin = None  # (register was |0>, EncodedOps.signature()) of the simulation that filled the register
+        self.resimulated_shots = 0    # shots of measure_all_without_cache that had to run the circuit again
 
     def _bin_samples(self, indices, bin_count):
         for idx in indices:
@@ -519,13 +554,22 @@ class SimulatedCircuit:
         self._bin_samples(self._state.sample(_rng.random(1)), bin_count)
         if self.config_progress:
             print(f"Measured state # 1/{shots}")
+        # what produced the register now in HBM: (started from |0>, signature of the ops).  A shot whose freshly encoded ops
+        # (Custom closures are evaluated again per shot, as upstream does) are byte-identical to those, applied to |0> again,
+        # would rebuild the very same register - it is measured without re-running the passes.  Closures that differ
+        # from shot to shot (the mixed-state use case upstream documents) re-simulate as before.
+        current = self._register_origin
         for i in range(shots - 1):
             if self.config_progress:
                 print("Register reset to zero state")
             enc = encode_gates(self.circuit_gates, self.num_qubits)  # Custom closures are evaluated again per shot
-            self._state.init_basis(0)
-            self._state.apply(enc)
-            self._host = None
+            origin = (True, enc.signature())
+            if origin != current:
+                self._state.init_basis(0)
+                self._state.apply(enc)
+                self._host = None
+                current = self._register_origin = origin
+                self.resimulated_shots += 1
             self._bin_samples(self._state.sample(_rng.random(1)), bin_count)
             if self.config_progress:
                 print(f"Measured state # {i + 2}/{shots}")

@@ -149,7 +149,6 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
     const double final_scale = P.hdr.final_scale;
     const bool last_is_reg = n_rounds && P.rounds[n_rounds - 1].type == ROUND_REG;
     const bool direct = (P.hdr.flags & PASS_DIRECT_STORE) != 0 && !(diag_mode & 4) && last_is_reg;
-    const bool warp_local = (P.hdr.flags & PASS_WARP_LOCAL) != 0 && T == 11 && !(diag_mode & 8);
     const bool need_base = direct || (P.hdr.ext_ctrl_mask[0] | P.hdr.ext_ctrl_mask[1] | P.hdr.ext_ctrl_mask[2]) != 0 || init.mode != 0;
     // Tiles of this CTA (tile ids and per-CTA counts fit 32 bits): the k-th tile it works on is
     //   t_k = ((blockIdx.x + (k >> ilog) * gridDim.x) << ilog) | (k & (2^ilog - 1)),   k < n_my.
@@ -350,9 +349,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
             }
             if (!(direct && last)) {
                 if (last) fence_proxy_async();  // the bulk store below reads what this thread wrote
-                // between two register rounds of a warp-local pass a warp reads only what it wrote itself
-                if (warp_local && !last && P.rounds[r + 1].type == ROUND_REG) __syncwarp();
-                else group_barrier(group, kGT);
+                group_barrier(group, kGT);
             }
         }
         if (!direct && gtid < 32u) {

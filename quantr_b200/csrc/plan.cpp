@@ -530,37 +530,6 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
                     }
         return false;
     };
-    // Warp-local rounds (PASS_WARP_LOCAL): two tile bits that are register bits in no round of the pass (passenger bits)
-    // become the warp-index bits of every round's thread mapping (thread-index bits 5 and 6 of a 128-thread compute
-    // group).  A warp then reads in round r + 1 only what it wrote itself in round r, and the pipelined kernel replaces the
-    // group barrier between rounds by a warp barrier.  The pair is chosen so that no round loses its conflict-free lane
-    // bits and a coalesced direct store keeps tile bits 0-2 on the lanes; highest positions first.
-    int warp_bits[2] = {-1, -1};
-    if (plan.opt.fuse && plan.opt.warp_local && T == 11 && kRegBits == 4 && pb.rounds.size() > 1) {
-        uint32_t used = 0;
-        bool ok = true;
-        for (size_t r = 0; r < pb.rounds.size(); ++r) {
-            ok &= !pb.rounds[r].dense;
-            for (int lp : round_regs[r]) used |= 1u << lp;
-        }
-        bool direct_possible = ok && plan.opt.direct_store;
-        if (ok) for (int lp : round_regs.back()) direct_possible &= lp >= 3;
-        for (int hi = T - 1; hi >= 1 && ok && warp_bits[0] < 0; --hi)
-            for (int lo = hi - 1; lo >= 0 && warp_bits[0] < 0; --lo) {
-                if (((used >> hi) | (used >> lo)) & 1u) continue;
-                if (direct_possible && lo < 3) continue;
-                const uint32_t excl = (1u << hi) | (1u << lo);
-                bool fine = true;
-                for (size_t r = 0; r < pb.rounds.size() && fine; ++r) {
-                    int p0[3], p1[3];
-                    if (pick_lane_bits(round_regs[r], 0u, p0)) fine = pick_lane_bits(round_regs[r], excl, p1);
-                }
-                if (fine) { warp_bits[0] = lo; warp_bits[1] = hi; }
-            }
-    }
-    bool warp_local = warp_bits[0] >= 0;
-    const uint32_t warp_excl = warp_local ? ((1u << warp_bits[0]) | (1u << warp_bits[1])) : 0u;
-
     size_t round_index = 0;
     for (const RoundB& rb : pb.rounds) {
         const std::vector<int>& reg_local_pre = round_regs[round_index++];
@@ -610,16 +579,14 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
         for (int j = 0; j < kRegBits; ++j) { dr.reg_pos[j] = (uint8_t)reg_local[j]; slot_of[reg_local[j]] = j; }
         for (int lp = 0; lp < T; ++lp)
             if (slot_of[lp] < 0) thr_local.push_back(lp);
-        {   // thread order: conflict-free lane bits first (pick_lane_bits), the warp-index bits of a warp-local pass last
+        {   // thread order: conflict-free lane bits first (pick_lane_bits)
             int pick[3] = {-1, -1, -1};
-            const bool picked = pick_lane_bits(reg_local, warp_excl, pick);
-            std::vector<int> ordered;
-            if (picked) ordered.assign(pick, pick + 3);
-            for (int lp : thr_local)
-                if (!(picked && (lp == pick[0] || lp == pick[1] || lp == pick[2])) && !((warp_excl >> lp) & 1u)) ordered.push_back(lp);
-            if (warp_local) { ordered.push_back(warp_bits[0]); ordered.push_back(warp_bits[1]); }
-            if (runs_to_segs_ordered(ordered).size() <= (size_t)kMaxThrSegs) thr_local.swap(ordered);
-            else if (warp_local) fail("internal: warp-local thread order needs too many segments");
+            if (pick_lane_bits(reg_local, 0u, pick)) {
+                std::vector<int> ordered(pick, pick + 3);
+                for (int lp : thr_local)
+                    if (lp != pick[0] && lp != pick[1] && lp != pick[2]) ordered.push_back(lp);
+                if (runs_to_segs_ordered(ordered).size() <= (size_t)kMaxThrSegs) thr_local.swap(ordered);
+            }
         }
         for (size_t i = 0; i < thr_local.size(); ++i) thr_index[thr_local[i]] = (int)i;
         auto thsegs = runs_to_segs_ordered(thr_local);
@@ -804,7 +771,6 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
     bool conditional = false;
     for (const DevOp& d : ops) conditional |= d.cmask_thr != 0 || d.cmask_ext != 0;
     if (!conditional) hdr.flags |= PASS_UNCONDITIONAL;
-    if (warp_local) hdr.flags |= PASS_WARP_LOCAL;
     for (const DevOp& d : ops) if (d.type == OP_DIAG && d.n_ext > hdr.max_ext) hdr.max_ext = d.n_ext;
     hdr.n_rounds = (uint32_t)rounds.size();
     hdr.n_ops = (uint32_t)ops.size();

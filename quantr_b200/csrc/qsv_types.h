@@ -82,11 +82,8 @@ constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeHdBa
 enum PassFlags : uint32_t {
     PASS_DIRECT_STORE = 2,  // the last round writes its registers straight to global memory (coalesced: its register bits
                             // exclude the three lowest tile bits)
-    PASS_UNCONDITIONAL = 4, // no op of the pass has a control among the thread or tile-index bits: every thread of every
+    PASS_UNCONDITIONAL = 4  // no op of the pass has a control among the thread or tile-index bits: every thread of every
                             // tile runs the whole op list, so the kernel walks it with uniform (scalar) control flow
-    PASS_WARP_LOCAL = 8     // thread-index bits 5 and 6 map to the same two tile bits in every round and those are
-                            // register bits in none (2^11 tiles, 128-thread groups): between rounds a warp only reads
-                            // what it wrote itself, so a warp barrier replaces the group barrier (plan.cpp emit_pass)
 };
 constexpr int kMaxRoundOps = 32;  // ops per register round (one 32-bit active mask)
 

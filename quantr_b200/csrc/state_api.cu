@@ -9,9 +9,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -77,6 +82,11 @@ struct qsv_state {
     int xchg_sms = 32;       // SMs left to the swap kernels while a pass runs next to them (option "exchange_sms")
     int xchg_slices_log2 = 2;  // option "exchange_slices_log2": 2^k slices per remap
     uint64_t n_overlapped = 0;   // remaps of the last plan run that were pipelined
+    bool peers_local = false;    // peer_ptr holds plain device pointers of this process (qsv_create_multi), not IPC mappings
+    // In-library multi-GPU (qsv_create_multi): this handle is a front for one sharded handle per device, each driven by its
+    // own host thread of `pool`; every call is forwarded to all of them (see the "multi" section below).
+    std::vector<qsv_state*> children;
+    struct MultiPool* pool = nullptr;
     std::string error;
 };
 
@@ -593,6 +603,106 @@ bool plan_cache_key(const qsv_state* s, const qsv_op* ops, size_t n_ops, bool fr
 
 }  // namespace
 
+// ---- in-library multi-GPU ("multi" handles) -------------------------------------------------------------------------
+// "single-process, multi-device inside the library, invisible to the caller".  qsv_create_multi builds one
+// sharded handle per device (rank r on devices[r], same NCCL communicator, shards mapped into each other by plain peer
+// access) and a host thread per device; every call on the front handle runs on all of them at once - exactly what one
+// process per GPU would do, so the sharded code paths above (remaps, collectives) are used unchanged.
+struct MultiPool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    std::function<int(int)> job;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+    std::vector<int> rc;
+
+    explicit MultiPool(int n) : rc((size_t)n, QSV_OK) {
+        for (int r = 0; r < n; ++r) threads.emplace_back([this, r] { loop(r); });
+    }
+    ~MultiPool() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto& t : threads) t.join();
+    }
+    void loop(int r) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<int(int)> f;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_work.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+                f = job;
+            }
+            int code;
+            try {
+                code = f(r);
+            } catch (...) {
+                code = QSV_ERR_INTERNAL;
+            }
+            {
+                std::lock_guard<std::mutex> lk(m);
+                rc[(size_t)r] = code;
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    // runs f(rank) on every worker at the same time; returns the first failing rank's code and its index
+    int run(const std::function<int(int)>& f, int* failed = nullptr) {
+        std::unique_lock<std::mutex> lk(m);
+        job = f;
+        pending = (int)threads.size();
+        ++generation;
+        cv_work.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+        for (size_t r = 0; r < rc.size(); ++r)
+            if (rc[r] != QSV_OK) {
+                if (failed) *failed = (int)r;
+                return rc[r];
+            }
+        return QSV_OK;
+    }
+};
+
+namespace {
+
+bool is_multi(const qsv_state* s) { return s && !s->children.empty(); }
+
+// forwards a call to every child; the front handle takes over the failing child's message
+int multi_run(qsv_state* s, const std::function<int(int)>& f) {
+    int failed = -1;
+    const int rc = s->pool->run(f, &failed);
+    if (rc != QSV_OK && failed >= 0) set_error(s, rc, "device %d: %s", s->children[(size_t)failed]->device, s->children[(size_t)failed]->error.c_str());
+    return rc;
+}
+
+// maps the siblings' shards into child `s` (same process: plain peer access, no IPC handles)
+int attach_local_peers(qsv_state* s, const std::vector<qsv_state*>& all) {
+    QSV_CUDA(s, cudaSetDevice(s->device));
+    std::vector<cplx*> ptrs(all.size(), nullptr);
+    for (size_t r = 0; r < all.size(); ++r) {
+        ptrs[r] = all[r]->d_state;
+        if ((int)r == s->rank) continue;
+        int can = 0;
+        QSV_CUDA(s, cudaDeviceCanAccessPeer(&can, s->device, all[r]->device));
+        if (!can) return set_error(s, QSV_ERR_UNSUPPORTED, "device %d cannot access device %d's memory", s->device, all[r]->device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(all[r]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return set_error(s, QSV_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", all[r]->device, cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    s->peer_ptr.swap(ptrs);
+    s->peers_local = true;
+    return QSV_OK;
+}
+
+}  // namespace
+
 #define QSV_ENTER(s)                                                          \
     if (!(s)) return set_error(nullptr, QSV_ERR_INVALID_ARG, "handle is NULL"); \
     {                                                                         \
@@ -646,7 +756,58 @@ int qsv_nccl_unique_id(void* out, size_t out_bytes) {
     return QSV_OK;
 }
 
+int qsv_create_multi(qsv_state** out, uint32_t n_qubits, const int* devices, int n_devices) {
+    if (!out) return set_error(nullptr, QSV_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (!devices || n_devices < 1) return set_error(nullptr, QSV_ERR_INVALID_ARG, "qsv_create_multi needs at least one device");
+    if (n_devices == 1) return qsv_create(out, n_qubits, devices[0]);
+    try {
+        uint32_t g = 0;
+        while ((1 << g) < n_devices) ++g;
+        if ((1 << g) != n_devices || n_devices > 16) return set_error(nullptr, QSV_ERR_INVALID_ARG, "the number of devices must be a power of two (at most 16)");
+        for (int a = 0; a < n_devices; ++a)
+            for (int b = a + 1; b < n_devices; ++b)
+                if (devices[a] == devices[b]) return set_error(nullptr, QSV_ERR_INVALID_ARG, "device %d is listed twice", devices[a]);
+        uint8_t id[128];
+        std::string err;
+        if (!shard_unique_id(id, sizeof(id), err)) return set_error(nullptr, QSV_ERR_NCCL, "%s", err.c_str());
+        qsv_state* front = new qsv_state();
+        front->n_qubits = n_qubits;
+        front->n_local = n_qubits > g ? n_qubits - g : 0;
+        front->n_alloc = front->n_local;
+        front->world = n_devices;
+        front->device = devices[0];
+        front->children.assign((size_t)n_devices, nullptr);
+        front->pool = new MultiPool(n_devices);
+        std::vector<std::string> msgs((size_t)n_devices);
+        int failed = -1;
+        int rc = front->pool->run([&](int r) {  // collective: the ranks of one NCCL communicator, created side by side
+            qsv_state* c = nullptr;
+            const int code = qsv_create_sharded(&c, n_qubits, devices[r], r, n_devices, id, sizeof(id));
+            front->children[(size_t)r] = c;
+            if (code != QSV_OK) msgs[(size_t)r] = qsv_last_error(nullptr);
+            return code;
+        }, &failed);
+        if (rc == QSV_OK)
+            rc = front->pool->run([&](int r) {
+                const int code = attach_local_peers(front->children[(size_t)r], front->children);
+                if (code != QSV_OK) msgs[(size_t)r] = front->children[(size_t)r]->error;
+                return code;
+            }, &failed);
+        if (rc != QSV_OK) {
+            const std::string msg = failed >= 0 ? msgs[(size_t)failed] : std::string("unknown error");
+            qsv_destroy(front);
+            return set_error(nullptr, rc, "device %d: %s", failed >= 0 ? devices[failed] : -1, msg.c_str());
+        }
+        *out = front;
+        return QSV_OK;
+    } catch (...) {
+        return set_error(nullptr, QSV_ERR_INTERNAL, "unexpected exception in qsv_create_multi");
+    }
+}
+
 int qsv_peer_export(qsv_state* s, void* out_handle, size_t out_bytes) {
+    if (is_multi(s)) return set_error(s, QSV_ERR_INVALID_ARG, "a multi-device handle maps its shards itself");
     QSV_ENTER(s);
     if (!out_handle || out_bytes < sizeof(cudaIpcMemHandle_t)) return set_error(s, QSV_ERR_INVALID_ARG, "handle buffer must hold %zu bytes", sizeof(cudaIpcMemHandle_t));
     cudaIpcMemHandle_t h;
@@ -656,6 +817,7 @@ int qsv_peer_export(qsv_state* s, void* out_handle, size_t out_bytes) {
 }
 
 int qsv_peer_import(qsv_state* s, const void* handles, size_t n_handles) {
+    if (is_multi(s)) return set_error(s, QSV_ERR_INVALID_ARG, "a multi-device handle maps its shards itself");
     QSV_ENTER(s);
     if (!s->comm) return set_error(s, QSV_ERR_INVALID_ARG, "peer import needs a sharded handle");
     if (n_handles == 0) {  // drop the peer mappings: remaps go through NCCL send/recv again
@@ -687,10 +849,26 @@ int qsv_peer_import(qsv_state* s, const void* handles, size_t n_handles) {
 
 int qsv_destroy(qsv_state* s) {
     if (!s) return QSV_OK;
+    if (s->pool) {  // multi-device front: every shard stops being used by its siblings before any of them is freed
+        s->pool->run([&](int r) {
+            qsv_state* c = s->children[(size_t)r];
+            if (!c) return (int)QSV_OK;
+            cudaSetDevice(c->device);
+            cudaStreamSynchronize(c->stream);
+            if (c->xstream) cudaStreamSynchronize(c->xstream);
+            c->peer_ptr.clear();
+            return (int)QSV_OK;
+        });
+        s->pool->run([&](int r) { return qsv_destroy(s->children[(size_t)r]); });
+        delete s->pool;
+        delete s;
+        return QSV_OK;
+    }
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    for (int r = 0; r < (int)s->peer_ptr.size(); ++r)
-        if (r != s->rank && s->peer_ptr[r]) cudaIpcCloseMemHandle(s->peer_ptr[r]);
+    if (!s->peers_local)
+        for (int r = 0; r < (int)s->peer_ptr.size(); ++r)
+            if (r != s->rank && s->peer_ptr[r]) cudaIpcCloseMemHandle(s->peer_ptr[r]);
     if (s->comm) shard_comm_destroy(s->comm);
     if (s->d_state) cudaFree(s->d_state);
     if (s->d_sums) cudaFree(s->d_sums);
@@ -711,6 +889,13 @@ const char* qsv_last_error(const qsv_state* s) { return s ? s->error.c_str() : g
 
 int qsv_set_option(qsv_state* s, const char* key, int64_t value) {
     if (!s || !key) return set_error(s, QSV_ERR_INVALID_ARG, "NULL argument");
+    if (is_multi(s)) {
+        for (qsv_state* c : s->children) {
+            const int rc = qsv_set_option(c, key, value);
+            if (rc != QSV_OK) return set_error(s, rc, "%s", c->error.c_str());
+        }
+        return QSV_OK;
+    }
     const std::string k(key);
     if (k == "tile_bits") {
         if (value < kRegBits || value > kMaxTileBits) return set_error(s, QSV_ERR_INVALID_ARG, "tile_bits must be in %d..%d", kRegBits, kMaxTileBits);
@@ -739,6 +924,12 @@ int qsv_set_option(qsv_state* s, const char* key, int64_t value) {
 int qsv_get_info(const qsv_state* s, const char* key, int64_t* value) {
     if (!s || !key || !value) return set_error(nullptr, QSV_ERR_INVALID_ARG, "NULL argument");
     const std::string k(key);
+    if (k == "devices") { *value = is_multi(s) ? (int64_t)s->children.size() : 1; return QSV_OK; }  // GPUs behind this handle
+    if (is_multi(s)) {  // the front of a multi-device handle: one register, spread over `devices` shards
+        if (k == "rank") { *value = 0; return QSV_OK; }
+        if (k == "world") { *value = 1; return QSV_OK; }
+        return qsv_get_info(s->children[0], key, value);
+    }
     if (k == "n_qubits") *value = s->n_qubits;
     else if (k == "n_local_qubits") *value = s->n_local;
     else if (k == "n_alloc_qubits") *value = s->n_alloc;
@@ -757,6 +948,13 @@ int qsv_get_info(const qsv_state* s, const char* key, int64_t* value) {
 }
 
 int qsv_init_basis(qsv_state* s, uint64_t index) {
+    if (is_multi(s)) {
+        for (qsv_state* c : s->children) {
+            const int rc = qsv_init_basis(c, index);
+            if (rc != QSV_OK) return set_error(s, rc, "%s", c->error.c_str());
+        }
+        return QSV_OK;
+    }
     QSV_ENTER(s);
     if (index >> s->n_qubits) return set_error(s, QSV_ERR_INVALID_ARG, "basis index out of range");
     // lazy: written to HBM right before the first pass (or first read), so a sharded plan can still pick its layout
@@ -768,6 +966,17 @@ int qsv_init_basis(qsv_state* s, uint64_t index) {
 }
 
 int qsv_upload(qsv_state* s, const double* host_amps, uint64_t first, uint64_t count) {
+    if (is_multi(s)) {  // any range of the register: every shard takes its part
+        if (!host_amps && count) return set_error(s, QSV_ERR_INVALID_ARG, "host_amps is NULL");
+        if ((first >> s->n_qubits) || count > (1ull << s->n_qubits) - first) return set_error(s, QSV_ERR_INVALID_ARG, "range is outside the register");
+        for (qsv_state* c : s->children) {
+            const uint64_t lo = std::max(first, rank_base(c)), hi = std::min(first + count, rank_base(c) + local_len(c));
+            if (lo >= hi) continue;
+            const int rc = qsv_upload(c, host_amps + 2 * (lo - first), lo, hi - lo);
+            if (rc != QSV_OK) return set_error(s, rc, "%s", c->error.c_str());
+        }
+        return QSV_OK;
+    }
     QSV_ENTER(s);
     if (!host_amps && count) return set_error(s, QSV_ERR_INVALID_ARG, "host_amps is NULL");
     if (first < rank_base(s) || first - rank_base(s) + count > local_len(s)) return set_error(s, QSV_ERR_INVALID_ARG, "range is outside this rank's shard");
@@ -780,6 +989,37 @@ int qsv_upload(qsv_state* s, const double* host_amps, uint64_t first, uint64_t c
 }
 
 int qsv_download(qsv_state* s, double* host_amps, uint64_t first, uint64_t count) {
+    if (is_multi(s)) {
+        if (!host_amps && count) return set_error(s, QSV_ERR_INVALID_ARG, "host_amps is NULL");
+        if ((first >> s->n_qubits) || count > (1ull << s->n_qubits) - first) return set_error(s, QSV_ERR_INVALID_ARG, "range is outside the register");
+        bool canonical = true;
+        for (qsv_state* c : s->children) canonical &= c->lazy_basis || c->layout_identity;
+        if (canonical) {  // every shard hands over its part of the range
+            for (qsv_state* c : s->children) {
+                const uint64_t lo = std::max(first, rank_base(c)), hi = std::min(first + count, rank_base(c) + local_len(c));
+                if (lo >= hi) continue;
+                const int rc = qsv_download(c, host_amps + 2 * (lo - first), lo, hi - lo);
+                if (rc != QSV_OK) return set_error(s, rc, "%s", c->error.c_str());
+            }
+            return QSV_OK;
+        }
+        // remapped layout: the collective, un-permuting download, in bounded pieces; rank 0's copy is the answer
+        const uint64_t piece = 1ull << 22;
+        std::vector<std::vector<double>> scratch(s->children.size());
+        for (uint64_t done = 0; done < count; done += piece) {
+            const uint64_t m = std::min(piece, count - done);
+            const int rc = multi_run(s, [&](int r) {
+                double* dst = host_amps + 2 * done;
+                if (r != 0) {
+                    scratch[(size_t)r].resize(2 * m);
+                    dst = scratch[(size_t)r].data();
+                }
+                return qsv_download(s->children[(size_t)r], dst, first + done, m);
+            });
+            if (rc != QSV_OK) return rc;
+        }
+        return QSV_OK;
+    }
     QSV_ENTER(s);
     if (!host_amps && count) return set_error(s, QSV_ERR_INVALID_ARG, "host_amps is NULL");
     if (!s->lazy_basis && !s->layout_identity) {
@@ -796,6 +1036,17 @@ int qsv_download(qsv_state* s, double* host_amps, uint64_t first, uint64_t count
 }
 
 int qsv_gather(qsv_state* s, const uint64_t* indices, uint64_t count, double* host_amps) {
+    if (is_multi(s)) {  // collective on the shards; rank 0's copy is the answer
+        std::vector<std::vector<double>> scratch(s->children.size());
+        return multi_run(s, [&](int r) {
+            double* dst = host_amps;
+            if (r != 0) {
+                scratch[(size_t)r].resize(2 * count + 2);
+                dst = scratch[(size_t)r].data();
+            }
+            return qsv_gather(s->children[(size_t)r], indices, count, dst);
+        });
+    }
     QSV_ENTER(s);
     if (count == 0) return QSV_OK;
     if (!indices || !host_amps) return set_error(s, QSV_ERR_INVALID_ARG, "NULL argument");
@@ -840,6 +1091,12 @@ int qsv_gather(qsv_state* s, const uint64_t* indices, uint64_t count, double* ho
 }
 
 int qsv_apply(qsv_state* s, const qsv_op* ops, size_t n_ops, qsv_stats* stats) {
+    if (is_multi(s)) {  // every device lowers and schedules the same gate list for its shard and runs it; remaps meet over NVLink
+        std::vector<qsv_stats> st(s->children.size());
+        const int rc = multi_run(s, [&](int r) { return qsv_apply(s->children[(size_t)r], ops, n_ops, &st[(size_t)r]); });
+        if (rc == QSV_OK && stats) *stats = st[0];
+        return rc;
+    }
     QSV_ENTER(s);
     try {
         // a pending basis state has no data to move, so the scheduler may choose the initial layout of a sharded register
@@ -897,6 +1154,7 @@ int qsv_apply(qsv_state* s, const qsv_op* ops, size_t n_ops, qsv_stats* stats) {
 }
 
 int qsv_run_plan(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
+    if (is_multi(s)) return set_error(s, QSV_ERR_UNSUPPORTED, "a plan object lives on one device; use qsv_apply on a multi-device handle (it caches its plans per shard)");
     QSV_ENTER(s);
     if (!p) return set_error(s, QSV_ERR_INVALID_ARG, "plan is NULL");
     try {
@@ -909,6 +1167,17 @@ int qsv_run_plan(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
 }
 
 int qsv_sample(qsv_state* s, const double* uniforms, uint64_t shots, uint64_t* out_indices) {
+    if (is_multi(s)) {  // collective on the shards; rank 0's copy is the answer
+        std::vector<std::vector<uint64_t>> scratch(s->children.size());
+        return multi_run(s, [&](int r) {
+            uint64_t* dst = out_indices;
+            if (r != 0) {
+                scratch[(size_t)r].resize(shots + 1);
+                dst = scratch[(size_t)r].data();
+            }
+            return qsv_sample(s->children[(size_t)r], uniforms, shots, dst);
+        });
+    }
     QSV_ENTER(s);
     if (shots == 0) return QSV_OK;
     if (!uniforms || !out_indices) return set_error(s, QSV_ERR_INVALID_ARG, "NULL argument");
@@ -951,6 +1220,12 @@ int qsv_sample(qsv_state* s, const double* uniforms, uint64_t shots, uint64_t* o
 }
 
 int qsv_norm_sqr(qsv_state* s, double* out) {
+    if (is_multi(s)) {
+        std::vector<double> v(s->children.size(), 0.0);
+        const int rc = multi_run(s, [&](int r) { return qsv_norm_sqr(s->children[(size_t)r], &v[(size_t)r]); });
+        if (rc == QSV_OK && out) *out = v[0];
+        return rc;
+    }
     QSV_ENTER(s);
     if (!out) return set_error(s, QSV_ERR_INVALID_ARG, "out is NULL");
     { int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
@@ -967,12 +1242,14 @@ int qsv_norm_sqr(qsv_state* s, double* out) {
 
 int qsv_get_layout(const qsv_state* s, uint8_t* out_layout, size_t cap) {
     if (!s || !out_layout || cap < s->n_qubits) return set_error(nullptr, QSV_ERR_INVALID_ARG, "bad argument");
+    if (is_multi(s)) return qsv_get_layout(s->children[0], out_layout, cap);
     memcpy(out_layout, s->layout, s->n_qubits);
     return QSV_OK;
 }
 
 int qsv_last_step_ms(const qsv_state* s, double* out_ms, size_t cap, size_t* n_steps) {
     if (!s || !n_steps) return set_error(nullptr, QSV_ERR_INVALID_ARG, "NULL argument");
+    if (is_multi(s)) return qsv_last_step_ms(s->children[0], out_ms, cap, n_steps);
     *n_steps = s->last_step_ms.size();
     if (out_ms)
         for (size_t i = 0; i < s->last_step_ms.size() && i < cap; ++i) out_ms[i] = s->last_step_ms[i];
@@ -991,6 +1268,10 @@ constexpr size_t kCkptChunk = (size_t)64 << 20;
 }  // namespace
 
 int qsv_save(qsv_state* s, const char* path) {
+    if (is_multi(s)) {  // one file per shard: <path>.r<rank>
+        if (!path) return set_error(s, QSV_ERR_INVALID_ARG, "path is NULL");
+        return multi_run(s, [&](int r) { return qsv_save(s->children[(size_t)r], (std::string(path) + ".r" + std::to_string(r)).c_str()); });
+    }
     QSV_ENTER(s);
     if (!path) return set_error(s, QSV_ERR_INVALID_ARG, "path is NULL");
     { int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
@@ -1018,6 +1299,10 @@ int qsv_save(qsv_state* s, const char* path) {
 }
 
 int qsv_load(qsv_state* s, const char* path) {
+    if (is_multi(s)) {
+        if (!path) return set_error(s, QSV_ERR_INVALID_ARG, "path is NULL");
+        return multi_run(s, [&](int r) { return qsv_load(s->children[(size_t)r], (std::string(path) + ".r" + std::to_string(r)).c_str()); });
+    }
     QSV_ENTER(s);
     if (!path) return set_error(s, QSV_ERR_INVALID_ARG, "path is NULL");
     FILE* f = fopen(path, "rb");
@@ -1049,6 +1334,13 @@ int qsv_load(qsv_state* s, const char* path) {
 }
 
 int qsv_synchronize(qsv_state* s) {
+    if (is_multi(s)) {
+        for (qsv_state* c : s->children) {
+            const int rc = qsv_synchronize(c);
+            if (rc != QSV_OK) return set_error(s, rc, "%s", c->error.c_str());
+        }
+        return QSV_OK;
+    }
     QSV_ENTER(s);
     QSV_CUDA(s, cudaStreamSynchronize(s->stream));
     return QSV_OK;
@@ -1056,6 +1348,7 @@ int qsv_synchronize(qsv_state* s) {
 
 int qsv_device_pointer(qsv_state* s, void** dev_ptr, void** cuda_stream) {
     if (!s) return set_error(nullptr, QSV_ERR_INVALID_ARG, "handle is NULL");
+    if (is_multi(s)) return set_error(s, QSV_ERR_UNSUPPORTED, "a multi-device handle has one shard per device, not one device pointer");
     { cudaSetDevice(s->device); int rc0 = materialize(s); if (rc0 != QSV_OK) return rc0; }
     if (dev_ptr) *dev_ptr = s->d_state;
     if (cuda_stream) *cuda_stream = s->stream;

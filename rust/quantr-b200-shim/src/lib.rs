@@ -55,6 +55,7 @@ pub mod ffi {
         pub fn qsv_create(out: *mut *mut QsvState, n_qubits: u32, device: c_int) -> c_int;
         pub fn qsv_create_sharded(out: *mut *mut QsvState, n_qubits: u32, device: c_int, rank: c_int, world: c_int,
                                   nccl_unique_id: *const c_void, nccl_unique_id_bytes: usize) -> c_int;
+        pub fn qsv_create_multi(out: *mut *mut QsvState, n_qubits: u32, devices: *const c_int, n_devices: c_int) -> c_int;
         pub fn qsv_nccl_unique_id(out: *mut c_void, out_bytes: usize) -> c_int;
         pub fn qsv_peer_export(s: *mut QsvState, out_handle: *mut c_void, out_bytes: usize) -> c_int;
         pub fn qsv_peer_import(s: *mut QsvState, handles: *const c_void, n_handles: usize) -> c_int;

@@ -136,15 +136,10 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
                     ext_phase[P.ops[o].diag_index] = diag_ext_phase(P.ops[o], blob, base_full);
                 }
             }
-        // PASS_WARP_LOCAL: the kernel has no group barrier between the rounds, so here every warp runs all rounds to the
-        // end before the next warp starts - a thread mapping that is not warp-local gives wrong amplitudes
-        const bool warp_local = (P.hdr.flags & PASS_WARP_LOCAL) != 0 && P.hdr.tile_bits == 11;
-        const uint32_t n_warp_iter = warp_local ? groups / 32u : 1u;
-        for (uint32_t wi = 0; wi < n_warp_iter; ++wi)
         for (uint32_t r = 0; r < P.hdr.n_rounds; ++r) {
             const DevRound& R = P.rounds[r];
             if (R.type == ROUND_REG) {
-                for (uint32_t e = warp_local ? 32u * wi : 0u; e < (warp_local ? 32u * wi + 32u : groups); ++e) {
+                for (uint32_t e = 0; e < groups; ++e) {
                     uint32_t act[W];
                     memcpy(act, &thr_act[(size_t)e * W], sizeof(act));
                     tile_active_mask<W>(P.hdr, P.ops, base_full, act);

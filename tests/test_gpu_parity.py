@@ -224,6 +224,35 @@ def test_post_select_example_and_measure_all_without_cache():
     qb.seed(1)
     bins = sim.measure_all_without_cache(40).take()
     assert set(k.to_string() for k in bins) <= {"00", "10"} and sum(bins.values()) == 40
+    assert sim.resimulated_shots == 0  # a deterministic closure encodes to the same ops every shot: the register is reused
+
+
+def test_measure_all_without_cache_resimulates_stochastic_closures():
+    """simulated_circuit.rs:81-114: 'potentially allows for mixed states to be simulated, through the implementation of
+    Gate::Custom' - a closure that flips its wire with probability 1/4 per *shot* must give a 3:1 mixture of |0> and |1>, which
+    only comes out if every shot whose closure differs re-runs the circuit; shots whose ops are byte-identical to the ones
+    that built the register in HBM reuse it."""
+    rng = np.random.default_rng(12)
+    state = {"flip": False, "calls": 0}
+
+    def noisy(prod):
+        if state["calls"] % 2 == 0:  # one decision per shot (the closure is called once per basis sub-state)
+            state["flip"] = rng.random() < 0.25
+        state["calls"] += 1
+        one = prod.get_qubits()[0] == st.Qubit.One
+        out = (not one) if state["flip"] else one
+        return st.SuperPosition.new_with_amplitudes_unchecked([0.0, 1.0] if out else [1.0, 0.0])
+
+    c = Circuit.new(3)
+    c.add_gate(G.Custom(noisy, [], "N"), 1)
+    sim = c.simulate()
+    sim.print_warnings(False)
+    qb.seed(3)
+    shots = 400
+    bins = {k.to_string(): v for k, v in sim.measure_all_without_cache(shots).take().items()}
+    assert set(bins) <= {"000", "010"} and sum(bins.values()) == shots
+    assert 60 <= bins.get("010", 0) <= 140  # binomial(400, 1/4): 100 +- 4 sigma
+    assert 0 < sim.resimulated_shots < shots  # only the shots whose closure changed its mind
 
 
 def _none_on_zero_closure(prod):

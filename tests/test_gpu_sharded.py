@@ -198,3 +198,67 @@ def test_two_gpu_pipelined_exchange_matches_oracle(tmp_path, monkeypatch):
     for label in ("pipelined2", "pipelined4", "pipelined8"):
         assert int(out[label + "_overlapped"]) >= 1, label
         assert np.max(np.abs(out[label] - ref)) < 1e-12, label
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs")
+def test_in_library_multi_gpu_handle_matches_oracle(tmp_path):
+    """'single-process, multi-device inside the library, invisible to the caller' - one handle from
+    qsv_create_multi, no launcher, no NCCL id or IPC handles in the caller's hands; the reference-facing Circuit API on top
+    of it through QSV_DEVICES (Circuit::simulate, src/circuit.rs:364-388, knows nothing about devices)."""
+    n = 15
+    rng = np.random.default_rng(77)
+    c = random_any_gate_circuit(OracleCircuit, G, n, 140, rng)
+    enc = encode_gates(c.circuit_gates, n)
+    reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    reg /= np.linalg.norm(reg)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense", threads=4)
+    s = qb.DeviceState(n, devices=[0, 1])
+    assert s.get_info("devices") == 2 and s.get_info("n_local_qubits") == n - 1
+    s.set_option("tile_bits", 7)
+    # uploaded register (any range: here two pieces that straddle the shard boundary), random circuit with remaps
+    cut = (1 << (n - 1)) + 37
+    s.upload(reg[:cut], first=0)
+    s.upload(reg[cut:], first=cut)
+    st = s.apply(enc)
+    assert st["n_exchanges"] >= 1
+    allidx = np.arange(1 << n, dtype=np.uint64)
+    assert np.max(np.abs(s.gather(allidx) - ref)) < 1e-12
+    assert np.max(np.abs(s.download(0, 1 << n) - ref)) < 1e-12  # un-permuting download if the run left the qubits remapped
+    assert np.max(np.abs(s.download(1000, 5000) - ref[1000:6000])) < 1e-12
+    assert abs(s.norm_sqr() - 1.0) < 1e-12
+    # sampling over the whole register: empirical distribution against |ref|^2
+    shots = 200000
+    idx = s.sample(np.random.default_rng(5).random(shots)).astype(np.int64)
+    probs = np.abs(ref) ** 2
+    top = np.argsort(probs)[-8:]
+    counts = np.bincount(idx, minlength=1 << n)
+    for t in top:
+        assert abs(counts[t] / shots - probs[t]) < 6 * np.sqrt(probs[t] / shots) + 1e-4
+    # basis state + QFT: the leading stage on the rank qubit is folded into the shards' initial amplitudes
+    x = 0x2ACE
+    encq = encode_gates(qft_circuit(OracleCircuit, G, n).circuit_gates, n)
+    s.init_basis(x)
+    stq = s.apply(encq)
+    assert stq["n_exchanges"] == 0
+    assert np.max(np.abs(s.gather(allidx) - qft_expected(n, x))) < 1e-12
+    # checkpoint: one file per shard
+    path = str(tmp_path / "ck")
+    s.save(path)
+    assert os.path.exists(path + ".r0") and os.path.exists(path + ".r1")
+    s.init_basis(0)
+    s.load(path)
+    assert np.max(np.abs(s.gather(allidx) - qft_expected(n, x))) < 1e-12
+    s.close()
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs")
+def test_circuit_api_over_two_gpus_via_qsv_devices(monkeypatch):
+    """The drop-in surface itself: Circuit.simulate / get_state / measure_all with QSV_DEVICES=0,1."""
+    monkeypatch.setenv("QSV_DEVICES", "0,1")
+    n = 12
+    got = qft_circuit(qb.Circuit, G, n, 0xACE).simulate()
+    want = qft_circuit(OracleCircuit, G, n, 0xACE).simulate().get_state().take().get_amplitudes()
+    assert got._state.get_info("devices") == 2
+    assert np.max(np.abs(got.get_state().take().get_amplitudes() - want)) < 1e-12
+    bins = got.measure_all(2000).take()
+    assert sum(bins.values()) == 2000
