@@ -598,7 +598,7 @@ QSV_HD void thread_active_mask(const DevPass& hdr, const DevRound* rounds, const
 #pragma unroll
     for (int w = 0; w < W; ++w) act[w] = 0xffffffffu;
     for (uint32_t r = 0; r < hdr.n_rounds; ++r) {
-        if (rounds[r].type != ROUND_REG) continue;
+        if (rounds[r].type == ROUND_DENSE) continue;  // (the gather ops of a permutation round lie outside its op range)
         const uint32_t lb = (uint32_t)deposit(e, rounds[r].thr_segs, rounds[r].n_thr_segs);
         for (uint32_t o = rounds[r].first_op; o < rounds[r].first_op + rounds[r].n_ops; ++o)
             if ((lb & ops[o].cmask_thr) != ops[o].cmask_thr) {
@@ -634,6 +634,39 @@ QSV_HD void round_load(const DevRound& R, uint32_t lb, const cplx* tile, cplx (&
     const char* tb = reinterpret_cast<const char*>(tile);
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const cplx*>(tb + (sb ^ R.xoff[s]));
+}
+
+// Permutation round (ROUND_PERM): a[s] = tile[P^-1(l_s)], l_s = the thread's tile-local index of slot s.  The round's ops
+// are applied to the 16 indices in reverse order (each op is its own inverse): idx ^= target bit where the op's tile-local
+// controls hold.  act: as in round_ops (an op whose controls outside the tile fail for this tile is skipped).
+template <int W, bool FAST = false>
+QSV_HD void round_perm_load(const DevRound& R, const DevOp* ops, const uint32_t (&act)[W], uint32_t lb, const cplx* tile, cplx (&a)[kSlots]) {
+    uint32_t idx[kSlots];
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+        uint32_t off = 0;
+#pragma unroll
+        for (int j = 0; j < kRegBits; ++j)
+            if ((s >> j) & 1) off |= 1u << R.reg_pos[j];
+        idx[s] = lb | off;
+    }
+    const uint32_t first = R.perm_first, n = R.n_perm;
+    for (uint32_t j = n; j-- > 0;) {
+        const uint32_t o = first + j;
+        if constexpr (!FAST) {
+            uint32_t word = act[0];
+#pragma unroll
+            for (int w = 1; w < W; ++w)
+                if ((int)(o >> 5) == w) word = act[w];
+            if (!((word >> (o & 31u)) & 1u)) continue;
+        }
+        const uint32_t cm = ops[o].cmask_thr, tb = 1u << ops[o].slot;
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s)
+            if ((idx[s] & cm) == cm) idx[s] ^= tb;
+    }
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) a[s] = tile[swz(idx[s])];
 }
 
 QSV_HD void round_store_tile(const DevRound& R, uint32_t lb, cplx* tile, const cplx (&a)[kSlots]) {

@@ -106,7 +106,22 @@ pass_kernel(cplx* __restrict__ state, const uint8_t* __restrict__ blob, uint64_t
         __syncthreads();
 
         for (uint32_t r = 0; r < n_rounds; ++r) {
-            if (P.rounds[r].type == ROUND_REG) {
+            if (P.rounds[r].type == ROUND_PERM) {  // gather through the tile: everybody reads before anybody writes
+                const uint32_t lb = active ? round_thread_base(P.rounds[r], tid) : 0u;
+                cplx a[kSlots];
+                if (active) round_perm_load<W, FAST>(P.rounds[r], P.ops, act, lb, tile, a);
+                __syncthreads();
+                if (active) {
+                    round_ops<W, FAST>(P.rounds[r], P.ops, ctx, act, tid, a);  // ordinary ops behind the gather, if any
+                    if (direct && r + 1 == n_rounds) {
+                        cplx* g = state + base + gstore_t;
+#pragma unroll
+                        for (int s = 0; s < kSlots; ++s) st_stream(g + P.loads.store_goff[s], cplx{a[s].x * final_scale, a[s].y * final_scale});
+                    } else {
+                        round_store_tile(P.rounds[r], lb, tile, a);
+                    }
+                }
+            } else if (P.rounds[r].type == ROUND_REG) {
                 if (active) {
                     const uint32_t lb = round_thread_base(P.rounds[r], tid);
                     cplx a[kSlots];

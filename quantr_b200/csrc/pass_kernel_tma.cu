@@ -147,7 +147,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
     cplx* ext_phase2 = ext_all + (size_t)group * 2u * (n_diag + 1);
     const uint32_t n_ext_segs = P.hdr.n_ext_segs, n_rounds = P.hdr.n_rounds;
     const double final_scale = P.hdr.final_scale;
-    const bool last_is_reg = n_rounds && P.rounds[n_rounds - 1].type == ROUND_REG;
+    const bool last_is_reg = n_rounds && P.rounds[n_rounds - 1].type != ROUND_DENSE;  // register or permutation round
     const bool direct = (P.hdr.flags & PASS_DIRECT_STORE) != 0 && !(diag_mode & 4) && last_is_reg;
     const bool need_base = direct || (P.hdr.ext_ctrl_mask[0] | P.hdr.ext_ctrl_mask[1] | P.hdr.ext_ctrl_mask[2]) != 0 || init.mode != 0;
     // Tiles of this CTA (tile ids and per-CTA counts fit 32 bits): the k-th tile it works on is
@@ -246,7 +246,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
                 ext_phase2[P.ops[o].diag_index] = ext_phase2[n_diag + 1 + P.ops[o].diag_index] = diag_ext_phase_terms(P.ops[o].theta0, nullptr, 0, 0);
         }
     for (uint32_t r = tid / kGT; r < n_rounds && r < kLbTabRounds; r += kG)  // group g fills rounds g, g + kG, ...
-        if (P.rounds[r].type == ROUND_REG) lbtab[r * kGT + gtid] = round_thread_base(P.rounds[r], gtid);
+        if (P.rounds[r].type != ROUND_DENSE) lbtab[r * kGT + gtid] = round_thread_base(P.rounds[r], gtid);
     const uint64_t gstore_t = direct ? deposit(round_thread_base(P.rounds[n_rounds - 1], gtid), P.hdr.tile_segs, P.hdr.n_tile_segs) : 0;
     const uint32_t soff_t = swz(gtid) << 4;
     // warp 0 of the group: a tile that left through its buffer; the refill of that buffer waits until the bulk store has
@@ -306,17 +306,21 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
 
         for (uint32_t r = 0; r < n_rounds; ++r) {
             const bool last = r + 1 == n_rounds;
-            if (P.rounds[r].type == ROUND_REG) {
+            if (P.rounds[r].type != ROUND_DENSE) {
+                const bool perm = P.rounds[r].type == ROUND_PERM;
                 const uint32_t lb = r < kLbTabRounds ? lbtab[r * kGT + gtid] : round_thread_base(P.rounds[r], gtid);
                 cplx a[kSlots];
-                round_load(P.rounds[r], lb, tile, a);
+                if (perm) round_perm_load<W, FAST>(P.rounds[r], P.ops, act, lb, tile, a);
+                else round_load(P.rounds[r], lb, tile, a);
+                // a permutation round gathers from all over the tile: everybody has read before anybody writes
+                if (perm && !(direct && last && !init.mode)) group_barrier(group, kGT);
                 if (direct && last && !init.mode) {
                     // the tile now lives in registers: hand the buffer to the tile that will use it next, a whole
                     // round of arithmetic before this group comes back for more
                     group_barrier(group, kGT);
                     if (gtid < 32u && k + kNB < n_my) issue_load(tile_of(k + kNB), slot, use + 1u);
                 }
-                round_ops<W, FAST>(P.rounds[r], P.ops, ctx, act, gtid, a);
+                round_ops<W, FAST>(P.rounds[r], P.ops, ctx, act, gtid, a);  // (a permutation round may carry ordinary ops behind its gather)
                 if (direct && last) {
                     cplx* g = state + base + gstore_t;
 #pragma unroll

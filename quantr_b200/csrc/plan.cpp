@@ -413,6 +413,9 @@ namespace {
 
 struct RoundB {
     bool dense = false;
+    bool perm = false;         // permutation round (ROUND_PERM): the first n_perm ops are X / CNot / Toffoli / multi-controlled X gates
+                               // on any tile bits (the gather); ordinary ops on the round's register bits may follow
+    size_t n_perm = 0;
     std::vector<int> reg;      // physical bits held in registers (targets first, then filler)
     std::vector<size_t> ops;   // indices into lops
 };
@@ -572,7 +575,7 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
             rounds.push_back(dr);
             continue;
         }
-        dr.type = ROUND_REG;
+        dr.type = rb.perm ? ROUND_PERM : ROUND_REG;
         // register bits: the round's targets, padded with the highest free tile bits
         const std::vector<int>& reg_local = reg_local_pre;
         std::vector<int> slot_of(16, -1), thr_local, thr_index(16, -1);
@@ -615,7 +618,7 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
         uint32_t qft4_diags = 0;
         bool qft4 = false;
         const int n_st = (int)rb.reg.size();  // stages = register bits that are targets (3: the fourth, highest, bit is a passenger)
-        if (plan.opt.fuse && plan.opt.qft4 && kRegBits == 4 && (n_st == 4 || n_st == 3) &&
+        if (!rb.perm && plan.opt.fuse && plan.opt.qft4 && kRegBits == 4 && (n_st == 4 || n_st == 3) &&
             (rb.ops.size() == (size_t)(2 * n_st) || rb.ops.size() == (size_t)(2 * n_st - 1))) {
             bool ok = true;
             for (int j = 0; j + 1 < n_st; ++j) ok &= tile_phys[reg_local[j + 1]] == tile_phys[reg_local[j]] + 1;
@@ -650,7 +653,28 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
                 n_hadamard += (uint32_t)n_st;
             }
         }
-        for (size_t ri = 0; ri < rb.ops.size(); ++ri) {
+        if (rb.perm) { dr.perm_first = (uint32_t)ops.size(); dr.n_perm = (uint32_t)rb.n_perm; }
+        for (size_t ri = 0; rb.perm && ri < rb.n_perm; ++ri) {  // the gather of a permutation round: targets and controls are tile-local positions
+            const LOp& lop = lops[rb.ops[ri]];
+            DevOp d;
+            memset(&d, 0, sizeof(d));
+            d.ext_slot = kNoExtSlot;
+            d.type = OP_MAT_XSWAP;
+            d.code = kCodeNop;
+            const int lp = local_of[lop.target];
+            if (lp < 0 || lop.kind != LOp::MAT || lop.mtype != OP_MAT_XSWAP || lop.dual) fail("internal: permutation round holds an op that is not an X gate inside the tile");
+            d.slot = (uint32_t)lp;
+            for (int b = 0; b < 64; ++b) {
+                if (!((lop.cmask >> b) & 1)) continue;
+                const int cl = b < nloc ? local_of[b] : -1;
+                if (cl < 0) d.cmask_ext |= 1ull << b;
+                else d.cmask_thr |= 1u << cl;
+            }
+            if (d.cmask_ext) hdr.ext_ctrl_mask[ops.size() >> 5] |= 1u << (ops.size() & 31);
+            ops.push_back(d);
+        }
+        if (rb.perm) dr.first_op = (uint32_t)ops.size();  // the ordinary ops behind the gather
+        for (size_t ri = rb.perm ? rb.n_perm : 0; ri < rb.ops.size(); ++ri) {
             size_t oi = rb.ops[ri];
             if (qft4 && lops[oi].kind == LOp::MAT) continue;  // the macro-op's Hadamards
             // Peephole: an uncontrolled Hadamard followed by a diagonal op controlled by exactly the Hadamard's bit
@@ -755,7 +779,7 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
 
     // Last round of the pass: if it is a register round whose register bits leave the three lowest tile bits to the
     // threads, its 16 amplitudes per thread go straight from registers to global memory (still 128-byte coalesced).
-    if (!rounds.empty() && rounds.back().type == ROUND_REG && T >= 7 && plan.opt.direct_store) {
+    if (!rounds.empty() && rounds.back().type != ROUND_DENSE && T >= 7 && plan.opt.direct_store) {
         const DevRound& lr = rounds.back();
         bool ok = true;
         for (int j = 0; j < kRegBits; ++j) ok &= lr.reg_pos[j] >= 3;
@@ -964,9 +988,63 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
             }
             if (packed.size() < pb.rounds.size()) pb.rounds.swap(packed);
         };
+        // Permutation rounds: a run of X / CNot / Toffoli / multi-controlled X ops on more than four targets (it would take
+        // several register rounds, each a trip through shared memory plus 96 register moves per op) becomes one gather
+        // through the tile (ROUND_PERM).  The pass's ops keep their order; everything else is packed into register rounds
+        // in that order.
+        auto form_perm_rounds = [&](PassB& pb) {
+            auto permable = [&](size_t i) { return lops[i].kind == LOp::MAT && lops[i].mtype == OP_MAT_XSWAP && !lops[i].dual; };
+            std::vector<size_t> order;
+            for (const RoundB& r : pb.rounds) order.insert(order.end(), r.ops.begin(), r.ops.end());
+            // maximal runs of X ops; a run qualifies when it has more than kRegBits distinct targets
+            std::vector<char> in_perm(order.size(), 0);
+            bool any = false;
+            for (size_t a = 0; a < order.size();) {
+                if (!permable(order[a])) { ++a; continue; }
+                size_t b = a;
+                uint64_t tg = 0;
+                while (b < order.size() && permable(order[b])) tg |= lops[order[b++]].targets();
+                if (popcnt(tg) > kRegBits) {
+                    for (size_t k = a; k < b; ++k) in_perm[k] = 1;
+                    any = true;
+                }
+                a = b;
+            }
+            if (!any) return;
+            std::vector<RoundB> out_rounds;
+            for (size_t k = 0; k < order.size(); ++k) {
+                const LOp& lop = lops[order[k]];
+                if (in_perm[k]) {
+                    if (out_rounds.empty() || !out_rounds.back().perm || out_rounds.back().n_perm != out_rounds.back().ops.size() ||
+                        out_rounds.back().ops.size() >= (size_t)kMaxRoundOps) {
+                        out_rounds.push_back(RoundB());
+                        out_rounds.back().perm = true;
+                    }
+                    out_rounds.back().ops.push_back(order[k]);
+                    out_rounds.back().n_perm = out_rounds.back().ops.size();
+                } else if (lop.kind == LOp::DENSE) {
+                    out_rounds.push_back(RoundB());
+                    out_rounds.back().dense = true;
+                    out_rounds.back().ops.push_back(order[k]);
+                } else {
+                    // (ordinary ops may follow the gather of a permutation round: they work on what it left in the registers)
+                    bool fresh = out_rounds.empty() || out_rounds.back().dense || out_rounds.back().ops.size() - out_rounds.back().n_perm >= (size_t)kMaxRoundOps;
+                    if (!fresh && lop.kind == LOp::MAT) {
+                        RoundB& r = out_rounds.back();
+                        if (std::find(r.reg.begin(), r.reg.end(), lop.target) == r.reg.end() && (int)r.reg.size() == kRegBits) fresh = true;
+                    }
+                    if (fresh) out_rounds.push_back(RoundB());
+                    RoundB& r = out_rounds.back();
+                    if (lop.kind == LOp::MAT && std::find(r.reg.begin(), r.reg.end(), lop.target) == r.reg.end()) r.reg.push_back(lop.target);
+                    r.ops.push_back(order[k]);
+                }
+            }
+            if (out_rounds.size() < pb.rounds.size() && out_rounds.size() <= (size_t)kMaxRounds) pb.rounds.swap(out_rounds);
+        };
         auto close_pass = [&]() {
             if (!cur.empty()) {
                 if (plan.opt.fuse && plan.opt.reorder && cur.rounds.size() > 2) repack_rounds(cur);
+                if (plan.opt.fuse && plan.opt.perm_rounds && cur.rounds.size() > 1) form_perm_rounds(cur);
                 out.push_back(std::move(cur));
                 low_mask = (T == nloc) ? 0 : ((1ull << L) - 1);
             }
@@ -1273,7 +1351,7 @@ std::string describe_plan(const Plan& plan) {
             for (uint32_t b = 0; b < h->tile_segs[s].width; ++b) { os << (first ? "" : ",") << (int)h->tile_segs[s].dst_lo + (int)b; first = false; }
         os << "],\"n_tiles\":" << h->n_tiles << ",\"bytes\":" << h->blob_bytes << ",\"flags\":" << h->flags << ",\"rounds\":[";
         for (uint32_t r = 0; r < h->n_rounds; ++r) {
-            os << (r ? "," : "") << "{\"type\":" << rounds[r].type << ",\"reg\":[" << (int)rounds[r].reg_pos[0] << "," << (int)rounds[r].reg_pos[1]
+            os << (r ? "," : "") << "{\"type\":" << rounds[r].type << ",\"n_perm\":" << (rounds[r].type == ROUND_PERM ? rounds[r].n_perm : 0u) << ",\"reg\":[" << (int)rounds[r].reg_pos[0] << "," << (int)rounds[r].reg_pos[1]
                << "," << (int)rounds[r].reg_pos[2] << "," << (int)rounds[r].reg_pos[3] << "],\"ops\":[";
             for (uint32_t o = 0; o < rounds[r].n_ops; ++o) os << (o ? "," : "") << ops[rounds[r].first_op + o].type;
             os << "]}";

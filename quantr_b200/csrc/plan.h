@@ -49,6 +49,7 @@ struct PlanOptions {
     int fold_prefix = 1;  // sharded basis states: leading gates on the qubits held in the rank id are applied on the host (build_plan)
     int reorder = 1;      // passes take later ops that commute with the ops they had to leave behind (plan.cpp schedule)
     int merge_1q = 1;     // 2x2 gates on the same target and controls are multiplied together across commuting ops; identities vanish
+    int perm_rounds = 1;  // runs of X / CNot / Toffoli gates on more than four targets become one gather through the tile (ROUND_PERM)
     int merge_ctrl = 1;   // ... and a controlled 2x2 gate absorbs its uncontrolled neighbours on the target (dual-matrix ops)
 };
 

@@ -33,6 +33,7 @@ int qsv_plan_create_ex(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubit
         if (const char* env = getenv("QSV_FOLD_PREFIX")) opt.fold_prefix = atoi(env) != 0;    // developer A/B switch
         if (const char* env = getenv("QSV_REORDER")) opt.reorder = atoi(env) != 0;            // developer A/B switch
         if (const char* env = getenv("QSV_MERGE_1Q")) opt.merge_1q = atoi(env) != 0;          // developer A/B switch
+        if (const char* env = getenv("QSV_PERM_ROUNDS")) opt.perm_rounds = atoi(env) != 0;    // developer A/B switch
         if (const char* env = getenv("QSV_MERGE_CTRL")) opt.merge_ctrl = atoi(env) != 0;      // developer A/B switch
         try {
             qsv::build_plan(p->plan, n_qubits, n_local_qubits, ops, n_ops, opt, layout, free_layout != 0);

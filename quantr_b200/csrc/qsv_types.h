@@ -98,7 +98,12 @@ enum DiagFlags : uint32_t {
 enum MatFlags : uint32_t {
     MAT_DUAL = 1  // DevOp::m holds two matrices: m[0..8) where every control holds, m[8..16) elsewhere
 };
-enum RoundType : uint32_t { ROUND_REG = 0, ROUND_DENSE = 1 };
+// ROUND_PERM: a run of X / CNot / Toffoli / multi-controlled X gates (OP_MAT_XSWAP) as one gather through the tile: thread
+// and slot layout as in a register round; every thread fetches, for each of its 16 tile-local indices l, the amplitude at
+// P^-1(l) (the ops applied to the index in reverse order), and writes it to l after a barrier.  Targets and controls may
+// be any tile bits (DevOp::slot = tile-local target position, DevOp::cmask_thr = all tile-local controls).  Ordinary ops on
+// the round's register bits may follow the gather (DevRound::n_ops of them), as in a register round.
+enum RoundType : uint32_t { ROUND_REG = 0, ROUND_DENSE = 1, ROUND_PERM = 2 };
 
 struct DiagExtTerm {
     uint32_t bit;  // physical bit (outside the tile, may be a rank bit)
@@ -137,7 +142,9 @@ struct DevRound {
     uint32_t n_ops;
     uint32_t n_thr_segs;
     uint8_t reg_pos[4];  // tile-local positions of the 4 register bits, ascending
-    uint32_t pad[3];
+    uint32_t perm_first;  // ROUND_PERM: ops [perm_first, perm_first + n_perm) are the gather (X gates); ops [first_op, first_op + n_ops)
+    uint32_t n_perm;      // are ordinary register-round ops applied to the gathered amplitudes before they are stored
+    uint32_t pad;
     Seg thr_segs[kMaxThrSegs];  // thread index e -> tile-local index with register bits zero
     uint32_t xoff[kMaxSlots];   // byte offset of swz(slot s's tile-local offset): address = (swz(lb) << 4) ^ xoff[s]
 };

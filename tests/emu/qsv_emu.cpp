@@ -138,7 +138,28 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
             }
         for (uint32_t r = 0; r < P.hdr.n_rounds; ++r) {
             const DevRound& R = P.rounds[r];
-            if (R.type == ROUND_REG) {
+            if (R.type == ROUND_PERM) {  // every thread gathers from the tile as it was before the round (the kernel has a barrier there)
+                std::vector<cplx> before(tile);
+                for (uint32_t e = 0; e < groups; ++e) {
+                    uint32_t act[W];
+                    memcpy(act, &thr_act[(size_t)e * W], sizeof(act));
+                    tile_active_mask<W>(P.hdr, P.ops, base_full, act);
+                    const uint32_t lb = round_thread_base(R, e);
+                    cplx a[kSlots];
+                    if (fast) round_perm_load<W, true>(R, P.ops, act, lb, before.data(), a);
+                    else round_perm_load<W, false>(R, P.ops, act, lb, before.data(), a);
+                    if (fast) round_ops<W, true>(R, P.ops, ctx, act, e, a);  // ordinary ops behind the gather, if any
+                    else round_ops<W, false>(R, P.ops, ctx, act, e, a);
+                    if (direct && r + 1 == P.hdr.n_rounds) {
+                        const uint64_t g = base + deposit(lb, P.hdr.tile_segs, P.hdr.n_tile_segs);
+                        for (int s = 0; s < kSlots; ++s) state[g + P.loads.store_goff[s]] = cplx{a[s].x * sc, a[s].y * sc};
+                    } else if (tma && r + 1 == P.hdr.n_rounds) {
+                        round_store_tile_scaled(R, lb, tile.data(), a, sc);
+                    } else {
+                        round_store_tile(R, lb, tile.data(), a);
+                    }
+                }
+            } else if (R.type == ROUND_REG) {
                 for (uint32_t e = 0; e < groups; ++e) {
                     uint32_t act[W];
                     memcpy(act, &thr_act[(size_t)e * W], sizeof(act));

@@ -239,3 +239,37 @@ def test_controlled_gates_absorb_their_target_neighbours():
             out, desc = emu_simulate(n, enc, reg, tile_bits=tile_bits, low_bits=low_bits, describe=True)
             assert desc["n_dual_ops"] > 0
             assert np.max(np.abs(out - ref)) < 1e-12, (trial, tile_bits, low_bits)
+
+
+def test_permutation_rounds_for_runs_of_x_gates():
+    """A run of X / CNot / Toffoli gates on more than four targets becomes one gather through the tile (ROUND_PERM):
+    targets and controls on any tile bit, controls outside the tile per tile; first, middle and last round of a pass
+    (direct store).  Anchor: the reference applies every gate on its own (src/circuit/simulation.rs:37-56); Grover's
+    ancilla V-chain (tests/grovers.rs:75-155 writes it with Custom multi-CNOTs) is the workload this is for."""
+    n = 13
+    rng = np.random.default_rng(21)
+    seen_perm = 0
+    for trial in range(8):
+        c = OracleCircuit.new(n)
+        for block in range(3):
+            if block != 1 or trial % 2:
+                for _ in range(4):  # something that is not a permutation in front / between / behind
+                    c.add_gate([G.H, G.Ry(0.7), G.Rz(0.4), G.T][int(rng.integers(0, 4))], int(rng.integers(0, n)))
+            for _ in range(int(rng.integers(6, 20))):
+                w = [int(x) for x in rng.permutation(n)[:3]]
+                k = int(rng.integers(0, 3))
+                if k == 0:
+                    c.add_gate(G.X, w[0])
+                elif k == 1:
+                    c.add_gate(G.CNot(w[0]), w[1])
+                else:
+                    c.add_gate(G.Toffoli(w[0], w[1]), w[2])
+        enc = encode_gates(c.circuit_gates, n)
+        reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+        reg /= np.linalg.norm(reg)
+        ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense")
+        for tile_bits, low_bits in [(0, 0), (8, 3), (10, 3), (11, 3), (12, 4)]:
+            out, desc = emu_simulate(n, enc, reg, tile_bits=tile_bits, low_bits=low_bits, describe=True)
+            assert np.max(np.abs(out - ref)) < 1e-12, (trial, tile_bits, low_bits)
+            seen_perm += sum(1 for p in desc["passes"] for r in p["rounds"] if r["type"] == 2)
+    assert seen_perm > 0
