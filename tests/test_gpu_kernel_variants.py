@@ -22,9 +22,9 @@ def run_inner(env_extra, select):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("mode,select", [("2", "golden or random or qft16 or x3sudoko or layered or rerun or none_overwrite"),
+@pytest.mark.parametrize("mode,select", [("2", "golden or random or qft16 or x3sudoko or layered or rerun or none_overwrite or x_gate_runs"),
                                          ("0", "layered or qft_closed_form"),
-                                         ("2-nofast", "golden or qft16 or random")])
+                                         ("2-nofast", "golden or qft16 or random or x_gate_runs")])
 def test_parity_suite_with_forced_kernel(mode, select):
     env = {"QSV_ASYNC": mode.split("-")[0]}
     if mode.endswith("nofast"):

@@ -51,6 +51,43 @@ def test_random_circuits_match_oracle(seed):
         assert np.max(np.abs(out - ref)) < TOL, (n, opts)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_random_x_gate_runs_and_merged_controls_match_oracle(seed):
+    """Runs of X / CNot / Toffoli gates on many wires (permutation rounds, ROUND_PERM) next to rotations that merge into the
+    controlled gates around them (dual-matrix ops): controls on register, thread and tile-index bits, first / middle / last
+    round of a pass.  Anchor: the reference applies every gate on its own (src/circuit/simulation.rs:37-56)."""
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(12, 18))
+    c = OracleCircuit.new(n)
+    for block in range(4):
+        for _ in range(int(rng.integers(0, 8))):
+            w = [int(x) for x in rng.permutation(n)[:2]]
+            th = float(rng.uniform(-3, 3))
+            k = int(rng.integers(0, 6))
+            if k < 4:
+                c.add_gate([G.H, G.Rx(th), G.Ry(th), G.Rz(th)][k], w[0])
+            elif k == 4:
+                c.add_gate(G.CZ(w[0]), w[1])
+            else:
+                c.add_gate(G.CRk(int(rng.integers(2, 6)), w[0]), w[1])
+        for _ in range(int(rng.integers(5, 24))):
+            w = [int(x) for x in rng.permutation(n)[:3]]
+            k = int(rng.integers(0, 3))
+            if k == 0:
+                c.add_gate(G.X, w[0])
+            elif k == 1:
+                c.add_gate(G.CNot(w[0]), w[1])
+            else:
+                c.add_gate(G.Toffoli(w[0], w[1]), w[2])
+    enc = encode_gates(c.circuit_gates, n)
+    reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    reg /= np.linalg.norm(reg)
+    ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense", threads=4)
+    for opts in ({}, {"tile_bits": 8, "low_bits": 3}, {"tile_bits": 11, "low_bits": 3}, {"tile_bits": 12, "low_bits": 4}, {"tile_bits": 13}):
+        out, _ = device_run(n, enc, reg, **opts)
+        assert np.max(np.abs(out - ref)) < TOL, (n, opts)
+
+
 @pytest.mark.parametrize("n", [20, 22, 24])
 def test_layered_circuit_matches_oracle_at_scale(n):
     """BASELINE config 3's generator (H/Rx/Ry/Rz/CNot/Toffoli) at sizes the dense oracle finishes in seconds."""
