@@ -581,7 +581,8 @@ inline uint32_t op_dispatch_code(const DevOp& op) {
     case kCodeHdBase + (HAS_REG ? 4 : 0) + 2: hd_apply<2, HAS_REG, FAST>(a, op, ctx, e); break;       \
     case kCodeHdBase + (HAS_REG ? 4 : 0) + 3: hd_apply<3, HAS_REG, FAST>(a, op, ctx, e); break;
 
-#define QSV_QFT4_CASE case kCodeQft4: qft4_apply<FAST>(a, &op + 1, op.slot, op.cmask_reg, ctx, e); break;
+// (the FAST build tests for the macro-op ahead of the dispatch trees: no second copy of its body there)
+#define QSV_QFT4_CASE case kCodeQft4: if constexpr (!FAST) qft4_apply<FAST>(a, &op + 1, op.slot, op.cmask_reg, ctx, e); break;
 
 #define QSV_DIAG_CASES(HAS_REG)                                                                                                    \
     case kCodeDiagBase + (HAS_REG ? 6 : 0) + 0: diag_apply<0, HAS_REG, FAST>(a, op, ctx, e); break;           \

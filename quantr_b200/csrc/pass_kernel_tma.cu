@@ -147,7 +147,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
     cplx* ext_phase2 = ext_all + (size_t)group * 2u * (n_diag + 1);
     const uint32_t n_ext_segs = P.hdr.n_ext_segs, n_rounds = P.hdr.n_rounds;
     const double final_scale = P.hdr.final_scale;
-    const bool last_is_reg = n_rounds && P.rounds[n_rounds - 1].type != ROUND_DENSE;  // register or permutation round
+    const bool last_is_reg = n_rounds && (FAST || P.rounds[n_rounds - 1].type != ROUND_DENSE);  // register or permutation round
     const bool direct = (P.hdr.flags & PASS_DIRECT_STORE) != 0 && !(diag_mode & 4) && last_is_reg;
     const bool need_base = direct || (P.hdr.ext_ctrl_mask[0] | P.hdr.ext_ctrl_mask[1] | P.hdr.ext_ctrl_mask[2]) != 0 || init.mode != 0;
     // Tiles of this CTA (tile ids and per-CTA counts fit 32 bits): the k-th tile it works on is
@@ -306,12 +306,16 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
 
         for (uint32_t r = 0; r < n_rounds; ++r) {
             const bool last = r + 1 == n_rounds;
-            if (P.rounds[r].type != ROUND_DENSE) {
-                const bool perm = P.rounds[r].type == ROUND_PERM;
+            if (FAST || P.rounds[r].type != ROUND_DENSE) {  // (FAST passes hold register rounds only: PASS_UNCONDITIONAL)
+                const bool perm = !FAST && P.rounds[r].type == ROUND_PERM;
                 const uint32_t lb = r < kLbTabRounds ? lbtab[r * kGT + gtid] : round_thread_base(P.rounds[r], gtid);
                 cplx a[kSlots];
-                if (perm) round_perm_load<W, FAST>(P.rounds[r], P.ops, act, lb, tile, a);
-                else round_load(P.rounds[r], lb, tile, a);
+                if constexpr (!FAST) {
+                    if (perm) round_perm_load<W, false>(P.rounds[r], P.ops, act, lb, tile, a);
+                    else round_load(P.rounds[r], lb, tile, a);
+                } else {
+                    round_load(P.rounds[r], lb, tile, a);
+                }
                 // a permutation round gathers from all over the tile: everybody has read before anybody writes
                 if (perm && !(direct && last && !init.mode)) group_barrier(group, kGT);
                 if (direct && last && !init.mode) {
@@ -337,7 +341,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
                 } else {
                     round_store_tile(P.rounds[r], lb, tile, a);
                 }
-            } else {
+            } else if constexpr (!FAST) {
                 const DevDense& D = *reinterpret_cast<const DevDense*>(blob + P.ops[P.rounds[r].first_op].dense_off);
                 cplx out[kSlots];
                 dense_compute(D, blob, gtid, tile, out);

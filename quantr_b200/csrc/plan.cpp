@@ -794,6 +794,7 @@ void emit_pass(Plan& plan, const PassB& pb, const std::vector<LOp>& lops) {
     }
     bool conditional = false;
     for (const DevOp& d : ops) conditional |= d.cmask_thr != 0 || d.cmask_ext != 0;
+    for (const DevRound& r : rounds) conditional |= r.type != ROUND_REG;  // the fast path is built without dense and permutation rounds
     if (!conditional) hdr.flags |= PASS_UNCONDITIONAL;
     for (const DevOp& d : ops) if (d.type == OP_DIAG && d.n_ext > hdr.max_ext) hdr.max_ext = d.n_ext;
     hdr.n_rounds = (uint32_t)rounds.size();

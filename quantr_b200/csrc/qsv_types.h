@@ -82,8 +82,9 @@ constexpr uint32_t kCodeNop = 0, kCodeMatBase = 1, kCodeDiagBase = 41, kCodeHdBa
 enum PassFlags : uint32_t {
     PASS_DIRECT_STORE = 2,  // the last round writes its registers straight to global memory (coalesced: its register bits
                             // exclude the three lowest tile bits)
-    PASS_UNCONDITIONAL = 4  // no op of the pass has a control among the thread or tile-index bits: every thread of every
-                            // tile runs the whole op list, so the kernel walks it with uniform (scalar) control flow
+    PASS_UNCONDITIONAL = 4  // no op of the pass has a control among the thread or tile-index bits and every round is a
+                            // register round: every thread of every tile runs the whole op list (the FAST builds of the
+                            // kernels: no control masks, no dense or permutation rounds compiled in)
 };
 constexpr int kMaxRoundOps = 32;  // ops per register round (one 32-bit active mask)
 
