@@ -119,11 +119,15 @@ constexpr uint32_t kLbTabRounds = 8;  // rounds whose per-thread tile-local base
 
 // diag_mode bits 0-1: where the DIAG thread phases live (pass_core.h DiagCtx); bit 2: every pass leaves through its tile
 // buffer with a bulk tensor store, PASS_DIRECT_STORE is ignored (A/B switch QSV_TMA_STORE).
-template <int T, int NR, int NO, bool FAST>
+// KIND: 0 = everything; 1 = FAST (pass_core.h pass_is_fast: no control masks, register rounds only); 2 = LEAN: control masks,
+// but register rounds only (no dense or permutation round compiled in).  The kernel sits at the 128-register ceiling and
+// every feature in the shared source perturbs its register allocation, hence the leaner builds for the common passes.
+template <int T, int NR, int NO, int KIND>
 __global__ void __launch_bounds__(TmaCfg<T>::kThreads, 1)
 pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ state, const uint8_t* __restrict__ blob, const cplx* __restrict__ ext_tbl,
                 uint64_t rank_hi, int diag_mode, PassInit init, const __grid_constant__ TmaTile tt, const __grid_constant__ PassParams<NR, NO> P) {
     using Cfg = TmaCfg<T>;
+    constexpr bool FAST = KIND == 1, LEAN = KIND != 0;
     constexpr uint32_t kGT = Cfg::kGroupThreads, kNB = Cfg::kBuffers, kG = Cfg::kGroups;
     constexpr uint32_t kTileLen = 1u << T;
     constexpr int W = (NO + 31) / 32;
@@ -147,7 +151,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
     cplx* ext_phase2 = ext_all + (size_t)group * 2u * (n_diag + 1);
     const uint32_t n_ext_segs = P.hdr.n_ext_segs, n_rounds = P.hdr.n_rounds;
     const double final_scale = P.hdr.final_scale;
-    const bool last_is_reg = n_rounds && (FAST || P.rounds[n_rounds - 1].type != ROUND_DENSE);  // register or permutation round
+    const bool last_is_reg = n_rounds && (LEAN || P.rounds[n_rounds - 1].type != ROUND_DENSE);  // register or permutation round
     const bool direct = (P.hdr.flags & PASS_DIRECT_STORE) != 0 && !(diag_mode & 4) && last_is_reg;
     const bool need_base = direct || (P.hdr.ext_ctrl_mask[0] | P.hdr.ext_ctrl_mask[1] | P.hdr.ext_ctrl_mask[2]) != 0 || init.mode != 0;
     // Tiles of this CTA (tile ids and per-CTA counts fit 32 bits): the k-th tile it works on is
@@ -306,11 +310,11 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
 
         for (uint32_t r = 0; r < n_rounds; ++r) {
             const bool last = r + 1 == n_rounds;
-            if (FAST || P.rounds[r].type != ROUND_DENSE) {  // (FAST passes hold register rounds only: PASS_UNCONDITIONAL)
-                const bool perm = !FAST && P.rounds[r].type == ROUND_PERM;
+            if (LEAN || P.rounds[r].type != ROUND_DENSE) {  // (FAST and LEAN passes hold register rounds only)
+                const bool perm = !LEAN && P.rounds[r].type == ROUND_PERM;
                 const uint32_t lb = r < kLbTabRounds ? lbtab[r * kGT + gtid] : round_thread_base(P.rounds[r], gtid);
                 cplx a[kSlots];
-                if constexpr (!FAST) {
+                if constexpr (!LEAN) {
                     if (perm) round_perm_load<W, false>(P.rounds[r], P.ops, act, lb, tile, a);
                     else round_load(P.rounds[r], lb, tile, a);
                 } else {
@@ -341,7 +345,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
                 } else {
                     round_store_tile(P.rounds[r], lb, tile, a);
                 }
-            } else if constexpr (!FAST) {
+            } else if constexpr (!LEAN) {
                 const DevDense& D = *reinterpret_cast<const DevDense*>(blob + P.ops[P.rounds[r].first_op].dense_off);
                 cplx out[kSlots];
                 dense_compute(D, blob, gtid, tile, out);
@@ -435,7 +439,7 @@ constexpr size_t kSmemLimit = (size_t)227 * 1024;
 
 }  // namespace
 
-template <int T, int NR, int NO, bool FAST>
+template <int T, int NR, int NO, int KIND>
 static cudaError_t launch_tma_t(cplx* state, const uint8_t* dev_blob, const uint8_t* host_blob, const cplx* ext_tbl, uint64_t rank_hi, uint32_t n_alloc, int sm_count,
                                 const PassInit& init, cudaStream_t stream, const PassSlice* slice, int grid_sms) {
     using Cfg = TmaCfg<T>;
@@ -456,12 +460,13 @@ static cudaError_t launch_tma_t(cplx* state, const uint8_t* dev_blob, const uint
     if (err != cudaSuccess) return err;
     const size_t fixed = tma_fixed_smem<T>(hdr);
     int mode = (fixed + sizeof(cplx) * kDiagTblLen * hdr.n_diag <= kSmemLimit) ? 1 : 0;  // DIAG tables in shared memory when they fit
+    constexpr bool FAST = KIND == 1;
     if (FAST) mode = 2;
     if (hdr.n_diag == 0) mode = 0;
     const size_t smem = fixed + (mode == 1 ? sizeof(cplx) * kDiagTblLen * hdr.n_diag : mode == 2 ? sizeof(cplx) * Cfg::kGroupThreads * hdr.n_diag : 0);
     if (smem > kSmemLimit) return cudaErrorInvalidValue;
     static std::atomic<uint64_t> configured{0};
-    err = ensure_dynamic_smem(pass_kernel_tma<T, NR, NO, FAST>, (int)kSmemLimit, configured);
+    err = ensure_dynamic_smem(pass_kernel_tma<T, NR, NO, KIND>, (int)kSmemLimit, configured);
     if (err != cudaSuccess) return err;
     // tile interleave (see the kernel): the groups of a CTA take tiles with consecutive ids; QSV_TILE_INTERLEAVE=0 turns it off
     static const int interleave = getenv("QSV_TILE_INTERLEAVE") ? atoi(getenv("QSV_TILE_INTERLEAVE")) : 1;
@@ -474,7 +479,7 @@ static cudaError_t launch_tma_t(cplx* state, const uint8_t* dev_blob, const uint
     uint64_t grid = (uint64_t)(grid_sms > 0 && grid_sms < sm_count ? grid_sms : sm_count);
     if (grid > (n_tiles >> ilog)) grid = n_tiles >> ilog;
     static const int tma_store = getenv("QSV_TMA_STORE") ? atoi(getenv("QSV_TMA_STORE")) : 0;  // developer A/B switch: 1 = no register->global stores
-    pass_kernel_tma<T, NR, NO, FAST><<<(unsigned)grid, Cfg::kThreads, smem, stream>>>(map, state, dev_blob, ext_tbl, rank_hi, mode | (tma_store ? 4 : 0) | (int)(ilog << 8), init, desc.tile, params);
+    pass_kernel_tma<T, NR, NO, KIND><<<(unsigned)grid, Cfg::kThreads, smem, stream>>>(map, state, dev_blob, ext_tbl, rank_hi, mode | (tma_store ? 4 : 0) | (int)(ilog << 8), init, desc.tile, params);
     return cudaGetLastError();
 }
 
@@ -493,11 +498,17 @@ cudaError_t launch_pass_tma_tile<QSV_TILE_BITS>(cplx* state, const uint8_t* dev_
     using Cfg = TmaCfg<QSV_TILE_BITS>;
     const bool small = hdr.n_rounds <= (uint32_t)kSmallRounds && hdr.n_ops <= (uint32_t)kSmallOps;
     const size_t fast_smem = tma_fixed_smem<QSV_TILE_BITS>(hdr) + sizeof(cplx) * Cfg::kGroupThreads * hdr.n_diag;
-    static const bool no_fast = getenv("QSV_NO_FAST") != nullptr;  // developer A/B switch
+    static const bool no_fast = getenv("QSV_NO_FAST") != nullptr;  // developer A/B switches
+    static const bool no_lean = getenv("QSV_NO_LEAN") != nullptr;
     if (!no_fast && small && (hdr.flags & PASS_UNCONDITIONAL) && fast_smem <= kSmemLimit)
-        return launch_tma_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, true>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream, slice, grid_sms);
-    if (small) return launch_tma_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, false>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream, slice, grid_sms);
-    return launch_tma_t<QSV_TILE_BITS, kMaxRounds, kMaxOps, false>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream, slice, grid_sms);
+        return launch_tma_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, 1>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream, slice, grid_sms);
+    bool reg_only = true;  // every round a register round: the build without dense and permutation rounds
+    const DevRound* rounds = reinterpret_cast<const DevRound*>(host_blob + hdr.rounds_off);
+    for (uint32_t r = 0; r < hdr.n_rounds; ++r) reg_only &= rounds[r].type == ROUND_REG;
+    if (small && reg_only && !no_lean)
+        return launch_tma_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, 2>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream, slice, grid_sms);
+    if (small) return launch_tma_t<QSV_TILE_BITS, kSmallRounds, kSmallOps, 0>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream, slice, grid_sms);
+    return launch_tma_t<QSV_TILE_BITS, kMaxRounds, kMaxOps, 0>(state, dev_blob, host_blob, ext_tbl, rank_hi, n_alloc, sm_count, init, stream, slice, grid_sms);
 }
 
 }  // namespace qsv
