@@ -722,29 +722,33 @@ int qsv_create(qsv_state** out, uint32_t n_qubits, int device) {
     }
 }
 
+// Second half of creating a sharded handle: joins the communicator (collective over all ranks).
+static int attach_comm(qsv_state* s, const void* nccl_unique_id, size_t nccl_unique_id_bytes) {
+    QSV_CUDA(s, cudaSetDevice(s->device));
+    std::string err;
+    s->comm = shard_comm_create(s->rank, s->world, nccl_unique_id, nccl_unique_id_bytes, s->stream, err);
+    if (!s->comm) return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
+    // NCCL sets its connections up lazily inside the first collective (hundreds of ms): pay for it here, collectively,
+    // instead of inside whichever remap, norm or sample happens to come first
+    if (!shard_barrier(s->comm, err) || cudaStreamSynchronize(s->stream) != cudaSuccess)
+        return set_error(s, QSV_ERR_NCCL, "first collective on the new communicator failed: %s", err.c_str());
+    return qsv_init_basis(s, 0);
+}
+
 int qsv_create_sharded(qsv_state** out, uint32_t n_qubits, int device, int rank, int world, const void* nccl_unique_id, size_t nccl_unique_id_bytes) {
     try {
         if (world == 1) return qsv_create(out, n_qubits, device);
         int rc = create_common(out, n_qubits, device, rank, world);
         if (rc != QSV_OK) return rc;
         qsv_state* s = *out;
-        std::string err;
-        s->comm = shard_comm_create(rank, world, nccl_unique_id, nccl_unique_id_bytes, s->stream, err);
-        if (!s->comm) {
-            set_error(nullptr, QSV_ERR_NCCL, "%s", err.c_str());
+        rc = attach_comm(s, nccl_unique_id, nccl_unique_id_bytes);
+        if (rc != QSV_OK) {
+            const std::string msg = s->error;
             qsv_destroy(s);
             *out = nullptr;
-            return QSV_ERR_NCCL;
+            return set_error(nullptr, rc, "%s", msg.c_str());
         }
-        // NCCL sets its connections up lazily inside the first collective (hundreds of ms): pay for it here, collectively,
-        // instead of inside whichever remap, norm or sample happens to come first
-        if (!shard_barrier(s->comm, err) || cudaStreamSynchronize(s->stream) != cudaSuccess) {
-            set_error(nullptr, QSV_ERR_NCCL, "first collective on the new communicator failed: %s", err.c_str());
-            qsv_destroy(s);
-            *out = nullptr;
-            return QSV_ERR_NCCL;
-        }
-        return qsv_init_basis(s, 0);
+        return QSV_OK;
     } catch (...) {
         return set_error(nullptr, QSV_ERR_INTERNAL, "unexpected exception in qsv_create_sharded");
     }
@@ -781,13 +785,20 @@ int qsv_create_multi(qsv_state** out, uint32_t n_qubits, const int* devices, int
         front->pool = new MultiPool(n_devices);
         std::vector<std::string> msgs((size_t)n_devices);
         int failed = -1;
-        int rc = front->pool->run([&](int r) {  // collective: the ranks of one NCCL communicator, created side by side
+        // in two steps, so that a device that cannot even hold its shard does not leave the others waiting inside NCCL
+        int rc = front->pool->run([&](int r) {
             qsv_state* c = nullptr;
-            const int code = qsv_create_sharded(&c, n_qubits, devices[r], r, n_devices, id, sizeof(id));
+            const int code = create_common(&c, n_qubits, devices[r], r, n_devices);
             front->children[(size_t)r] = c;
             if (code != QSV_OK) msgs[(size_t)r] = qsv_last_error(nullptr);
             return code;
         }, &failed);
+        if (rc == QSV_OK)
+            rc = front->pool->run([&](int r) {  // collective: the ranks of one NCCL communicator, created side by side
+                const int code = attach_comm(front->children[(size_t)r], id, sizeof(id));
+                if (code != QSV_OK) msgs[(size_t)r] = front->children[(size_t)r]->error;
+                return code;
+            }, &failed);
         if (rc == QSV_OK)
             rc = front->pool->run([&](int r) {
                 const int code = attach_local_peers(front->children[(size_t)r], front->children);

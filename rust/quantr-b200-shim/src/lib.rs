@@ -113,9 +113,21 @@ impl DeviceState {
         }
     }
 
+    /// One GPU, or - with `QSV_DEVICES=0,1,..` (a power of two of devices) - one handle over several GPUs of this
+    /// process: the library shards the register itself (`qsv_create_multi`), `Circuit::simulate` never sees a device.
+    /// Registers too small to shard (fewer than four qubits per device) stay on the first device.
     pub fn new(num_qubits: usize) -> DeviceState {
         let mut handle = std::ptr::null_mut();
-        let code = unsafe { ffi::qsv_create(&mut handle, num_qubits as u32, 0) };
+        let mut devices: Vec<c_int> = std::env::var("QSV_DEVICES").ok()
+            .map(|v| v.split(',').filter_map(|x| x.trim().parse().ok()).collect()).unwrap_or_default();
+        while devices.len() > 1 && num_qubits < 4 + (usize::BITS - 1 - devices.len().leading_zeros()) as usize {
+            devices.truncate(devices.len() / 2);
+        }
+        let code = if devices.len() > 1 {
+            unsafe { ffi::qsv_create_multi(&mut handle, num_qubits as u32, devices.as_ptr(), devices.len() as c_int) }
+        } else {
+            unsafe { ffi::qsv_create(&mut handle, num_qubits as u32, devices.first().copied().unwrap_or(0)) }
+        };
         let s = DeviceState { handle, num_qubits, _not_sync: std::marker::PhantomData };
         s.check(code, "qsv_create");
         s
