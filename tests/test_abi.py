@@ -58,6 +58,34 @@ def test_create_fails_loudly_without_a_gpu():
         qb.Circuit.new(2).add_gate(qb.Gate.H, 0).simulate()
 
 
+def test_create_multi_validates_its_arguments_and_has_no_fallback(monkeypatch):
+    """qsv_create_multi (one handle over several GPUs of the process): argument errors are reported before any device
+    is touched; without a GPU it fails as loudly as qsv_create, through the reference-facing API (QSV_DEVICES) too."""
+    lib = F.load_library()
+    h = C.c_void_p()
+    dev3 = (C.c_int32 * 3)(0, 1, 2)
+    assert lib.qsv_create_multi(C.byref(h), 10, dev3, 3) == 1 and not h.value  # not a power of two
+    assert b"power of two" in lib.qsv_last_error(None)
+    dup = (C.c_int32 * 2)(1, 1)
+    assert lib.qsv_create_multi(C.byref(h), 10, dup, 2) == 1 and b"twice" in lib.qsv_last_error(None)
+    assert lib.qsv_create_multi(C.byref(h), 10, None, 2) == 1
+    assert lib.qsv_create_multi(None, 10, dup, 2) == 1
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    two = (C.c_int32 * 2)(0, 1)
+    rc = lib.qsv_create_multi(C.byref(h), 10, two, 2)
+    assert rc != 0 and not h.value
+    import quantr_b200 as qb
+    monkeypatch.setenv("QSV_DEVICES", "0,1")
+    with pytest.raises(F.QsvError):
+        qb.Circuit.new(8).add_gate(qb.Gate.H, 0).simulate()
+
+
 def test_null_handles_are_rejected():
     lib = F.load_library()
     assert lib.qsv_init_basis(None, 0) == 1
