@@ -70,6 +70,7 @@ struct qsv_state {
     std::vector<CachedPlan> plan_cache;
     uint64_t plan_stamp = 0;
     std::vector<double> last_step_ms;  // "timing" option: device time of every step of the last plan run
+    std::vector<cudaEvent_t> tev;      // pooled events of the "timing" option: one before every step + one after the last
     std::vector<cplx*> peer_ptr;  // peer-mapped shards (qsv_peer_import); empty = NCCL send/recv exchange
     // Pipelined exchange (run_overlapped): the remap runs slice by slice on a second stream while the passes next to it
     // work on the other slices.  Cross-GPU hand-shakes are flag words behind the shard (kFlagBytes after the amplitudes,
@@ -295,7 +296,7 @@ int run_exchange(qsv_state* s, const PlanStep& st, double* ms_out) {
         QSV_CUDA(s, cudaMalloc(&s->d_staging, want * 2));
         s->staging_bytes = want;
     }
-    if (s->timing) QSV_CUDA(s, cudaEventRecord(s->ev0, s->stream));
+    (void)ms_out;  // timed by the caller (run_plan_impl records an event before every step)
     std::string err;
     if (!s->peer_ptr.empty()) {
         // peer-memory path: barrier (every rank has finished the passes before the remap), one in-place swap kernel
@@ -324,13 +325,6 @@ int run_exchange(qsv_state* s, const PlanStep& st, double* ms_out) {
         }
     } else if (!shard_exchange_bits(s->comm, s->d_state, s->n_local, st.partner_bits.data(), g, s->d_staging, s->staging_bytes, err)) {
         return set_error(s, QSV_ERR_NCCL, "%s", err.c_str());
-    }
-    if (s->timing) {
-        QSV_CUDA(s, cudaEventRecord(s->ev1, s->stream));
-        QSV_CUDA(s, cudaEventSynchronize(s->ev1));
-        float ms = 0.f;
-        QSV_CUDA(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-        if (ms_out) *ms_out += ms;
     }
     return QSV_OK;
 }
@@ -464,6 +458,12 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
             if (grp.slice_next) in_group[i + 1] = 1, sliceable[i + 1] = 0;
         }
     }
+    const bool timed = s->timing || trace_passes;  // (no pipelined groups then: every step is timed on its own)
+    while (timed && s->tev.size() < plan.steps.size() + 1) {
+        cudaEvent_t ev;
+        QSV_CUDA(s, cudaEventCreate(&ev));
+        s->tev.push_back(ev);
+    }
     for (size_t i = 0; i < plan.steps.size(); ++i) {
         const PlanStep& st = plan.steps[i];
         if (in_group[i]) continue;  // runs slice by slice inside its remap's group
@@ -474,43 +474,34 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
             ++s->n_overlapped;
             continue;
         }
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        const bool timed = (s->timing || trace_passes) && st.kind == PlanStep::PASS;
-        if (timed) {
-            cudaEventCreate(&e0);
-            cudaEventCreate(&e1);
-            cudaEventRecord(e0, s->stream);
-        }
+        if (timed) QSV_CUDA(s, cudaEventRecord(s->tev[i], s->stream));
         if (st.kind == PlanStep::PASS) {
-            const uint8_t* dev_pass = static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_offsets[st.pass_index];
-            const cplx* ext_tbl = plan.dev_tbl_offsets[st.pass_index] == SIZE_MAX
-                                      ? nullptr
-                                      : reinterpret_cast<const cplx*>(static_cast<const uint8_t*>(plan.dev_blob) + plan.dev_tbl_offsets[st.pass_index]);
-            QSV_CUDA(s, launch_pass(s->d_state, dev_pass, plan.passes[st.pass_index].data(), ext_tbl, rank_base(s), s->n_alloc, s->sm_count,
-                                    (i == 0 && fused_init) ? &pass_init : nullptr, s->stream));
+            rc = launch_pass_step(s, plan, st.pass_index, (i == 0 && fused_init) ? &pass_init : nullptr, nullptr, 0);
+            if (rc != QSV_OK) return rc;
         } else {
-            const double before = exch_ms;
-            rc = run_exchange(s, st, &exch_ms);
+            rc = run_exchange(s, st, nullptr);
             if (rc != QSV_OK) return rc;
             ++n_exch;
-            if (s->timing) s->last_step_ms.push_back(exch_ms - before);
         }
-        if (timed) {
-            cudaEventRecord(e1, s->stream);
-            cudaEventSynchronize(e1);
+    }
+    if (timed) {
+        // "timing": events around every step, read after ONE host synchronisation at the end (the steps run back to back
+        // as in an untimed run; round 1 synchronised after every pass)
+        QSV_CUDA(s, cudaEventRecord(s->tev[plan.steps.size()], s->stream));
+        QSV_CUDA(s, cudaEventSynchronize(s->tev[plan.steps.size()]));
+        for (size_t i = 0; i < plan.steps.size(); ++i) {
+            const PlanStep& st = plan.steps[i];
             float ms = 0.f;
-            cudaEventElapsedTime(&ms, e0, e1);
-            pass_ms += ms;
+            QSV_CUDA(s, cudaEventElapsedTime(&ms, s->tev[i], s->tev[i + 1]));
+            if (st.kind == PlanStep::PASS) pass_ms += ms; else exch_ms += ms;
             if (s->timing) s->last_step_ms.push_back(ms);
-            if (trace_passes) {
+            if (trace_passes && st.kind == PlanStep::PASS) {
                 const DevPass& h = *reinterpret_cast<const DevPass*>(plan.passes[st.pass_index].data());
                 int run_bits = 0;
                 if (h.n_tile_segs && h.tile_segs[0].dst_lo == 0) run_bits = h.tile_segs[0].width;
                 fprintf(stderr, "[qsv] pass %u: T=%u run=%uB rounds=%u ops=%u diag=%u flags=%u  %.3f ms  %.0f GB/s\n", st.pass_index, h.tile_bits, 16u << run_bits,
                         h.n_rounds, h.n_ops, h.n_diag, h.flags, ms, 32.0 * (double)(1ull << s->n_alloc) / (ms * 1e-3) / 1e9);
             }
-            cudaEventDestroy(e0);
-            cudaEventDestroy(e1);
         }
     }
     set_layout(s, plan.final_layout.data());
@@ -888,6 +879,7 @@ int qsv_destroy(qsv_state* s) {
     if (s->d_scratch) cudaFree(s->d_scratch);
     for (auto& e : s->plan_cache) qsv_plan_destroy(e.plan);
     for (cudaEvent_t ev : s->xev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : s->tev) cudaEventDestroy(ev);
     if (s->xstream) cudaStreamDestroy(s->xstream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
