@@ -45,7 +45,6 @@ struct qsv_state {
     uint32_t block_bits = 0;
     bool prefix_valid = false;
     double total_prob = 0.0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ShardComm* comm = nullptr;
     // layout[b] = physical position of logical index bit b (positions >= n_local live in the rank id)
     uint8_t layout[64];
@@ -222,8 +221,6 @@ int create_common(qsv_state** out, uint32_t n_qubits, int device, int rank, int 
     if (const char* env = getenv("QSV_OVERLAP")) s->overlap = atoi(env) != 0;
     if (const char* env = getenv("QSV_XCHG_SMS")) s->xchg_sms = atoi(env);
     if (const char* env = getenv("QSV_XCHG_SLICES_LOG2")) s->xchg_slices_log2 = atoi(env);
-    cudaEventCreate(&s->ev0);
-    cudaEventCreate(&s->ev1);
     set_layout(s, nullptr);
     *out = s;
     return QSV_OK;
@@ -881,8 +878,6 @@ int qsv_destroy(qsv_state* s) {
     for (cudaEvent_t ev : s->xev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : s->tev) cudaEventDestroy(ev);
     if (s->xstream) cudaStreamDestroy(s->xstream);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return QSV_OK;
