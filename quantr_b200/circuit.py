@@ -344,12 +344,18 @@ class Plan:
             out.append(("pass", pidx.value) if kind.value == 0 else ("exchange", [partners[j] for j in range(g)]))
         return out
 
+    def prefix_local_bits(self) -> int:
+        """Top local index bits the plan's folded prefix spreads the basis state over (Plan::prefix_local_bits)."""
+        return int(self.describe().get("prefix_local_bits", 0))
+
     def initial_amplitudes(self, basis_index: int) -> np.ndarray:
-        """Amplitude of every rank when the plan starts from the basis state `basis_index` (see qsv_plan_initial_amplitudes)."""
-        world = 1 << (self.n_qubits - self.n_local)
-        out = np.zeros(world, dtype=np.complex128)
+        """The 2^(g + prefix_local_bits) amplitudes the plan starts from when the register is the basis state `basis_index`:
+        entry j sits at the physical index whose top bits spell j (rank id first), the other bits as in the basis state
+        (see qsv_plan_initial_amplitudes).  Without a folded prefix: one entry per rank."""
+        count = 1 << (self.n_qubits - self.n_local + self.prefix_local_bits())
+        out = np.zeros(count, dtype=np.complex128)
         self.lib.qsv_plan_initial_amplitudes.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_double), C.c_size_t]
-        F.check_plan(self.lib.qsv_plan_initial_amplitudes(self.handle, basis_index, out.ctypes.data_as(C.POINTER(C.c_double)), world), self.lib)
+        F.check_plan(self.lib.qsv_plan_initial_amplitudes(self.handle, basis_index, out.ctypes.data_as(C.POINTER(C.c_double)), count), self.lib)
         return out
 
     def layout(self, final: bool = False) -> list:

@@ -193,6 +193,16 @@ cudaError_t launch_peer_swap(cplx* local, cplx* remote, uint32_t n_local, const 
     return cudaGetLastError();
 }
 
+// A folded prefix written to HBM (registers whose first pass cannot synthesise it): state[(j << shift) | low] = tbl[j].
+__global__ void scatter_prefix_kernel(cplx* __restrict__ state, const cplx* __restrict__ tbl, uint64_t count, uint32_t shift, uint64_t low) {
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) state[(j << shift) | low] = tbl[j];
+}
+cudaError_t launch_scatter_prefix(cplx* state, const cplx* tbl, uint32_t sup_bits, uint32_t n_local, uint64_t low, cudaStream_t stream) {
+    const uint64_t count = 1ull << sup_bits;
+    scatter_prefix_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(state, tbl, count, n_local - sup_bits, low);
+    return cudaGetLastError();
+}
+
 // Cross-GPU flags of the pipelined exchange.  A wait that outlasts any legitimate exchange (seconds) traps so that a
 // protocol error surfaces as a launch failure instead of a hung device.
 __global__ void flag_signal_kernel(FlagPeers peers, int world, uint32_t index, uint32_t value) {

@@ -56,6 +56,8 @@ template <int TILE_BITS>
 bool pass_tma_supported_tile(const uint8_t* host_blob, uint32_t n_alloc);
 
 cudaError_t launch_set_amp(cplx* state, uint64_t index, double re, double im, cudaStream_t stream);
+// state[(j << (n_local - sup_bits)) | low] = tbl[j], j < 2^sup_bits: the amplitudes a folded prefix left (Plan::prefix_local_bits)
+cudaError_t launch_scatter_prefix(cplx* state, const cplx* tbl, uint32_t sup_bits, uint32_t n_local, uint64_t low, cudaStream_t stream);
 // in-place swap of this rank's block 'spelled' peer with the peer's block 'spelled' rank (peer-mapped memory, NVLink)
 // slice: null, or the part of the shard to swap (the blocks' amplitudes whose index bits slice->bit[] spell slice->value)
 cudaError_t launch_peer_swap(cplx* local, cplx* remote, uint32_t n_local, const uint8_t* partner, uint32_t g, int rank, int peer, int sm_count, cudaStream_t stream,

@@ -290,11 +290,32 @@ struct PassInit {
     uint32_t holds_here; // the tile lies in this rank's shard
     uint32_t n_alloc;    // log2 of the shard length
     double amp_re, amp_im;  // the amplitude (1 unless a sharded plan folded leading gates into the initial state, plan.h Plan::prefix)
+    // A folded prefix on the top `sup_bits` local index bits (Plan::prefix_local_bits): the register holds 2^sup_bits
+    // amplitudes, amp_tbl[j] at the local index whose top sup_bits bits spell j and whose other bits are those of `x_local`.
+    uint32_t sup_bits;
+    uint32_t sup_local_mask;  // the support bits that are tile bits of this pass, as a tile-local mask
+    uint64_t sup_mask;        // the support bits (local index positions)
+    uint64_t x_local;         // local index of the basis state
+    const cplx* amp_tbl;
 };
-inline PassInit make_pass_init(const DevPass& hdr, uint64_t phys_index, uint32_t n_local, uint32_t mode) {
+// does the tile at `base_full` hold a non-zero amplitude of the initial state?
+QSV_HD bool init_tile_holds(const PassInit& pi, uint64_t base_full) { return ((base_full ^ pi.base_full) & ~pi.sup_mask) == 0; }
+// initial amplitude of tile-local element l of a holding tile at local base `base` (tile_segs: the pass's tile bits)
+QSV_HD cplx init_tile_element(const PassInit& pi, const DevPass& hdr, uint64_t base, uint32_t l) {
+    if (((l ^ pi.local) & ~pi.sup_local_mask) != 0) return cplx{0.0, 0.0};
+    if (pi.sup_bits == 0) return cplx{pi.amp_re, pi.amp_im};
+    const uint64_t p = base | (pi.sup_local_mask ? deposit(l, hdr.tile_segs, hdr.n_tile_segs) : 0ull);
+    return pi.amp_tbl[(p & pi.sup_mask) >> (pi.n_alloc - pi.sup_bits)];
+}
+inline PassInit make_pass_init(const DevPass& hdr, uint64_t phys_index, uint32_t n_local, uint32_t mode, uint32_t sup_bits = 0, const cplx* amp_tbl = nullptr) {
     const uint64_t local_mask = (1ull << n_local) - 1ull;
     const uint64_t ext_mask = deposit(hdr.n_tiles - 1ull, hdr.ext_segs, hdr.n_ext_segs);
     PassInit pi;
+    pi.sup_bits = sup_bits;
+    pi.sup_mask = sup_bits ? (((1ull << sup_bits) - 1ull) << (n_local - sup_bits)) : 0ull;
+    pi.sup_local_mask = (uint32_t)extract(pi.sup_mask, hdr.tile_segs, hdr.n_tile_segs);
+    pi.x_local = phys_index & local_mask;
+    pi.amp_tbl = amp_tbl;
     pi.base_full = (phys_index & local_mask & ext_mask) | (phys_index & ~local_mask);
     pi.local = (uint32_t)extract(phys_index & local_mask, hdr.tile_segs, hdr.n_tile_segs);
     pi.mode = mode;

@@ -215,7 +215,9 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
     // and computed by the group it falls to in the loop below.
     if (init.mode == 2) {
         const uint64_t n_rows = 1ull << (init.n_alloc - 3);
-        const uint64_t row_mask = init.ext_mask >> 3, row_hold = (init.base_full & init.ext_mask & ((1ull << init.n_alloc) - 1ull)) >> 3;
+        // (with a folded prefix on the top local bits several tiles hold amplitudes: their rows differ in the support bits only)
+        const uint64_t hold_mask = init.ext_mask & ~init.sup_mask;
+        const uint64_t row_mask = hold_mask >> 3, row_hold = (init.base_full & hold_mask & ((1ull << init.n_alloc) - 1ull)) >> 3;
         const bool here = (init.base_full >> init.n_alloc) == (rank_hi >> init.n_alloc);
         const uint64_t rows_per_cta = (n_rows + gridDim.x - 1) / gridDim.x;
         const uint64_t r0 = rows_per_cta * blockIdx.x, r1 = r0 + rows_per_cta < n_rows ? r0 + rows_per_cta : n_rows;
@@ -271,7 +273,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
         const DiagCtx ctx{blob, ext_phase, (diag_mode & 3) == 1 ? diag_smem : nullptr, (diag_mode & 3) == 2 ? diag_smem : nullptr, kGT};
         cplx* tile;
         if (init.mode) {
-            const bool holds = base_full == init.base_full;  // uniform over the group
+            const bool holds = init_tile_holds(init, base_full);  // uniform over the group
             if (init.mode == 2 && !holds) continue;  // zero tile in, zero tile out: written by the stream above
             tile = tiles + (size_t)group * kTileLen;
             if (gtid < 32u && refill_pending) {  // the group's previous tile left through this buffer: wait until the bulk store has read it
@@ -283,8 +285,7 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
             char* tb = reinterpret_cast<char*>(tile);
 #pragma unroll
             for (uint32_t i = 0; i < (uint32_t)kSlots; ++i)
-                *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) =
-                    (holds && i * kGT + gtid == init.local) ? cplx{init.amp_re, init.amp_im} : cplx{0.0, 0.0};
+                *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) = holds ? init_tile_element(init, P.hdr, base, i * kGT + gtid) : cplx{0.0, 0.0};
             for (uint32_t o = gtid; o < P.hdr.n_ops; o += kGT)
                 if (P.ops[o].type == OP_DIAG) ext_phase[P.ops[o].diag_index] = diag_ext_phase(P.ops[o], blob, base_full);
         } else {

@@ -916,22 +916,39 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
     // product state, so the host applies them to the 2^g rank amplitudes at run time; if that prefix contains a
     // non-diagonal gate the canonical layout is kept and the prefix leaves the schedule.  QFT-n on 2^g ranks then needs
     // no remap at all (its first g stages are the prefix, every later stage is local).
+    // The same holds for the top LOCAL qubits (large registers only, PlanOptions::prefix_min_local): after leading ops on
+    // the top g + k index bits the state has 2^(g+k) non-zero amplitudes, which the host computes and the first pass
+    // synthesises instead of reading the register (k <= kMaxPrefixLocalBits).  QFT-33 from a basis state: 14 stages folded,
+    // the remaining 19 are one write-only pass (8 stages) and one pass over the contiguous low bits (11 stages).
     plan.prefix.clear();
-    if (plan.free_initial_layout && g > 0 && plan.opt.fold_prefix && plan.opt.fuse) {
-        const uint64_t rank_mask = (((1ull << g) - 1ull) << n_local);
-        size_t len = 0;
-        bool has_mat = false;
-        while (len < plan.lops.size()) {
-            const LOp& lop = plan.lops[len];
-            if (lop.kind == LOp::DENSE || (lop.targets() & ~rank_mask)) break;
-            has_mat |= lop.kind == LOp::MAT;
-            ++len;
-        }
-        while (len > 0 && plan.lops[len - 1].kind == LOp::DIAG) --len;  // trailing diagonals stay in the schedule (they fuse for free)
-        if (has_mat && len > 0) {
-            plan.prefix.assign(plan.lops.begin(), plan.lops.begin() + (long)len);
-            plan.lops.erase(plan.lops.begin(), plan.lops.begin() + (long)len);
-            for (int b = 0; b < 64; ++b) layout[b] = (uint8_t)b;  // canonical layout
+    plan.prefix_local_bits = 0;
+    if (free_layout && initial_layout == nullptr && plan.opt.fold_prefix && plan.opt.fuse) {
+        int k_max = 0;
+        if ((int)n_local >= plan.opt.prefix_min_local && (int)n_local == nloc) k_max = std::min<int>(kMaxPrefixLocalBits, (int)n_local - 12);
+        if (k_max < 0) k_max = 0;
+        if (g > 0 || k_max > 0) {
+            const uint64_t support = (((1ull << (g + k_max)) - 1ull) << ((int)n_local - k_max));
+            size_t len = 0;
+            bool has_mat = false;
+            while (len < plan.lops.size()) {
+                const LOp& lop = plan.lops[len];
+                if (lop.kind == LOp::DENSE || (lop.targets() & ~support)) break;
+                has_mat |= lop.kind == LOp::MAT;
+                ++len;
+            }
+            while (len > 0 && plan.lops[len - 1].kind == LOp::DIAG) --len;  // trailing diagonals stay in the schedule (they fuse for free)
+            if (has_mat && len > 0) {
+                uint64_t touched = 0;
+                for (size_t i = 0; i < len; ++i) touched |= plan.lops[i].targets();
+                int lowest = n;  // lowest targeted bit: the support is the contiguous block of top bits down to it
+                for (int b = 0; b < n; ++b)
+                    if ((touched >> b) & 1) { lowest = b; break; }
+                plan.prefix_local_bits = lowest < (int)n_local ? (uint32_t)((int)n_local - lowest) : 0u;
+                plan.prefix.assign(plan.lops.begin(), plan.lops.begin() + (long)len);
+                plan.lops.erase(plan.lops.begin(), plan.lops.begin() + (long)len);
+                for (int b = 0; b < 64; ++b) layout[b] = (uint8_t)b;  // canonical layout
+                plan.free_initial_layout = g > 0;
+            }
         }
     }
     plan.initial_layout.assign(layout.begin(), layout.begin() + n);
@@ -1252,19 +1269,21 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
 }
 
 void prefix_amplitudes(const Plan& plan, uint64_t basis_index, std::vector<cplx>& out) {
-    const uint32_t n = plan.n_qubits, nl = plan.n_local, g = n - nl;
-    const uint64_t P = 1ull << g;
+    const uint32_t n = plan.n_qubits, g = n - plan.n_local;
+    const uint32_t nl = plan.n_local - plan.prefix_local_bits;  // bits below the support: constants of the basis state
+    const uint64_t P = 1ull << (n - nl);
     out.assign(P, cplx{0.0, 0.0});
     // physical index of the basis state under the initial layout
     uint64_t phys = 0;
     for (uint32_t b = 0; b < n; ++b) phys |= ((basis_index >> b) & 1ull) << plan.initial_layout[b];
     out[phys >> nl] = cplx{1.0, 0.0};
+    (void)g;
     if (plan.prefix.empty()) return;
-    // the prefix exists only under the canonical layout: logical bit = physical bit; local bits are constants
+    // the prefix exists only under the canonical layout: logical bit = physical bit; the bits below the support are constants
     const uint64_t local = phys & ((1ull << nl) - 1ull), rank_mask = (P - 1ull) << nl;
     for (const LOp& op : plan.prefix) {
         if (op.kind == LOp::MAT) {
-            const bool local_sat = (local & op.cmask & ~rank_mask) == (op.cmask & ~rank_mask);  // controls on local bits (constants here)
+            const bool local_sat = (local & op.cmask & ~rank_mask) == (op.cmask & ~rank_mask);  // controls on the constant bits
             if (!local_sat && !op.dual) continue;
             const uint64_t cm = (op.cmask & rank_mask) >> nl, tb = 1ull << (op.target - (int)nl);
             for (uint64_t r = 0; r < P; ++r) {
@@ -1337,7 +1356,8 @@ std::string describe_plan(const Plan& plan) {
     std::ostringstream os;
     os << "{\"n_qubits\":" << plan.n_qubits << ",\"n_local\":" << plan.n_local << ",\"n_alloc\":" << plan.n_alloc
        << ",\"tile_bits\":" << std::min<int>(plan.opt.tile_bits, (int)plan.n_alloc) << ",\"low_bits\":" << plan.opt.low_bits
-       << ",\"n_gates\":" << plan.n_gates << ",\"n_lowered_ops\":" << plan.lops.size() << ",\"prefix_ops\":" << plan.prefix.size();
+       << ",\"n_gates\":" << plan.n_gates << ",\"n_lowered_ops\":" << plan.lops.size() << ",\"prefix_ops\":" << plan.prefix.size()
+       << ",\"prefix_local_bits\":" << plan.prefix_local_bits;
     size_t n_dual = 0;
     for (const LOp& lop : plan.lops) n_dual += lop.kind == LOp::MAT && lop.dual;
     os << ",\"n_dual_ops\":" << n_dual << ",\"passes\":[";

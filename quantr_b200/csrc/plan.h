@@ -14,6 +14,8 @@
 
 namespace qsv {
 
+constexpr int kMaxPrefixLocalBits = 14;  // local index bits a folded prefix may spread the basis state over (a 256 KiB table per rank)
+
 // A gate lowered to physical-bit space (bit = n-1-wire).
 struct LOp {
     enum Kind { MAT, DIAG, DENSE } kind = MAT;
@@ -46,7 +48,8 @@ struct PlanOptions {
     int direct_store = 1; // last round stores registers straight to global memory when that stays coalesced
     int qft4 = 1;         // whole QFT-ladder rounds become one radix-16 macro-op (pass_core.h qft4_apply)
     int big_low_pass = 1; // a pass over the contiguous low index bits may use a 2^12 tile next to 2^11 strided passes
-    int fold_prefix = 1;  // sharded basis states: leading gates on the qubits held in the rank id are applied on the host (build_plan)
+    int fold_prefix = 1;  // basis states: leading gates on the top qubits (rank id + up to kMaxPrefixLocalBits local ones) are applied on the host (build_plan)
+    int prefix_min_local = 23;  // ... local qubits are folded only on registers of at least this many local qubits (small ones: not worth a table upload per run)
     int reorder = 1;      // passes take later ops that commute with the ops they had to leave behind (plan.cpp schedule)
     int merge_1q = 1;     // 2x2 gates on the same target and controls are multiplied together across commuting ops; identities vanish
     int perm_rounds = 1;  // runs of X / CNot / Toffoli gates on more than four targets become one gather through the tile (ROUND_PERM)
@@ -77,6 +80,11 @@ struct Plan {
     // of rank amplitudes when the plan runs (prefix_amplitudes) instead of forcing a global-qubit remap.  Logical bit
     // space; empty = none.  A plan with a prefix needs a register that is a basis state.
     std::vector<LOp> prefix;
+    // ... and, on registers of prefix_min_local qubits or more, on the top `prefix_local_bits` LOCAL index bits as well: the
+    // state after the prefix has 2^(g + prefix_local_bits) non-zero amplitudes - every combination of those top bits, the
+    // other bits as in the basis state - which the host computes (prefix_amplitudes) and the first pass synthesises
+    // (PassInit::amp_tbl) or a scatter kernel writes.  QFT-33 from a basis state: 14 of its 33 stages cost nothing.
+    uint32_t prefix_local_bits = 0;
     uint64_t n_gates = 0, n_rounds = 0;
     // device residency (owned by the state API)
     void* dev_blob = nullptr;
@@ -94,9 +102,9 @@ void merge_single_qubit_gates(std::vector<LOp>& lops, bool merge_ctrl = true);
 void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* ops, size_t n_ops, const PlanOptions& opt,
                 const uint8_t* initial_layout = nullptr, bool free_layout = false);
 std::string describe_plan(const Plan& plan);
-// Amplitude of every rank (2^g complex values, index = rank id under the plan's initial layout) after the plan's prefix
-// has been applied to the basis state `basis_index` (canonical index); all amplitudes sit at the same local index.
-// Without a prefix: 1 on the rank that holds the basis state.
+// The 2^(g + prefix_local_bits) amplitudes after the plan's prefix has been applied to the basis state `basis_index`
+// (canonical index): entry j belongs to the physical index whose top g + prefix_local_bits bits spell j (rank id first)
+// and whose other bits are the basis state's.  Without a prefix: 1 on the rank that holds the basis state (2^g entries).
 void prefix_amplitudes(const Plan& plan, uint64_t basis_index, std::vector<cplx>& out);
 
 // Pipelined exchange (state_api.cu run_overlapped): an EXCHANGE step can run slice by slice against the pass before it

@@ -145,12 +145,17 @@ void set_layout(qsv_state* s, const uint8_t* layout) {
 // Writes a pending basis state to HBM (under the current layout).
 // `amp` (optional): this rank's amplitude at the basis state's local index when a sharded plan folded its leading
 // gates into the initial state (Plan::prefix); default: 1 on the rank that holds the basis state.
-int materialize(qsv_state* s, const cplx* amp = nullptr) {
+// `tbl` / `sup_bits` (optional): the plan folded gates on the top sup_bits local qubits as well (Plan::prefix_local_bits);
+// tbl = this rank's 2^sup_bits amplitudes in device memory.
+int materialize(qsv_state* s, const cplx* amp = nullptr, const cplx* tbl = nullptr, uint32_t sup_bits = 0) {
     if (!s->lazy_basis) return QSV_OK;
     s->lazy_basis = false;
     QSV_CUDA(s, cudaMemsetAsync(s->d_state, 0, sizeof(cplx) << s->n_alloc, s->stream));
     const uint64_t phys = to_physical(s, s->lazy_index);
-    if (amp) {
+    if (tbl && sup_bits) {
+        const uint64_t low = phys & ((1ull << (s->n_local - sup_bits)) - 1ull);
+        QSV_CUDA(s, launch_scatter_prefix(s->d_state, tbl, sup_bits, s->n_local, low, s->stream));
+    } else if (amp) {
         if (amp->x != 0.0 || amp->y != 0.0) QSV_CUDA(s, launch_set_amp(s->d_state, phys & (local_len(s) - 1), amp->x, amp->y, s->stream));
     } else if ((phys >> s->n_local) == (uint64_t)s->rank) {
         QSV_CUDA(s, launch_set_amp(s->d_state, phys & (local_len(s) - 1), 1.0, 0.0, s->stream));
@@ -403,11 +408,23 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     // then starts from its own amplitude at the basis state's local index
     cplx rank_amp{1.0, 0.0};
     const bool folded = !plan.prefix.empty();
+    const uint32_t sup_bits = folded ? plan.prefix_local_bits : 0u;
+    cplx* d_tbl = nullptr;
+    int rc = QSV_OK;
     if (folded) {
         if (!s->lazy_basis) return set_error(s, QSV_ERR_INVALID_ARG, "this plan was built for a register that is a basis state (qsv_init_basis)");
         std::vector<cplx> amps;
         prefix_amplitudes(plan, s->lazy_index, amps);
-        rank_amp = amps[(size_t)s->rank];
+        if (sup_bits == 0) {
+            rank_amp = amps[(size_t)s->rank];
+        } else {  // this rank's 2^sup_bits amplitudes go to the device: the first pass synthesises its tiles from them
+            const size_t count = (size_t)1 << sup_bits;
+            rc = ensure_scratch(s, sizeof(cplx) * count);
+            if (rc != QSV_OK) return rc;
+            d_tbl = static_cast<cplx*>(s->d_scratch);
+            QSV_CUDA(s, cudaMemcpyAsync(d_tbl, amps.data() + (size_t)s->rank * count, sizeof(cplx) * count, cudaMemcpyHostToDevice, s->stream));
+            QSV_CUDA(s, cudaStreamSynchronize(s->stream));  // `amps` goes out of scope
+        }
     }
     // Fused initialisation (pass_kernel_tma.cu): a pending basis state is not written to HBM when the plan's first step is
     // a pass the pipelined kernel runs; that pass synthesises the one tile holding the amplitude and writes every other
@@ -420,14 +437,14 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
         const DevPass& h0 = *reinterpret_cast<const DevPass*>(plan.passes[plan.steps[0].pass_index].data());
         uint64_t phys = to_physical(s, s->lazy_index);
         if (folded) phys = (phys & (local_len(s) - 1)) | rank_base(s);  // every rank holds an amplitude at that local index
-        pass_init = make_pass_init(h0, phys, s->n_local, fused_init_mode >= 2 ? 2u : 1u);
+        pass_init = make_pass_init(h0, phys, s->n_local, fused_init_mode >= 2 ? 2u : 1u, sup_bits, d_tbl);
         pass_init.amp_re = rank_amp.x;
         pass_init.amp_im = rank_amp.y;
-        if (rank_amp.x == 0.0 && rank_amp.y == 0.0) pass_init.base_full = ~0ull;  // nothing to synthesise: the shard is all zero
+        if (sup_bits == 0 && rank_amp.x == 0.0 && rank_amp.y == 0.0) pass_init.base_full = ~0ull;  // nothing to synthesise: the shard is all zero
         fused_init = true;
         s->lazy_basis = false;
     }
-    int rc = materialize(s, folded ? &rank_amp : nullptr);
+    rc = materialize(s, folded ? &rank_amp : nullptr, d_tbl, sup_bits);
     if (rc != QSV_OK) return rc;
     rc = upload_plan(s, p);
     if (rc != QSV_OK) return rc;

@@ -99,7 +99,7 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
         const uint64_t base = deposit(t, P.hdr.ext_segs, P.hdr.n_ext_segs);
         if (tma && tma_tile_base(desc.tile, (uint32_t)t) != base) __builtin_trap();  // the kernel derives the tile base from the tile id fields
         const uint64_t base_full = base | rank_hi;
-        const bool holds = init && base_full == init->base_full;
+        const bool holds = init && init_tile_holds(*init, base_full);
         if (init && init->mode == 2 && !holds && tma) {  // bulk store from the zeroed buffer
             memset(tile.data(), 0, sizeof(cplx) * tile_len);
             tma_move(t, true);
@@ -120,7 +120,7 @@ static void run_pass(const uint8_t* blob, cplx* state, uint64_t rank_hi, const P
             const uint32_t soff_t = swz(tid) << 4;
             for (uint32_t i = 0; i < n_loads; ++i)
                 if (i * threads + tid < tile_len) {
-                    cplx v = init ? ((holds && i * threads + tid == init->local) ? cplx{init->amp_re, init->amp_im} : cplx{0.0, 0.0})  // synthesised, the register is not read
+                    cplx v = init ? (holds ? init_tile_element(*init, P.hdr, base, i * threads + tid) : cplx{0.0, 0.0})  // synthesised, the register is not read
                                   : state[base + goff_t + P.loads.goff[i]];
                     *reinterpret_cast<cplx*>(tb + (soff_t ^ P.loads.soff[i])) = v;
                 }
@@ -295,7 +295,18 @@ extern "C" int qsv_emu_run_plan_fused_init(const qsv_plan* p, double* amps, uint
     for (const PlanStep& st : p->plan.steps) {
         const uint8_t* blob = p->plan.passes[st.pass_index].data();
         if (first) {
-            const PassInit pi = make_pass_init(*reinterpret_cast<const DevPass*>(blob), phys_index, p->plan.n_local, mode);
+            // a plan with a folded prefix starts from the prefix's amplitudes (canonical layout: phys_index is the basis index)
+            std::vector<cplx> tbl;
+            PassInit pi;
+            if (!p->plan.prefix.empty()) {
+                prefix_amplitudes(p->plan, phys_index, tbl);
+                const uint32_t k = p->plan.prefix_local_bits;
+                pi = make_pass_init(*reinterpret_cast<const DevPass*>(blob), (phys_index & ((1ull << p->plan.n_local) - 1ull)) | rank_hi, p->plan.n_local, mode, k,
+                                    k ? tbl.data() + ((size_t)rank << k) : nullptr);
+                if (k == 0) { pi.amp_re = tbl[(size_t)rank].x; pi.amp_im = tbl[(size_t)rank].y; }
+            } else {
+                pi = make_pass_init(*reinterpret_cast<const DevPass*>(blob), phys_index, p->plan.n_local, mode);
+            }
             run_pass(blob, reinterpret_cast<cplx*>(amps), rank_hi, &pi, p->plan.n_alloc);
             first = false;
         } else {

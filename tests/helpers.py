@@ -295,9 +295,10 @@ def emu_simulate_sharded(n, enc, world, *, basis_index=0, register=None, tile_bi
     if register is None:
         # every rank starts from its own amplitude at the basis state's local index (one rank holds 1 unless the plan
         # folded the circuit's leading gates on the rank-id qubits into the initial state)
-        local = logical_to_physical(basis_index, lay0) & ((1 << nl) - 1)
-        for r, a in enumerate(plan.initial_amplitudes(basis_index)):
-            full[(r << nl) | local] = a
+        k = plan.prefix_local_bits()  # the folded prefix may also cover the top k local bits
+        low = logical_to_physical(basis_index, lay0) & ((1 << (nl - k)) - 1)
+        for j, a in enumerate(plan.initial_amplitudes(basis_index)):
+            full[(j << (nl - k)) | low] = a
     else:
         assert lay0 == list(range(n))
         full[:] = register

@@ -273,3 +273,59 @@ def test_permutation_rounds_for_runs_of_x_gates():
             assert np.max(np.abs(out - ref)) < 1e-12, (trial, tile_bits, low_bits)
             seen_perm += sum(1 for p in desc["passes"] for r in p["rounds"] if r["type"] == 2)
     assert seen_perm > 0
+
+
+@pytest.mark.parametrize("n,world,tile_bits,low_bits,mode,tma", [(16, 1, 6, 2, 2, 0), (16, 1, 8, 3, 1, 0), (17, 1, 11, 3, 2, 1), (16, 1, 11, 4, 2, 1),
+                                                               (17, 2, 7, 3, 2, 0), (18, 4, 11, 3, 2, 1)])
+def test_prefix_folded_over_the_top_local_qubits(n, world, tile_bits, low_bits, mode, tma, monkeypatch):
+    """Leading gates on the top qubits of a basis state - the rank-id qubits and up to 14 local ones - see a product state:
+    the host applies them to the 2^(g+k) non-zero amplitudes (plan.cpp prefix_amplitudes) and the first pass synthesises its
+    tiles from that table (PassInit::amp_tbl) instead of reading the register; QFT-33 drops from 4 passes to 2.  Checked here
+    on small registers (QSV_PREFIX_MIN_LOCAL=0) for QFT and for random circuits (support bits inside and outside the first
+    pass's tile), fused initialisation in every mode and through the tensor-map walk; buffers start as NaN."""
+    import ctypes as C
+    from helpers import emu_lib, emu_simulate_sharded
+    monkeypatch.setenv("QSV_PREFIX_MIN_LOCAL", "0")
+    lib = emu_lib()
+    lib.qsv_emu_run_plan_fused_init.restype = C.c_int
+    lib.qsv_emu_run_plan_fused_init.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint64, C.c_uint64, C.c_uint32]
+    lib.qsv_emu_set_tma_mode(tma)
+    try:
+        rng = np.random.default_rng(n * 7 + world)
+        g = world.bit_length() - 1
+        nl = n - g
+        folded = 0
+        for trial in range(4):
+            x = int(rng.integers(0, 1 << n))
+            if trial == 0:
+                c = qft_circuit(OracleCircuit, G, n)
+            else:
+                c = OracleCircuit.new(n)
+                for w in range(n):  # a column of one-wire gates (config 3's first layer), then anything
+                    c.add_gate([G.H, G.Rx(0.3 + w), G.Ry(1.1 * w), G.Rz(0.7)][int(rng.integers(0, 4))], w)
+                c2 = random_any_gate_circuit(OracleCircuit, G, n, 30, rng)
+                c.circuit_gates.extend(c2.circuit_gates)
+            enc = encode_gates(c.circuit_gates, n)
+            reg = np.zeros(1 << n, dtype=np.complex128)
+            reg[x] = 1.0
+            ref = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense", threads=2)
+            plan = qb.Plan(n, enc, n_local=nl, tile_bits=tile_bits, low_bits=low_bits, free_layout=True, lib=lib)
+            desc = plan.describe()
+            folded += desc["prefix_local_bits"]
+            only_passes = all(k == "pass" for k, _ in plan.steps())
+            if only_passes and plan.layout(False) == list(range(n)):
+                shards = []
+                for r in range(world):
+                    amps = np.full(1 << nl, np.nan + 1j * np.nan, dtype=np.complex128)
+                    assert lib.qsv_emu_run_plan_fused_init(plan.handle, amps.ctypes.data_as(C.POINTER(C.c_double)), r, x, mode) == 0
+                    shards.append(amps)
+                from helpers import physical_index_table
+                out = np.concatenate(shards)[physical_index_table(n, plan.layout(True))]
+                assert np.max(np.abs(out - ref)) < 1e-12, (trial, "fused")
+            plan.close()
+            # the same plan with the prefix amplitudes written to the register first (what materialize + the scatter kernel do)
+            out2, _, _ = emu_simulate_sharded(n, enc, world, basis_index=x, tile_bits=tile_bits, low_bits=low_bits)
+            assert np.max(np.abs(out2 - ref)) < 1e-12, (trial, "scattered")
+        assert folded > 0
+    finally:
+        lib.qsv_emu_set_tma_mode(0)
