@@ -297,7 +297,18 @@ struct PassInit {
     uint64_t sup_mask;        // the support bits (local index positions)
     uint64_t x_local;         // local index of the basis state
     const cplx* amp_tbl;
+    // mode 2: the tiles that hold amplitudes, enumerated directly - tile id = hold_id_val | pdep(q, hold_id_mask), q < 2^popc(mask)
+    // (dealt evenly to the compute groups of all CTAs; a CTA scanning only its own tile ids would find them on a few CTAs)
+    uint32_t hold_id_mask, hold_id_val;
 };
+QSV_HD uint32_t pdep32(uint32_t v, uint32_t mask) {
+    uint32_t r = 0;
+    for (uint32_t m = mask; m; m &= m - 1u) {
+        if (v & 1u) r |= m & (0u - m);
+        v >>= 1;
+    }
+    return r;
+}
 // does the tile at `base_full` hold a non-zero amplitude of the initial state?
 QSV_HD bool init_tile_holds(const PassInit& pi, uint64_t base_full) { return ((base_full ^ pi.base_full) & ~pi.sup_mask) == 0; }
 // initial amplitude of tile-local element l of a holding tile at local base `base` (tile_segs: the pass's tile bits)
@@ -316,6 +327,8 @@ inline PassInit make_pass_init(const DevPass& hdr, uint64_t phys_index, uint32_t
     pi.sup_local_mask = (uint32_t)extract(pi.sup_mask, hdr.tile_segs, hdr.n_tile_segs);
     pi.x_local = phys_index & local_mask;
     pi.amp_tbl = amp_tbl;
+    pi.hold_id_mask = (uint32_t)extract(pi.sup_mask & ext_mask, hdr.ext_segs, hdr.n_ext_segs);
+    pi.hold_id_val = (uint32_t)extract(phys_index & local_mask & ext_mask & ~pi.sup_mask, hdr.ext_segs, hdr.n_ext_segs);
     pi.base_full = (phys_index & local_mask & ext_mask) | (phys_index & ~local_mask);
     pi.local = (uint32_t)extract(phys_index & local_mask, hdr.tile_segs, hdr.n_tile_segs);
     pi.mode = mode;

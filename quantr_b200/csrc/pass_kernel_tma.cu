@@ -222,8 +222,9 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
         const uint64_t rows_per_cta = (n_rows + gridDim.x - 1) / gridDim.x;
         const uint64_t r0 = rows_per_cta * blockIdx.x, r1 = r0 + rows_per_cta < n_rows ? r0 + rows_per_cta : n_rows;
         const uint32_t sub = tid & 7u;  // amplitude within the row
-        for (uint64_t r = r0 + (tid >> 3); r < r1; r += Cfg::kThreads >> 3)
-            if (!(here && (r & row_mask) == row_hold)) st_stream(state + (r << 3) + sub, cplx{0.0, 0.0});
+        if (!(here && row_mask == 0))  // (a prefix folded over every tile-id bit: all tiles hold amplitudes, nothing to zero)
+            for (uint64_t r = r0 + (tid >> 3); r < r1; r += Cfg::kThreads >> 3)
+                if (!(here && (r & row_mask) == row_hold)) st_stream(state + (r << 3) + sub, cplx{0.0, 0.0});
     }
     __syncthreads();
     // prologue: the first kNB tiles, spread over the groups
@@ -264,8 +265,20 @@ pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, cplx* __restrict__ sta
     // tiles are dealt round-robin to the groups (every tile of a pass costs the same); buffer and use number of the
     // group's current tile are carried along instead of recomputed (k mod kNB, k / kNB)
     uint32_t slot = group % kNB, use = group / kNB, parity = 0;
-    for (uint32_t k = group; k < n_my; k += kG, parity ^= 1u) {
-        const uint32_t t_id = tile_of(k);
+    // init mode 2 walks the tiles that hold amplitudes (PassInit::hold_id_*), dealt evenly over all groups of all CTAs
+    const bool hold_enum = init.mode == 2;
+    const uint64_t n_hold = 1ull << __popc(init.hold_id_mask);
+    for (uint32_t it = 0;; ++it, parity ^= 1u) {
+        const uint32_t k = group + it * kG;
+        uint32_t t_id;
+        if (hold_enum) {
+            const uint64_t q = (uint64_t)blockIdx.x * kG + group + (uint64_t)it * gridDim.x * kG;
+            if (q >= n_hold) break;
+            t_id = init.hold_id_val | pdep32((uint32_t)q, init.hold_id_mask);
+        } else {
+            if (k >= n_my) break;
+            t_id = tile_of(k);
+        }
         uint64_t base = 0;
         if (need_base) base = tma_tile_base(tt, t_id);
         const uint64_t base_full = base | rank_hi;

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <sstream>
 #include <stdexcept>
 
@@ -858,11 +859,17 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
     plan.opt = opt_in;
     plan.passes.clear();
     plan.steps.clear();
-    plan.lops.clear();
     plan.n_rounds = 0;
-    lower_gates(n_qubits, ops, n_ops, plan.lops, &plan.n_gates);
-    if (plan.opt.fuse && plan.opt.merge_1q) merge_single_qubit_gates(plan.lops, plan.opt.merge_ctrl != 0);
-    if (plan.opt.fuse) merge_diagonals(plan.lops);
+    {
+        static std::atomic<uint64_t> next_stamp{1};
+        plan.stamp = next_stamp.fetch_add(1);
+    }
+    if (ops || n_ops == 0 || plan.lops.empty()) {  // (build_prefix_subplan hands over ready-made lowered ops instead of gates)
+        plan.lops.clear();
+        lower_gates(n_qubits, ops, n_ops, plan.lops, &plan.n_gates);
+        if (plan.opt.fuse && plan.opt.merge_1q) merge_single_qubit_gates(plan.lops, plan.opt.merge_ctrl != 0);
+        if (plan.opt.fuse) merge_diagonals(plan.lops);
+    }
     // tile size: 11 for registers the pipelined kernel serves (measured on B200, DESIGN.md 6: four compute groups of
     // 128 threads overlap better than two of 256), else 12; widened when a Custom gate needs more tile bits
     int tile_bits_auto = plan.n_alloc >= 23 ? 11 : 12;
@@ -924,7 +931,10 @@ void build_plan(Plan& plan, uint32_t n_qubits, uint32_t n_local, const qsv_op* o
     plan.prefix_local_bits = 0;
     if (free_layout && initial_layout == nullptr && plan.opt.fold_prefix && plan.opt.fuse) {
         int k_max = 0;
-        if ((int)n_local >= plan.opt.prefix_min_local && (int)n_local == nloc) k_max = std::min<int>(kMaxPrefixLocalBits, (int)n_local - 12);
+        // up to kHostPrefixBits the host computes the table; beyond, the prefix runs on a sub-register of g + k qubits on the
+        // device (build_prefix_subplan, state_api.cu): up to all but the lowest eight qubits
+        if ((int)n_local >= plan.opt.prefix_min_local && (int)n_local == nloc)
+            k_max = std::min<int>(plan.opt.prefix_subregister ? kMaxPrefixLocalBits : kHostPrefixBits, (int)n_local - plan.opt.prefix_keep_bits);  // (default 16: at most 1/32 of the first pass's 2^11-amplitude tiles hold amplitudes)
         if (k_max < 0) k_max = 0;
         if (g > 0 || k_max > 0) {
             const uint64_t support = (((1ull << (g + k_max)) - 1ull) << ((int)n_local - k_max));
@@ -1308,6 +1318,49 @@ void prefix_amplitudes(const Plan& plan, uint64_t basis_index, std::vector<cplx>
             }
         }
     }
+}
+
+// The folded prefix as a circuit of its own on the g + k support qubits (index bit b of the register = bit b - nf of the
+// sub-register, nf = n - g - k): controls on the constant low bits are resolved against the basis state (an op whose
+// control is 0 there vanishes), phases that depend on them become constants.  The sub-register's final state is the table
+// prefix_amplitudes computes on the host - here for prefixes too wide for that (k > kHostPrefixBits).
+void build_prefix_subplan(const Plan& plan, uint64_t basis_index, Plan& sub) {
+    const uint32_t n = plan.n_qubits, nf = plan.n_local - plan.prefix_local_bits, ns = n - nf;
+    const uint64_t low_mask = (1ull << nf) - 1ull, x_low = basis_index & low_mask;  // canonical layout: physical = logical
+    sub = Plan();
+    for (const LOp& op : plan.prefix) {
+        LOp o = op;
+        if (op.kind == LOp::DENSE) fail("internal: dense op in a folded prefix");
+        const uint64_t c_low = op.cmask & low_mask;
+        const bool low_sat = (x_low & c_low) == c_low;
+        o.cmask = op.cmask >> nf;
+        if (op.kind == LOp::MAT) {
+            o.target = op.target - (int)nf;
+            if (!low_sat) {  // the controls on the constant bits fail: the op is its "elsewhere" matrix (dual) or nothing
+                if (!op.dual) continue;
+                memcpy(o.m, op.m2, sizeof(o.m));
+                o.dual = false;
+                o.cmask = 0;
+                OpType t;
+                if (!classify_mat(o.m, &t)) continue;
+                o.mtype = t;
+            }
+        } else {
+            if (!low_sat) continue;
+            o.lin.clear();
+            for (auto& t : op.lin) {
+                if (t.first < (int)nf) { if ((x_low >> t.first) & 1ull) o.theta0 += t.second; }
+                else o.lin.push_back({t.first - (int)nf, t.second});
+            }
+        }
+        sub.lops.push_back(std::move(o));
+    }
+    PlanOptions opt = plan.opt;
+    opt.fold_prefix = 0;
+    opt.tile_bits = 0;
+    opt.low_bits = 0;
+    sub.n_gates = plan.prefix.size();
+    build_plan(sub, ns, ns, nullptr, sub.lops.empty() ? 0 : 1, opt, nullptr, false);  // (ops = NULL with n_ops = 1: keep sub.lops)
 }
 
 bool plan_overlap_group(const Plan& plan, size_t step, const std::vector<char>& sliceable, uint32_t log2_slices, OverlapGroup& out) {

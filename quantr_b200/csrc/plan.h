@@ -14,7 +14,8 @@
 
 namespace qsv {
 
-constexpr int kMaxPrefixLocalBits = 14;  // local index bits a folded prefix may spread the basis state over (a 256 KiB table per rank)
+constexpr int kHostPrefixBits = 14;      // folded prefixes up to this many local bits are applied on the host (a 256 KiB table per rank)
+constexpr int kMaxPrefixLocalBits = 26;  // ... wider ones run on a sub-register on the device (1 GiB at most)
 
 // A gate lowered to physical-bit space (bit = n-1-wire).
 struct LOp {
@@ -49,6 +50,9 @@ struct PlanOptions {
     int qft4 = 1;         // whole QFT-ladder rounds become one radix-16 macro-op (pass_core.h qft4_apply)
     int big_low_pass = 1; // a pass over the contiguous low index bits may use a 2^12 tile next to 2^11 strided passes
     int fold_prefix = 1;  // basis states: leading gates on the top qubits (rank id + up to kMaxPrefixLocalBits local ones) are applied on the host (build_plan)
+    int prefix_subregister = 1;  // prefixes wider than kHostPrefixBits local qubits run on a device sub-register (state_api.cu); 0: stop at kHostPrefixBits
+    int prefix_keep_bits = 16;   // ... and never over the lowest prefix_keep_bits local qubits: the first pass computes the tiles that hold
+                                 // amplitudes outside its pipeline, so they must stay a small fraction (tests lower it)
     int prefix_min_local = 23;  // ... local qubits are folded only on registers of at least this many local qubits (small ones: not worth a table upload per run)
     int reorder = 1;      // passes take later ops that commute with the ops they had to leave behind (plan.cpp schedule)
     int merge_1q = 1;     // 2x2 gates on the same target and controls are multiplied together across commuting ops; identities vanish
@@ -85,6 +89,7 @@ struct Plan {
     // other bits as in the basis state - which the host computes (prefix_amplitudes) and the first pass synthesises
     // (PassInit::amp_tbl) or a scatter kernel writes.  QFT-33 from a basis state: 14 of its 33 stages cost nothing.
     uint32_t prefix_local_bits = 0;
+    uint64_t stamp = 0;  // unique per built plan (caches keyed by a plan's address tell a new plan at an old address apart)
     uint64_t n_gates = 0, n_rounds = 0;
     // device residency (owned by the state API)
     void* dev_blob = nullptr;
@@ -106,6 +111,9 @@ std::string describe_plan(const Plan& plan);
 // (canonical index): entry j belongs to the physical index whose top g + prefix_local_bits bits spell j (rank id first)
 // and whose other bits are the basis state's.  Without a prefix: 1 on the rank that holds the basis state (2^g entries).
 void prefix_amplitudes(const Plan& plan, uint64_t basis_index, std::vector<cplx>& out);
+// The prefix as a plan over the g + prefix_local_bits support qubits, for the basis state `basis_index` (its low bits are
+// folded into the ops as constants); the sub-register's final state equals prefix_amplitudes' table.
+void build_prefix_subplan(const Plan& plan, uint64_t basis_index, Plan& sub);
 
 // Pipelined exchange (state_api.cu run_overlapped): an EXCHANGE step can run slice by slice against the pass before it
 // and the pass after it when some local index bits are neither partner bits of the exchange nor tile bits of those

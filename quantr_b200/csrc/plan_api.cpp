@@ -31,6 +31,8 @@ int qsv_plan_create_ex(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubit
         if (const char* env = getenv("QSV_QFT4")) opt.qft4 = atoi(env) != 0;  // developer A/B switch
         if (const char* env = getenv("QSV_BIG_LOW_PASS")) opt.big_low_pass = atoi(env) != 0;  // developer A/B switch
         if (const char* env = getenv("QSV_FOLD_PREFIX")) opt.fold_prefix = atoi(env) != 0;    // developer A/B switch
+        if (const char* env = getenv("QSV_PREFIX_SUBREG")) opt.prefix_subregister = atoi(env) != 0;  // developer A/B switch
+        if (const char* env = getenv("QSV_PREFIX_KEEP_BITS")) opt.prefix_keep_bits = atoi(env);      // tests
         if (const char* env = getenv("QSV_PREFIX_MIN_LOCAL")) opt.prefix_min_local = atoi(env);  // tests: fold local qubits on small registers too
         if (const char* env = getenv("QSV_REORDER")) opt.reorder = atoi(env) != 0;            // developer A/B switch
         if (const char* env = getenv("QSV_MERGE_1Q")) opt.merge_1q = atoi(env) != 0;          // developer A/B switch

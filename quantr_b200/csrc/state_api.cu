@@ -82,6 +82,13 @@ struct qsv_state {
     int xchg_sms = 32;       // SMs left to the swap kernels while a pass runs next to them (option "exchange_sms")
     int xchg_slices_log2 = 2;  // option "exchange_slices_log2": 2^k slices per remap
     uint64_t n_overlapped = 0;   // remaps of the last plan run that were pipelined
+    // A folded prefix wider than the host table (Plan::prefix_local_bits > kHostPrefixBits) runs on a sub-register of the
+    // support qubits on this device; its final state is the table the plan's first pass synthesises its tiles from.
+    qsv_state* sub = nullptr;
+    qsv_plan* sub_plan = nullptr;
+    const void* sub_plan_of = nullptr;  // the plan and basis state sub_plan was made for
+    uint64_t sub_plan_basis = 0, sub_plan_stamp = 0;
+    cudaEvent_t sub_done = nullptr;
     bool peers_local = false;    // peer_ptr holds plain device pointers of this process (qsv_create_multi), not IPC mappings
     // In-library multi-GPU (qsv_create_multi): this handle is a front for one sharded handle per device, each driven by its
     // own host thread of `pool`; every call is forwarded to all of them (see the "multi" section below).
@@ -394,6 +401,50 @@ int run_overlapped(qsv_state* s, const Plan& plan, size_t step, const OverlapGro
     return QSV_OK;
 }
 
+int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats);
+
+// The folded prefix of `p` on a sub-register of the g + k support qubits (plan.cpp build_prefix_subplan): every rank runs the
+// whole prefix (2^(g+k) amplitudes, at most 1 GiB) and uses its own 2^k slice.  The sub-plan is kept per (plan, basis state);
+// the sub-register is simulated again on every run.  *d_tbl = this rank's slice, ready on s->stream.
+int run_prefix_subregister(qsv_state* s, qsv_plan* p, cplx** d_tbl) {
+    const Plan& plan = p->plan;
+    const uint32_t g = s->n_qubits - s->n_local, k = plan.prefix_local_bits, ns = g + k;
+    if (s->sub && s->sub->n_qubits != ns) {
+        qsv_destroy(s->sub);
+        s->sub = nullptr;
+    }
+    if (!s->sub) {
+        int rc = create_common(&s->sub, ns, s->device, 0, 1);
+        if (rc != QSV_OK) return set_error(s, rc, "sub-register of %u qubits for the folded prefix: %s", ns, qsv_last_error(nullptr));
+    }
+    if (!s->sub_done) QSV_CUDA(s, cudaEventCreateWithFlags(&s->sub_done, cudaEventDisableTiming));
+    if (!s->sub_plan || s->sub_plan_of != (const void*)p || s->sub_plan_basis != s->lazy_index || s->sub_plan_stamp != p->plan.stamp) {
+        if (s->sub_plan) qsv_plan_destroy(s->sub_plan);
+        s->sub_plan = new (std::nothrow) qsv_plan();
+        if (!s->sub_plan) return set_error(s, QSV_ERR_OUT_OF_MEMORY, "host allocation failed");
+        try {
+            build_prefix_subplan(plan, s->lazy_index, s->sub_plan->plan);
+        } catch (const std::exception& e) {
+            qsv_plan_destroy(s->sub_plan);
+            s->sub_plan = nullptr;
+            return set_error(s, QSV_ERR_INTERNAL, "prefix sub-plan: %s", e.what());
+        }
+        s->sub_plan_of = p;
+        s->sub_plan_basis = s->lazy_index;
+        s->sub_plan_stamp = p->plan.stamp;
+    }
+    const uint32_t nf = s->n_local - k;
+    int rc = qsv_init_basis(s->sub, s->lazy_index >> nf);
+    if (rc == QSV_OK) rc = run_plan_impl(s->sub, s->sub_plan, nullptr);
+    if (rc == QSV_OK) rc = materialize(s->sub);  // (a prefix that lowered to nothing: the basis state itself)
+    if (rc != QSV_OK) return set_error(s, rc, "folded prefix on the sub-register: %s", s->sub->error.c_str());
+    QSV_CUDA(s, cudaSetDevice(s->device));
+    QSV_CUDA(s, cudaEventRecord(s->sub_done, s->sub->stream));
+    QSV_CUDA(s, cudaStreamWaitEvent(s->stream, s->sub_done, 0));
+    *d_tbl = s->sub->d_state + ((size_t)s->rank << k);
+    return QSV_OK;
+}
+
 int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     Plan& plan = p->plan;
     if (plan.n_qubits != s->n_qubits || plan.n_local != s->n_local)
@@ -413,6 +464,12 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
     int rc = QSV_OK;
     if (folded) {
         if (!s->lazy_basis) return set_error(s, QSV_ERR_INVALID_ARG, "this plan was built for a register that is a basis state (qsv_init_basis)");
+        // (QSV_HOST_PREFIX_BITS: tests send narrower prefixes through the sub-register as well)
+        static const uint32_t host_prefix_bits = getenv("QSV_HOST_PREFIX_BITS") ? (uint32_t)atoi(getenv("QSV_HOST_PREFIX_BITS")) : (uint32_t)kHostPrefixBits;
+        if (sup_bits > host_prefix_bits) {
+            rc = run_prefix_subregister(s, p, &d_tbl);
+            if (rc != QSV_OK) return rc;
+        } else {
         std::vector<cplx> amps;
         prefix_amplitudes(plan, s->lazy_index, amps);
         if (sup_bits == 0) {
@@ -424,6 +481,7 @@ int run_plan_impl(qsv_state* s, qsv_plan* p, qsv_stats* stats) {
             d_tbl = static_cast<cplx*>(s->d_scratch);
             QSV_CUDA(s, cudaMemcpyAsync(d_tbl, amps.data() + (size_t)s->rank * count, sizeof(cplx) * count, cudaMemcpyHostToDevice, s->stream));
             QSV_CUDA(s, cudaStreamSynchronize(s->stream));  // `amps` goes out of scope
+        }
         }
     }
     // Fused initialisation (pass_kernel_tma.cu): a pending basis state is not written to HBM when the plan's first step is
@@ -865,6 +923,12 @@ int qsv_peer_import(qsv_state* s, const void* handles, size_t n_handles) {
 
 int qsv_destroy(qsv_state* s) {
     if (!s) return QSV_OK;
+    if (s->sub_plan) qsv_plan_destroy(s->sub_plan);
+    if (s->sub) qsv_destroy(s->sub);
+    if (s->sub_done) cudaEventDestroy(s->sub_done);
+    s->sub_plan = nullptr;
+    s->sub = nullptr;
+    s->sub_done = nullptr;
     if (s->pool) {  // multi-device front: every shard stops being used by its siblings before any of them is freed
         s->pool->run([&](int r) {
             qsv_state* c = s->children[(size_t)r];

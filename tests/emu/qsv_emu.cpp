@@ -284,6 +284,28 @@ static int peer_exchange(double** shards, uint32_t n_local, const uint8_t* partn
     return 0;
 }
 
+// The folded prefix run as a plan of its own on the support qubits (plan.cpp build_prefix_subplan; on the device this is how
+// prefixes too wide for the host table are applied): out = the sub-register's final state, 2^(g + prefix_local_bits) amplitudes.
+extern "C" int qsv_emu_prefix_subplan_table(const qsv_plan* p, uint64_t basis_index, double* out, size_t cap) {
+    if (!p || !out) return 1;
+    try {
+        Plan sub;
+        build_prefix_subplan(p->plan, basis_index, sub);
+        const uint32_t nf = p->plan.n_local - p->plan.prefix_local_bits;
+        if (cap < ((size_t)1 << sub.n_alloc)) return 2;
+        std::vector<cplx> reg((size_t)1 << sub.n_alloc, cplx{0.0, 0.0});
+        reg[basis_index >> nf] = cplx{1.0, 0.0};
+        for (const PlanStep& st : sub.steps) {
+            if (st.kind != PlanStep::PASS) return 3;
+            run_pass(sub.passes[st.pass_index].data(), reg.data(), 0, nullptr, sub.n_alloc);
+        }
+        memcpy(out, reg.data(), sizeof(cplx) * reg.size());
+        return 0;
+    } catch (...) {
+        return 4;
+    }
+}
+
 // A plan on a basis state with the initialisation fused into its first pass (state_api.cu, QSV_FUSED_INIT): `amps` is
 // never read by that pass.  phys_index = the basis index under the plan's initial layout, rank bits included.
 extern "C" int qsv_emu_run_plan_fused_init(const qsv_plan* p, double* amps, uint64_t rank, uint64_t phys_index, uint32_t mode) {

@@ -43,3 +43,12 @@ def test_dense_custom_round_stays_covered():
     """Multi-controlled Custom gates are lowered to controlled ops by default; with that switched off every Custom gate
     of the reference's tests goes through the dense (CSR) round again."""
     run_inner({"QSV_STRUCTURED_CUSTOM": "0"}, "x3sudoko or golden or none_overwrite or qft16 or post_select")
+
+
+def test_folded_prefix_through_the_device_sub_register():
+    """Leading gates on the top qubits of a basis state are folded into the initial amplitudes (plan.cpp build_plan): up to 14
+    local qubits on the host, wider prefixes (QFT-33: 17) as a plan of their own on a sub-register on the device.  Here every
+    prefix goes through the sub-register, and the ones of small registers are folded too."""
+    run_inner({"QSV_HOST_PREFIX_BITS": "0"}, "qft_closed_form or layered or config3_depth100_live or grover")
+    run_inner({"QSV_HOST_PREFIX_BITS": "0", "QSV_PREFIX_MIN_LOCAL": "0", "QSV_PREFIX_KEEP_BITS": "8", "QSV_ASYNC": "2"}, "golden or qft16 or rerun or x3sudoko")
+    run_inner({"QSV_PREFIX_MIN_LOCAL": "0", "QSV_PREFIX_KEEP_BITS": "6"}, "golden or random or qft16 or none_overwrite")

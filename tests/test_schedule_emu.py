@@ -286,6 +286,7 @@ def test_prefix_folded_over_the_top_local_qubits(n, world, tile_bits, low_bits, 
     import ctypes as C
     from helpers import emu_lib, emu_simulate_sharded
     monkeypatch.setenv("QSV_PREFIX_MIN_LOCAL", "0")
+    monkeypatch.setenv("QSV_PREFIX_KEEP_BITS", "8")
     lib = emu_lib()
     lib.qsv_emu_run_plan_fused_init.restype = C.c_int
     lib.qsv_emu_run_plan_fused_init.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint64, C.c_uint64, C.c_uint32]
@@ -329,3 +330,38 @@ def test_prefix_folded_over_the_top_local_qubits(n, world, tile_bits, low_bits, 
         assert folded > 0
     finally:
         lib.qsv_emu_set_tma_mode(0)
+
+
+@pytest.mark.parametrize("n,world", [(16, 1), (18, 2), (17, 4), (20, 1)])
+def test_wide_prefix_runs_as_a_plan_on_the_support_qubits(n, world, monkeypatch):
+    """Prefixes wider than the host table (more than 14 local qubits: QFT-33 folds 25 of its 33 stages) are applied on the
+    device, as a plan of their own on a sub-register of the support qubits (plan.cpp build_prefix_subplan: controls on the
+    constant low bits resolved against the basis state, their phases folded into constants).  That plan's final state must
+    be the table the host computes (prefix_amplitudes)."""
+    import ctypes as C
+    from helpers import emu_lib
+    monkeypatch.setenv("QSV_PREFIX_MIN_LOCAL", "0")
+    monkeypatch.setenv("QSV_PREFIX_KEEP_BITS", "8")
+    lib = emu_lib()
+    lib.qsv_emu_prefix_subplan_table.restype = C.c_int
+    lib.qsv_emu_prefix_subplan_table.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_double), C.c_size_t]
+    rng = np.random.default_rng(n + world)
+    nl = n - (world.bit_length() - 1)
+    for trial in range(4):
+        if trial == 0:
+            c = qft_circuit(OracleCircuit, G, n)
+        else:
+            c = OracleCircuit.new(n)
+            for w in range(n):
+                c.add_gate([G.H, G.Rx(0.3 + w), G.Ry(1.1 * w), G.Rz(0.7)][int(rng.integers(0, 4))], w)
+            c.circuit_gates.extend(random_any_gate_circuit(OracleCircuit, G, n, 30, rng).circuit_gates)
+        enc = encode_gates(c.circuit_gates, n)
+        x = int(rng.integers(0, 1 << n))
+        plan = qb.Plan(n, enc, n_local=nl, free_layout=True, lib=lib, tile_bits=6, low_bits=2)
+        assert plan.prefix_local_bits() > 0
+        want = plan.initial_amplitudes(x)
+        got = np.zeros(max(len(want), 16), dtype=np.complex128)
+        assert lib.qsv_emu_prefix_subplan_table(plan.handle, x, got.ctypes.data_as(C.POINTER(C.c_double)), len(got)) == 0
+        assert np.max(np.abs(got[:len(want)] - want)) < 1e-13
+        assert abs(np.sum(np.abs(want) ** 2) - 1.0) < 1e-12
+        plan.close()
