@@ -607,6 +607,10 @@ def main():
                 "achieved_GBps_per_direction": (pstats["exchange_bytes"] / (exchange_ms * 1e-3) / 1e9) if exchange_ms > 0 else None,
                 "path": exchange_path, "nvlink_peak_GBps_per_direction": NVLINK_PEAK, "peak_source": "B200_PROFILING.md measured peer copy"},
             "exchange_probe": exchange_probe, "prefix_ops_folded_into_initial_state": pdesc.get("prefix_ops", 0),
+            "prefix": {"lowered_ops": pdesc.get("prefix_ops", 0), "local_qubits": pdesc.get("prefix_local_bits", 0), "rank_qubits": g,
+                       "note": "leading gates on the top qubits of the basis state act on a product state: they are applied, on every step, to its "
+                               "2^(rank_qubits + local_qubits) non-zero amplitudes only (host up to 14 local qubits, a device sub-register beyond; its "
+                               "kernel launches are not in gpu_launches); the first pass synthesises its tiles from that table. QSV_FOLD_PREFIX=0 turns it off"},
             "sharded_parity_max_abs_err": parity_err, "sharded_parity_remaps": parity_remaps,
             "clocks": clocks.summary(), "norm_sqr": norm,
         }
