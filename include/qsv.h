@@ -231,12 +231,15 @@ int qsv_plan_create(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubits,
 int qsv_plan_create_ex(qsv_plan** out, uint32_t n_qubits, uint32_t n_local_qubits, const qsv_op* ops, size_t n_ops,
                        uint32_t tile_bits, uint32_t low_bits, int fuse, const uint8_t* layout, int free_layout);
 int qsv_plan_destroy(qsv_plan* p);
-/* Sharded plans built with `free_layout`: the amplitude every rank starts from when the register is the basis state
- * `basis_index` - out[2r], out[2r+1] = re, im for rank r (cap >= number of ranks), all at the local index the plan's
- * initial layout gives the basis state.  One rank holds 1 and the others 0 unless the scheduler folded the circuit's
- * leading gates on the qubits held in the rank id into the initial state (they act on a product state; QFT-n on 2^g
- * ranks then needs no global-qubit remap).  qsv_run_plan / qsv_apply use it internally; it is exported for callers that
- * drive the ranks themselves. */
+/* Plans built with `free_layout`: the amplitudes the plan starts from when the register is the basis state
+ * `basis_index`.  The scheduler folds the circuit's leading gates on the top qubits - the ones held in the rank id and, on
+ * registers of 2^23 amplitudes per rank or more, up to `n_local - 16` local ones - into the initial state: they act on a
+ * product state, so they are applied (on every run) to its 2^(g+k) non-zero amplitudes only, and the plan's first pass
+ * starts from those.  out[2j], out[2j+1] = re, im of the amplitude at the physical index whose top g + k bits spell j
+ * (rank id first) and whose other bits are the basis state's; cap >= 2^(g+k); k = "prefix_local_bits" of
+ * qsv_plan_serialize.  Without a folded prefix: one entry per rank, 1 on the rank that holds the basis state.  QFT-n on
+ * 2^g ranks needs no global-qubit remap because of it.  qsv_run_plan / qsv_apply use it internally; it is exported for
+ * callers that drive the ranks themselves. */
 int qsv_plan_initial_amplitudes(const qsv_plan* p, uint64_t basis_index, double* out, size_t cap);
 
 /* Plan introspection (host-side tests, sharded drivers).  Step kinds: */
