@@ -276,7 +276,7 @@ def test_permutation_rounds_for_runs_of_x_gates():
 
 
 @pytest.mark.parametrize("n,world,tile_bits,low_bits,mode,tma", [(16, 1, 6, 2, 2, 0), (16, 1, 8, 3, 1, 0), (17, 1, 11, 3, 2, 1), (16, 1, 11, 4, 2, 1),
-                                                               (17, 2, 7, 3, 2, 0), (18, 4, 11, 3, 2, 1)])
+                                                               (17, 2, 7, 3, 2, 0), (18, 4, 11, 3, 2, 1), (19, 8, 11, 3, 2, 1), (18, 8, 7, 2, 2, 0)])
 def test_prefix_folded_over_the_top_local_qubits(n, world, tile_bits, low_bits, mode, tma, monkeypatch):
     """Leading gates on the top qubits of a basis state - the rank-id qubits and up to 14 local ones - see a product state:
     the host applies them to the 2^(g+k) non-zero amplitudes (plan.cpp prefix_amplitudes) and the first pass synthesises its
@@ -332,7 +332,7 @@ def test_prefix_folded_over_the_top_local_qubits(n, world, tile_bits, low_bits, 
         lib.qsv_emu_set_tma_mode(0)
 
 
-@pytest.mark.parametrize("n,world", [(16, 1), (18, 2), (17, 4), (20, 1)])
+@pytest.mark.parametrize("n,world", [(16, 1), (18, 2), (17, 4), (20, 1), (19, 8)])
 def test_wide_prefix_runs_as_a_plan_on_the_support_qubits(n, world, monkeypatch):
     """Prefixes wider than the host table (more than 14 local qubits: QFT-33 folds 25 of its 33 stages) are applied on the
     device, as a plan of their own on a sub-register of the support qubits (plan.cpp build_prefix_subplan: controls on the
