@@ -432,6 +432,35 @@ def main():
     total_ms = ev_start.elapsed_time(ev_end)
     overlapped_remaps = state.get_info("overlapped_exchanges") if world > 1 else 0  # of the last timed step
 
+    # ---- the same workload with the prefix folding switched off (N = 1; context for the headline: every stage then runs as
+    # part of a pass over the whole register) -------------------------------------------------------------------------
+    unfolded = None
+    if world == 1 and pdesc.get("prefix_ops", 0) and not args.no_extras:
+        try:
+            os.environ["QSV_FOLD_PREFIX"] = "0"
+            try:
+                plan_nf = qb.Plan(n, enc, n_local=n_local, tile_bits=args.tile_bits, low_bits=args.low_bits, free_layout=True)
+            finally:
+                del os.environ["QSV_FOLD_PREFIX"]
+            for _ in range(2):
+                state.init_basis(x)
+                state.run_plan(plan_nf)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            for _ in range(args.steps):
+                state.init_basis(x)
+                state.run_plan(plan_nf)
+            e1.record(ext)
+            barrier()
+            unfolded = {"ms_per_step": e0.elapsed_time(e1) / args.steps, "fused_passes": plan_nf.stats()["n_passes"],
+                        "note": "QSV_FOLD_PREFIX=0: no gate is folded into the initial amplitudes"}
+            plan_nf.close()
+        except Exception as e:  # context only: never fatal for the headline line
+            unfolded = {"error": str(e)}
+        state.init_basis(x)
+        state.run_plan(plan)  # the register holds the headline plan's result again for the checks below
+
     # ---- per-pass device times (CUDA events around every launch, inside the library): a second, separately timed loop --
     state.set_option("timing", 1)
     pass_ms = None
@@ -606,7 +635,7 @@ def main():
                         "what the remaps add to the step when they run slice by slice next to their neighbouring passes",
                 "achieved_GBps_per_direction": (pstats["exchange_bytes"] / (exchange_ms * 1e-3) / 1e9) if exchange_ms > 0 else None,
                 "path": exchange_path, "nvlink_peak_GBps_per_direction": NVLINK_PEAK, "peak_source": "B200_PROFILING.md measured peer copy"},
-            "exchange_probe": exchange_probe, "prefix_ops_folded_into_initial_state": pdesc.get("prefix_ops", 0),
+            "exchange_probe": exchange_probe, "prefix_ops_folded_into_initial_state": pdesc.get("prefix_ops", 0), "without_prefix_folding": unfolded,
             "prefix": {"lowered_ops": pdesc.get("prefix_ops", 0), "local_qubits": pdesc.get("prefix_local_bits", 0), "rank_qubits": g,
                        "note": "leading gates on the top qubits of the basis state act on a product state: they are applied, on every step, to its "
                                "2^(rank_qubits + local_qubits) non-zero amplitudes only (host up to 14 local qubits, a device sub-register beyond; its "
