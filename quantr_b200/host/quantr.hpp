@@ -227,8 +227,21 @@ namespace detail {
 
 struct StateHandle {  // owns the qsv_state* ; freed on drop
     qsv_state* h = nullptr;
+    // QSV_DEVICES=0,1,..: one handle over several GPUs of the process (qsv_create_multi); registers too small to shard
+    // (fewer than four qubits per device) stay on the first device
     explicit StateHandle(uint32_t n, int device = 0) {
-        int rc = qsv_create(&h, n, device);
+        std::vector<int> devices;
+        if (const char* env = getenv("QSV_DEVICES"))
+            for (const char* p = env; *p;) {
+                char* end = nullptr;
+                const long v = strtol(p, &end, 10);
+                if (end == p) break;
+                devices.push_back((int)v);
+                p = *end == ',' ? end + 1 : end;
+            }
+        auto log2_of = [](size_t c) { uint32_t g = 0; while (((size_t)1 << (g + 1)) <= c) ++g; return g; };
+        while (devices.size() > 1 && n < 4 + log2_of(devices.size())) devices.resize(devices.size() / 2);
+        const int rc = devices.size() > 1 ? qsv_create_multi(&h, n, devices.data(), (int)devices.size()) : qsv_create(&h, n, devices.empty() ? device : devices[0]);
         if (rc != QSV_OK) ffi_panic(nullptr, rc, "qsv_create");
     }
     ~StateHandle() { if (h) qsv_destroy(h); }
