@@ -1,0 +1,4 @@
+set -u
+cd $GRAFT_REPO_ROOT
+timeout 80 python -m pytest tests/test_cpp_host.py -m gpu -q 2>&1 | tail -2
+timeout 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
