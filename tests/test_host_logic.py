@@ -183,3 +183,38 @@ def test_structured_custom_gates_are_lowered_to_controlled_ops():
     plan = qb.Plan(n, enc, lib=lib)
     d = plan.describe()
     assert d["n_lowered_ops"] == 1 and plan.stats()["n_passes"] == 1
+
+
+def test_headline_plans_keep_their_shape():
+    """Guards the schedules the measured numbers in DESIGN.md 6 belong to (host-only: plans are built, nothing runs):
+    QFT-33 from a basis state = 17 stages folded into the initial amplitudes + one write-only pass + one pass over the
+    contiguous low bits; QFT-36 on 8 ranks the same per rank and no remap; Grover-36 on 8 ranks = 3 remaps, each of
+    which the pipelined exchange can run against both of its neighbouring passes."""
+    import ctypes as C
+    from helpers import emu_lib, encode_gates, qft_circuit
+    from workloads import grover_circuit
+    import quantr_b200 as qb
+    lib = emu_lib()
+    for n, nl in ((33, 33), (36, 33)):
+        enc = encode_gates(qft_circuit(qb.Circuit, qb.Gate, n).get_gates(), n)
+        plan = qb.Plan(n, enc, n_local=nl, free_layout=True, lib=lib)
+        d = plan.describe()
+        assert d["prefix_local_bits"] == 17 and d["prefix_ops"] == 2 * (n - nl + 17) - 1
+        assert [k for k, _ in plan.steps()] == ["pass", "pass"]
+        assert [len(p["rounds"]) for p in d["passes"]] == [2, 2]
+        assert d["passes"][1]["tile"] == list(range(11))  # the contiguous low bits
+        assert plan.layout(False) == list(range(n)) and plan.layout(True) == list(range(n))
+        plan.close()
+    c, _info = grover_circuit(qb.Circuit, qb.Gate, 36, iterations=1)
+    plan = qb.Plan(36, encode_gates(c.get_gates(), 36), n_local=33, free_layout=True, lib=lib)
+    steps = plan.steps()
+    exchanges = [i for i, (k, _) in enumerate(steps) if k != "pass"]
+    assert len(exchanges) == 3 and len(steps) - len(exchanges) <= 12
+    assert any(r["type"] == 2 for p in plan.describe()["passes"] for r in p["rounds"])  # the Toffoli chains as permutation rounds
+    lib.qsv_emu_overlap_group.restype = C.c_int
+    sliceable = (C.c_uint8 * len(steps))(*[1 if k == "pass" else 0 for k, _ in steps])
+    for i in exchanges:
+        out = (C.c_uint32 * 6)()
+        assert lib.qsv_emu_overlap_group(plan.handle, i, sliceable, 2, out) == 1
+        assert out[0] == 1 and out[1] == 1 and out[2] == 2  # both neighbours sliced, four slices
+    plan.close()
