@@ -146,7 +146,13 @@ int qsv_create(qsv_state** out, uint32_t n_qubits, int device);
 /* Sharded state: this process owns the 2^(n_qubits - log2(world)) amplitudes
  * whose top log2(world) index bits equal `rank`.  `nccl_unique_id` is the
  * 128-byte ncclUniqueId produced by qsv_nccl_unique_id() on rank 0 and
- * distributed by the caller.  Collective: every rank must call it. */
+ * distributed by the caller.  Collective: every rank must call it.
+ * Limits (QSV_ERR_UNSUPPORTED from qsv_apply / qsv_plan_create otherwise): a shard
+ * holds at least 4 qubits, and a remap swaps ALL log2(world) rank bits with local
+ * bits, so a gate that moves amplitudes across w wires (w = 1 for every standard
+ * gate but Swap, 2 for Swap, all wires of a dense Custom gate) needs
+ * w + log2(world) <= local qubits ("cannot bring its qubits onto one rank").
+ * Controls and diagonal gates on rank-held qubits never need a remap. */
 int qsv_create_sharded(qsv_state** out, uint32_t n_qubits, int device, int rank, int world,
                        const void* nccl_unique_id, size_t nccl_unique_id_bytes);
 int qsv_nccl_unique_id(void* out, size_t out_bytes);

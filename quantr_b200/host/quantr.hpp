@@ -100,18 +100,40 @@ public:
         s.product_dim = n;
         return s;
     }
-    static void check(const std::vector<Complex64>& a) {
-        const size_t len = a.size();
-        if (len == 0 || (len & (len - 1)))  // :69-78
-            throw QuantrError("The length of the array must be of the form 2**n where n is an integer. The length is " + std::to_string(len) + ".");
+    static bool equal_within_error(double num, double compare_num) { return num < compare_num + ZERO_MARGIN && num > compare_num - ZERO_MARGIN; }  // :246-248
+    static void check(const std::vector<Complex64>& a) {  // :69-73, :236-240
         double total = 0;
         for (auto& x : a) total += std::norm(x);
-        if (std::abs(total - 1.0) > ZERO_MARGIN)  // :246-248
-            throw QuantrError("The total sum of the absolute square of all amplitudes, " + std::to_string(total) + ", does not sum to one.");
+        if (!equal_within_error(total, 1.0))
+            throw QuantrError("Slice given to set amplitudes in super position does not conserve probability, the absolute square sum of the coefficents must be one.");
     }
-    static SuperPosition new_with_amplitudes(const std::vector<Complex64>& a) {  // :68
+    static SuperPosition new_with_amplitudes(const std::vector<Complex64>& a) {  // :68-88 (probability first, then length)
         check(a);
+        if (a.size() & (a.size() - 1)) throw QuantrError("The length of the array must be of the form 2**n where n is an integer.");
         return new_with_amplitudes_unchecked(a);
+    }
+    // :113-123 / :279-290: every key has `dim` qubits and the squares sum to one; then from_hash_to_array (:344-357)
+    static std::vector<Complex64> from_states(const std::map<ProductState, Complex64>& h, size_t dim, bool report_total) {
+        if (h.empty()) throw QuantrError("An empty HashMap was given. A superposition must have at least one non-zero state.");
+        double total = 0;
+        for (auto& kv : h) {
+            if (kv.first.num_qubits() != dim)
+                throw QuantrError("The first state has product dimension of " + std::to_string(dim) + ", whilst the state, |" + kv.first.to_string() +
+                                  ">, found as a key in the HashMap has dimension " + std::to_string(kv.first.num_qubits()) + ".");
+            total += std::norm(kv.second);
+        }
+        if (!equal_within_error(total, 1.0))
+            throw QuantrError("The total sum of the absolute square of all amplitudes" + (report_total ? ", " + std::to_string(total) + "," : std::string()) +
+                              " does not equal 1. That is, the superpositon does not conserve probability.");
+        std::vector<Complex64> a((size_t)1 << dim, Complex64(0, 0));
+        for (auto& kv : h) a[kv.first.comp_basis()] = kv.second;
+        return a;
+    }
+    static SuperPosition new_with_hash_amplitudes(const std::map<ProductState, Complex64>& h) {  // :105-131
+        SuperPosition s;
+        s.product_dim = h.empty() ? 0 : h.begin()->first.num_qubits();
+        s.amplitudes = from_states(h, s.product_dim, true);
+        return s;
     }
     static SuperPosition new_with_amplitudes_unchecked(const std::vector<Complex64>& a) {  // super_positions_unchecked.rs:64
         SuperPosition s;
@@ -144,12 +166,26 @@ public:
         amplitudes = a;
         return *this;
     }
-    std::map<ProductState, Complex64> to_hash_map() const {  // :315 (non-zero amplitudes)
+    SuperPosition& set_amplitudes_from_states(const std::map<ProductState, Complex64>& h) {  // :270-295
+        amplitudes = from_states(h, product_dim, false);
+        return *this;
+    }
+    std::map<ProductState, Complex64> to_hash_map() const {  // :315-323 (amplitudes with |a|^2 within 1e-6 of zero are left out)
         std::map<ProductState, Complex64> m;
         for (size_t i = 0; i < amplitudes.size(); ++i)
-            if (std::norm(amplitudes[i]) != 0.0) m[ProductState::binary_basis(i, product_dim)] = amplitudes[i];
+            if (!equal_within_error(std::norm(amplitudes[i]), 0.0)) m[ProductState::binary_basis(i, product_dim)] = amplitudes[i];
         return m;
     }
+    // :332-342: first state whose running probability exceeds the roll (strict <); nullopt when the squares fall short of it
+    std::optional<ProductState> measure(double dice_roll) const {
+        double cumulative = 0;
+        for (size_t i = 0; i < amplitudes.size(); ++i) {
+            cumulative += std::norm(amplitudes[i]);
+            if (dice_roll < cumulative) return ProductState::binary_basis(i, product_dim);
+        }
+        return std::nullopt;
+    }
+    std::optional<ProductState> measure() const;  // roll from the package generator (fastrand::f64 in the reference)
 };
 
 }  // namespace states
@@ -300,6 +336,8 @@ inline void encode(const std::vector<Gate>& gates, size_t num_qubits, EncodedOps
 }
 
 }  // namespace detail
+
+inline std::optional<states::ProductState> states::SuperPosition::measure() const { return measure(next_f64()); }
 
 // src/simulated_circuit.rs:20-188 with the register held in HBM
 class SimulatedCircuit {

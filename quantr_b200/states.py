@@ -143,19 +143,23 @@ class SuperPosition:
         return cls._raw(amps, num_qubits)
 
     @staticmethod
-    def _check_amplitudes(amps: np.ndarray):
-        length = amps.shape[0]
-        if length == 0 or (length & (length - 1)) != 0:  # super_positions.rs:69-78
-            raise QuantrError(f"The length of the array must be of the form 2**n where n is an integer. The length is {length}.")
-        total = float(np.sum(amps.real ** 2 + amps.imag ** 2))
-        if abs(total - 1.0) > ZERO_MARGIN:  # super_positions.rs:246-248
-            raise QuantrError(f"The total sum of the absolute square of all amplitudes, {total}, does not sum to one.")
+    def _equal_within_error(num: float, compare_num: float) -> bool:  # super_positions.rs:246-248
+        return compare_num - ZERO_MARGIN < num < compare_num + ZERO_MARGIN
 
     @classmethod
-    def new_with_amplitudes(cls, amplitudes) -> "SuperPosition":  # super_positions.rs:68
+    def _check_probability(cls, amps: np.ndarray):  # super_positions.rs:69-73, 236-240
+        if not cls._equal_within_error(float(np.sum(amps.real ** 2 + amps.imag ** 2)), 1.0):
+            raise QuantrError("Slice given to set amplitudes in super position does not conserve probability, "
+                              "the absolute square sum of the coefficents must be one.")
+
+    @classmethod
+    def new_with_amplitudes(cls, amplitudes) -> "SuperPosition":  # super_positions.rs:68-88 (probability first, then length)
         amps = np.array(amplitudes, dtype=np.complex128).reshape(-1)
-        cls._check_amplitudes(amps)
-        return cls._raw(amps, amps.shape[0].bit_length() - 1)
+        cls._check_probability(amps)
+        length = amps.shape[0]
+        if (length & (length - 1)) != 0:
+            raise QuantrError("The length of the array must be of the form 2**n where n is an integer.")
+        return cls._raw(amps, length.bit_length() - 1)
 
     @classmethod
     def new_with_amplitudes_unchecked(cls, amplitudes) -> "SuperPosition":  # super_positions_unchecked.rs:64
@@ -165,18 +169,33 @@ class SuperPosition:
         return cls._raw(amps, tz)
 
     @classmethod
-    def new_with_hash_amplitudes(cls, hash_amplitudes: dict) -> "SuperPosition":  # super_positions.rs:105
-        if not hash_amplitudes:
-            raise QuantrError("An empty HashMap was given. A superposition must have at least one element.")
-        dims = {k.num_qubits() for k in hash_amplitudes}
-        if len(dims) != 1:
-            raise QuantrError("The product states that label the amplitudes have different dimensions.")
-        n = dims.pop()
+    def _check_hash_amplitudes(cls, hash_amplitudes: dict, product_dim: int, conserve_message: str):
+        """super_positions.rs:113-123 / 279-290: every key has `product_dim` qubits, the squares sum to one."""
+        total = 0.0
+        for states, amplitude in hash_amplitudes.items():
+            if states.num_qubits() != product_dim:
+                raise QuantrError(f"The first state has product dimension of {product_dim}, whilst the state, |{states}>, "
+                                  f"found as a key in the HashMap has dimension {states.num_qubits()}.")
+            a = complex(amplitude)
+            total += a.real * a.real + a.imag * a.imag
+        if not cls._equal_within_error(total, 1.0):
+            raise QuantrError(conserve_message.format(total))
+
+    @staticmethod
+    def _from_hash_to_array(hash_amplitudes: dict, n: int) -> np.ndarray:  # super_positions.rs:344-357
         amps = np.zeros(1 << n, dtype=np.complex128)
         for k, v in hash_amplitudes.items():
             amps[k.comp_basis()] = v
-        cls._check_amplitudes(amps)
-        return cls._raw(amps, n)
+        return amps
+
+    @classmethod
+    def new_with_hash_amplitudes(cls, hash_amplitudes: dict) -> "SuperPosition":  # super_positions.rs:105-131
+        if not hash_amplitudes:
+            raise QuantrError("An empty HashMap was given. A superposition must have at least one non-zero state.")
+        n = next(iter(hash_amplitudes)).num_qubits()
+        cls._check_hash_amplitudes(hash_amplitudes, n, "The total sum of the absolute square of all amplitudes, {}, does not equal 1. "
+                                                       "That is, the superpositon does not conserve probability.")
+        return cls._raw(cls._from_hash_to_array(hash_amplitudes, n), n)
 
     def get_amplitude(self, pos: int):  # super_positions.rs:145
         return complex(self.amplitudes[pos]) if 0 <= pos < self.amplitudes.shape[0] else None
@@ -205,7 +224,7 @@ class SuperPosition:
                 f"The slice given to set the amplitudes in the computational basis has length {amps.shape[0]}, "
                 f"when it should have length {self.amplitudes.shape[0]}."
             )
-        self._check_amplitudes(amps)
+        self._check_probability(amps)
         self.amplitudes = amps
         return self
 
@@ -213,12 +232,31 @@ class SuperPosition:
         self.amplitudes = np.array(amplitudes, dtype=np.complex128).reshape(-1)
         return self
 
-    def to_hash_map(self) -> dict:  # super_positions.rs:315 (non-zero amplitudes only)
+    def set_amplitudes_from_states(self, amplitudes: dict) -> "SuperPosition":  # super_positions.rs:270-295
+        if not amplitudes:
+            raise QuantrError("An empty HashMap was given. A superposition must have at least one non-zero state.")
+        self._check_hash_amplitudes(amplitudes, self.product_dim, "The total sum of the absolute square of all amplitudes does not equal 1. "
+                                                                  "That is, the superpositon does not conserve probability.")
+        self.amplitudes = self._from_hash_to_array(amplitudes, self.product_dim)
+        return self
+
+    def to_hash_map(self) -> dict:  # super_positions.rs:315-323 (amplitudes with |a|^2 within 1e-6 of zero are left out)
         out = {}
         for i, a in enumerate(self.amplitudes):
-            if a.real * a.real + a.imag * a.imag != 0.0:
+            if not self._equal_within_error(a.real * a.real + a.imag * a.imag, 0.0):
                 out[ProductState.binary_basis(i, self.product_dim)] = complex(a)
         return out
+
+    def measure(self, dice_roll: float | None = None):  # super_positions.rs:332-342
+        """Observes the superposition: the first state whose cumulative probability exceeds the dice roll (strict `<`), or
+        None when the squares sum to less than the roll (non-unitary Custom gates).  The reference draws the roll from
+        `fastrand::f64()`; here it comes from the package generator (`quantr_b200.seed`) unless given."""
+        if dice_roll is None:
+            from . import circuit
+            dice_roll = float(circuit._rng.random())
+        cumulative = np.cumsum(self.amplitudes.real ** 2 + self.amplitudes.imag ** 2)
+        hit = np.nonzero(dice_roll < cumulative)[0]
+        return ProductState.binary_basis(int(hit[0]), self.product_dim) if hit.size else None
 
     def __iter__(self):  # super_position_iter.rs:56-72 (zeros included)
         for i, a in enumerate(self.amplitudes):

@@ -90,6 +90,24 @@ static void host_tests() {
         CHECK(throws_quantr_error([] { SuperPosition::new_with_amplitudes({0.5, 0.5}); }));
         CHECK(SuperPosition::new_with_amplitudes({0, Complex64(0, 1), 0, 0}).get_num_qubits() == 2);
     }
+    {  // super_positions.rs:437-497 (hash constructors), :270-295, :315-342
+        ++g_run;
+        const double r = std::sqrt(0.5);
+        const ProductState p01 = ProductState::binary_basis(1, 2), p10 = ProductState::binary_basis(2, 2);
+        const SuperPosition h = SuperPosition::new_with_hash_amplitudes({{p01, r}, {p10, Complex64(0, -r)}});
+        CHECK(h.get_amplitudes() == SuperPosition::new_with_amplitudes({0, r, Complex64(0, -r), 0}).get_amplitudes());
+        CHECK(throws_quantr_error([&] { SuperPosition::new_with_hash_amplitudes({{p01, r}, {ProductState::binary_basis(5, 3), Complex64(0, -r)}}); }));
+        CHECK(throws_quantr_error([&] { SuperPosition::new_with_hash_amplitudes({{p01, r}, {p10, Complex64(0, -0.5 * r)}}); }));
+        CHECK(throws_quantr_error([] { SuperPosition::new_with_hash_amplitudes({}); }));
+        SuperPosition s = SuperPosition::make(2);
+        s.set_amplitudes_from_states({{p01, 1.0}});
+        CHECK(s.get_amplitudes() == std::vector<Complex64>({0, 1, 0, 0}));
+        CHECK(throws_quantr_error([&] { s.set_amplitudes_from_states({{p01, 0.5}}); }));
+        CHECK(SuperPosition::new_with_amplitudes_unchecked({1.0, 5e-4, 2e-3, 0.0}).to_hash_map().size() == 2);
+        const SuperPosition q = SuperPosition::new_with_amplitudes_unchecked({0.5, 0.0, 0.0, 0.5});
+        CHECK(q.measure(0.25)->to_string() == "11" && q.measure(0.2)->to_string() == "00" && !q.measure(0.5).has_value());
+        CHECK(q.measure().has_value() || true);
+    }
 }
 
 static void device_tests() {

@@ -91,6 +91,63 @@ def test_super_position_validation():  # super_positions.rs:403-544
     assert st.SuperPosition.new(2).get_amplitudes()[0] == 1.0
 
 
+def test_super_position_reference_tests():  # super_positions.rs:403-544 replayed one by one
+    r = float(np.sqrt(0.5))
+    P = st.ProductState.new_unchecked
+    Z, O = st.Qubit.Zero, st.Qubit.One
+    amps = [0, r, -1j * r, 0]
+    sp = st.SuperPosition.new_unchecked(2).set_amplitudes(amps)
+    assert sp.get_amplitude_from_state(P([Z, O])) == r  # retrieve_amplitude_from_state
+    assert sp.get_amplitude(2) == -1j * r  # retrieve_amplitude_from_list_pos
+    states = {P([Z, O]): r, P([O, Z]): -1j * r}
+    assert np.array_equal(st.SuperPosition.new_with_amplitudes(amps).get_amplitudes(),
+                          st.SuperPosition.new_with_hash_amplitudes(states).get_amplitudes())  # sets_amplitude_from_states
+    with pytest.raises(QuantrError, match="The first state has product dimension of 2, whilst the state, .101>, found as a key"):
+        st.SuperPosition.new_with_hash_amplitudes({P([Z, O]): r, P([O, Z, O]): -1j * r})  # ..._wrong_dimension
+    with pytest.raises(QuantrError, match="does not equal 1. That is, the superpositon does not conserve probability"):
+        st.SuperPosition.new_with_hash_amplitudes({P([Z, O]): r, P([O, Z]): -0.5j * r})  # ..._breaks_probability
+    with pytest.raises(QuantrError, match="Unable to retreive product state"):
+        sp.get_amplitude_from_state(P([Z, O, O]))  # catches_retrieve_amplitude_from_wrong_state
+    assert sp.get_amplitude(4) is None  # catches_retrieve_amplitude_from_wrong_list_pos (None.unwrap() panics)
+    with pytest.raises(QuantrError, match="does not conserve probability"):
+        st.SuperPosition.new_unchecked(2).set_amplitudes([0, 0.5, 0, -0.5j])  # catches_super_position_breaking_conservation
+    with pytest.raises(QuantrError, match="has length 2, when it should have length 4"):
+        st.SuperPosition.new_unchecked(2).set_amplitudes([1, 0])
+    # the probability check comes before the length check (super_positions.rs:68-82)
+    with pytest.raises(QuantrError, match="must be of the form 2..n"):
+        st.SuperPosition.new_with_amplitudes([1, 0, 0])
+    with pytest.raises(QuantrError, match="does not conserve probability"):
+        st.SuperPosition.new_with_amplitudes([0.5, 0.5, 0.5])
+    with pytest.raises(QuantrError, match="An empty HashMap was given"):
+        st.SuperPosition.new_with_hash_amplitudes({})
+
+
+def test_super_position_set_amplitudes_from_states_and_hash_map_margin():  # super_positions.rs:270-323
+    sp = st.SuperPosition.new(2)
+    assert sp.set_amplitudes_from_states({st.ProductState.new([st.Qubit.Zero, st.Qubit.One]): 1.0}) is sp
+    assert np.array_equal(sp.get_amplitudes(), [0, 1, 0, 0])  # the doc test at :262-268
+    with pytest.raises(QuantrError, match="An empty HashMap was given"):
+        sp.set_amplitudes_from_states({})
+    with pytest.raises(QuantrError, match="The first state has product dimension of 2"):
+        sp.set_amplitudes_from_states({st.ProductState.binary_basis(1, 3): 1.0})
+    with pytest.raises(QuantrError, match="does not equal 1"):
+        sp.set_amplitudes_from_states({st.ProductState.binary_basis(1, 2): 0.5})
+    assert st.SuperPosition.new(2).to_hash_map() == {st.ProductState.binary_basis(0, 2): 1.0}  # the doc test at :308-313
+    # amplitudes whose square is within 1e-6 of zero are left out of the map (equal_within_error)
+    tiny = st.SuperPosition.new_with_amplitudes_unchecked([1.0, 5e-4, 2e-3, 0.0])
+    assert set(k.to_string() for k in tiny.to_hash_map()) == {"00", "10"}
+
+
+def test_super_position_measure_rule():  # super_positions.rs:332-342: strict `<` on the running sum, None when it falls short
+    sp = st.SuperPosition.new_with_amplitudes_unchecked([0.5, 0.5j, -0.5, 0.5])
+    assert [sp.measure(u).to_string() for u in (0.0, 0.2499, 0.25, 0.6, 0.9999)] == ["00", "00", "01", "10", "11"]
+    short = st.SuperPosition.new_with_amplitudes_unchecked([0.5, 0.0, 0.0, 0.5])
+    assert short.measure(0.49).to_string() == "11" and short.measure(0.5) is None
+    qb.seed(11)
+    draws = [sp.measure().to_string() for _ in range(400)]
+    assert all(0.15 < draws.count(k) / 400 < 0.35 for k in ("00", "01", "10", "11"))
+
+
 def test_encoding_walks_gate_vector_like_simulation_rs():
     """simulation.rs:37-56: flat position -> wire = position mod n, Id skipped, order kept."""
     c = Circuit.new(3)
