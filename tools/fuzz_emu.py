@@ -22,10 +22,10 @@ NMIN, NMAX = int(os.environ.get("FUZZ_NMIN", 1)), int(os.environ.get("FUZZ_NMAX"
 def random_custom(rng, n):
     """One Custom gate of a random shape: dense unitary, permutation with phases, multi-controlled pair gate, partial
     (None on some inputs), non-unitary."""
-    k = int(rng.integers(1, min(n, 5) + 1))
+    shape = int(rng.integers(0, 6))
+    k = int(rng.integers(1, min(n, 10 if shape in (2, 5) else 5) + 1))  # structured closures may be wide
     wires = [int(w) for w in rng.permutation(n)[:k]]
     target, controls = wires[-1], wires[:-1]
-    shape = int(rng.integers(0, 5))
     dim = 1 << k
     if shape == 0:
         m = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
@@ -49,6 +49,14 @@ def random_custom(rng, n):
             v[base] = q[0, b]
             v[base + 1] = q[1, b]
             cols[base + b] = v
+    elif shape == 5:  # multi-controlled gate that fires on a random control pattern: a phased flip of the target
+        pat = int(rng.integers(0, dim >> 1)) << 1
+        ph = np.exp(1j * rng.uniform(0, 2 * np.pi, size=2))
+        cols = {}
+        for b in range(2):
+            v = np.zeros(dim, dtype=np.complex128)
+            v[pat | (b ^ 1)] = ph[b]
+            cols[pat | b] = v
     elif shape == 3:  # some inputs untouched (None), the others a dense image
         cols = {}
         for i in range(dim):
