@@ -653,8 +653,14 @@ bool plan_cache_key(const qsv_state* s, const qsv_op* ops, size_t n_ops, bool fr
         if (op.kind == QSV_GATE_CUSTOM) {
             if (!op.matrix) return false;
             const size_t dim = (size_t)1 << (op.n_controls + 1);
-            if (key.size() + dim * dim * 16 + dim > kMaxKey) return false;
-            put(op.matrix, dim * dim * 16);
+            size_t n_cols = dim;
+            if (op.iparam == 1) {  // compact columns (qsv.h): one column per sub-state with none_mask == 0
+                if (!op.none_mask) return false;
+                n_cols = 0;
+                for (size_t i = 0; i < dim; ++i) n_cols += op.none_mask[i] == 0;
+            }
+            if (key.size() + n_cols * dim * 16 + dim > kMaxKey) return false;
+            put(op.matrix, n_cols * dim * 16);
             const uint8_t has_none = op.none_mask ? 1 : 0;
             put(&has_none, 1);
             if (op.none_mask) put(op.none_mask, dim);
