@@ -162,6 +162,30 @@ def test_x3sudoko_on_device():
             assert count < 150
 
 
+@pytest.mark.parametrize("open_control", [None, 5])
+def test_wide_multi_controlled_custom_gate_on_device(open_control):
+    """multicnot::<17> (tests/grovers.rs:157-172 generalised): a Custom gate on 17 wires is passed as compact columns
+    (qsv.h, iparam = 1) and lowered to one controlled op of the fused pass - no dense round, no 13-wire limit.  Run twice:
+    the second call takes the handle's plan cache."""
+    from workloads import wide_multicnot_circuit
+    n = 17
+    c, expect = wide_multicnot_circuit(Circuit, G, st, n, open_control)
+    enc = encode_gates(c.circuit_gates, n)
+    s = qb.DeviceState(n)
+    try:
+        for _ in range(2):
+            s.init_basis(0)
+            stats = s.apply(enc)
+            amps = s.download()
+            want = np.zeros(1 << n, dtype=np.complex128)
+            for k, v in expect.items():
+                want[k] = v
+            assert np.max(np.abs(amps - want)) < TOL
+            assert stats["n_passes"] >= 1
+    finally:
+        s.close()
+
+
 def test_grovers_config1_measure_all():
     """BASELINE config 1 (examples/grovers.rs) + the assertions of tests/grovers.rs:62-69."""
     qb.seed(0)

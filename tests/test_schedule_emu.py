@@ -365,3 +365,20 @@ def test_wide_prefix_runs_as_a_plan_on_the_support_qubits(n, world, monkeypatch)
         assert np.max(np.abs(got[:len(want)] - want)) < 1e-13
         assert abs(np.sum(np.abs(want) ** 2) - 1.0) < 1e-12
         plan.close()
+
+
+@pytest.mark.parametrize("open_control", [None, 4])
+def test_wide_multicnot_compact_columns(open_control):
+    """multicnot::<15> (tests/grovers.rs:157-172 generalised): 15 wires go to the scheduler as compact columns (qsv.h,
+    iparam = 1) and come back as one controlled op - no dense round, no 13-wire limit."""
+    from workloads import wide_multicnot_circuit
+    n = 15
+    c, expect = wide_multicnot_circuit(OracleCircuit, G, st, n, open_control)
+    enc = encode_gates(c.circuit_gates, n)
+    assert enc.ops[enc.n_ops - 1].iparam == 1
+    out, desc = emu_simulate(n, enc, None, describe=True)
+    want = np.zeros(1 << n, dtype=np.complex128)
+    for k, v in expect.items():
+        want[k] = v
+    assert np.max(np.abs(out - want)) < 1e-14
+    assert all(r["type"] != 1 for p in desc["passes"] for r in p["rounds"])  # no dense round (qsv_types.h ROUND_DENSE = 1)

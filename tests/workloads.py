@@ -87,3 +87,30 @@ def grover_expected_amplitudes(info, iterations, n_probe=4096, seed=99):
         idx.append((int(i) << low) | int(j))
         exp.append(0.0)
     return am, ao, {"indices": idx, "expect": [complex(e) for e in exp]}
+
+
+def wide_multicnot_circuit(C, G, st, n, open_control=None):
+    """The reference's multicnot::<N> closure (tests/grovers.rs:157-172) on all n wires: n - 1 controls, flips the last wire
+    when every control is |1>, None otherwise.  X on the controls first (all but `open_control`), H + S on the target so
+    the flip is visible in both amplitudes.  Returns the circuit and its expected non-zero amplitudes {index: value}."""
+    def multicnot(prod):
+        q = prod.get_qubits()
+        if all(x == st.Qubit.One for x in q[:-1]):
+            return prod.clone().invert_digit(len(q) - 1).into_super_position()
+        return None
+
+    c = C.new(n)
+    for w in range(n - 1):
+        if w != open_control:
+            c.add_gate(G.X, w)
+    c.add_gate(G.H, n - 1).add_gate(G.S, n - 1)
+    c.add_gate(G.Custom(multicnot, list(range(n - 1)), "X"), n - 1)
+    base = 0
+    for w in range(n - 1):
+        if w != open_control:
+            base |= 1 << (n - 1 - w)
+    r = 0.5 ** 0.5
+    a0, a1 = r, 1j * r  # H then S on |0>
+    if open_control is None:
+        a0, a1 = a1, a0
+    return c, {base: a0, base | 1: a1}
