@@ -28,3 +28,21 @@ def test_fuzz_slice_tma_mode():
             fuzz_emu.one(seed)
     finally:
         lib.qsv_emu_set_tma_mode(0)
+
+
+def test_oracle_modes_agree_under_fuzz():
+    """The checker checked: the faithful restatement (per-gate hash-map rebuild, first-assign / then-add, None overwrite;
+    simulation.rs:64-135) and the dense one agree on the fuzzer's circuits, Custom closures with None results and
+    non-unitary images included."""
+    import numpy as np
+    from helpers import encode_gates, orc
+    for seed in range(90000, 90060):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(1, 9))
+        c = fuzz_emu.build(rng, n, int(rng.integers(1, 60)), p_custom=0.4)
+        enc = encode_gates(c.circuit_gates, n)
+        reg = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+        reg /= np.linalg.norm(reg)
+        a = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="dense")
+        b = orc.simulate(n, enc.ops, enc.n_ops, reg, mode="faithful")
+        assert np.max(np.abs(a - b)) <= 1e-11 * max(1.0, float(np.max(np.abs(a)))), seed
