@@ -287,6 +287,7 @@ struct StateHandle {  // owns the qsv_state* ; freed on drop
 
 // Gate list -> qsv_op[] exactly as simulation.rs:37-56 walks it; Custom closures are evaluated on the 2^k basis
 // states of [controls..., target] (simulation.rs:137-156) into a matrix + none mask.
+constexpr size_t kCompactCustomWires = 11;  // same threshold as the Python and Rust hosts
 struct EncodedOps {
     std::vector<qsv_op> ops;
     std::vector<std::vector<uint32_t>> controls;
@@ -314,20 +315,32 @@ inline void encode(const std::vector<Gate>& gates, size_t num_qubits, EncodedOps
         op.iparam = g.iparam;
         if (g.kind == QSV_GATE_CUSTOM) {
             const size_t k = g.controls.size() + 1, dim = (size_t)1 << k;
-            out.matrices.emplace_back(2 * dim * dim, 0.0);
+            // wide gates (multi-controlled gates such as multicnot::<N>, tests/grovers.rs:157-172) go over as compact
+            // columns: one 2^k column per sub-state the closure answered for (qsv.h, iparam = 1)
+            const bool compact = k >= kCompactCustomWires;
+            out.matrices.emplace_back(compact ? 0 : 2 * dim * dim, 0.0);
             out.masks.emplace_back(dim, 0);
             auto& m = out.matrices.back();
             auto& none = out.masks.back();
+            size_t n_cols = 0;
             for (size_t s = 0; s < dim; ++s) {
                 std::optional<SuperPosition> image = g.func(ProductState::binary_basis(s, k));
                 if (!image) { none[s] = 1; continue; }
                 if (image->get_dimension() != dim)
                     throw QuantrError("The custom gate '" + g.name + "' returned a superposition of the wrong dimension.");
+                if (compact) {
+                    if (++n_cols > 64)
+                        throw QuantrError("The custom gate '" + g.name + "' acts on " + std::to_string(k) + " wires and answers for more than 64 basis states; dense Custom gates are limited to 13 wires.");
+                    for (size_t t = 0; t < dim; ++t) { m.push_back(image->amplitudes[t].real()); m.push_back(image->amplitudes[t].imag()); }
+                    continue;
+                }
                 for (size_t t = 0; t < dim; ++t) {
                     m[(t * dim + s) * 2] = image->amplitudes[t].real();
                     m[(t * dim + s) * 2 + 1] = image->amplitudes[t].imag();
                 }
             }
+            if (compact) op.iparam = 1;
+            if (m.empty()) m.push_back(0.0);  // a closure that answers None everywhere: no column, but a non-NULL pointer
             op.matrix = m.data();
             op.none_mask = none.data();
         }

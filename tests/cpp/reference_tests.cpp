@@ -90,6 +90,28 @@ static void host_tests() {
         CHECK(throws_quantr_error([] { SuperPosition::new_with_amplitudes({0.5, 0.5}); }));
         CHECK(SuperPosition::new_with_amplitudes({0, Complex64(0, 1), 0, 0}).get_num_qubits() == 2);
     }
+    {  // wide Custom gates are encoded as compact columns (qsv.h iparam = 1): multicnot::<12>, tests/grovers.rs:157-172
+        ++g_run;
+        const size_t n = 12;
+        auto multicnot = [n](ProductState p) -> std::optional<SuperPosition> {
+            for (size_t i = 0; i + 1 < n; ++i) if (p.qubits[i] != Qubit::One) return std::nullopt;
+            p.invert_digit(n - 1);
+            return SuperPosition::from(p);
+        };
+        std::vector<uint32_t> ctrl;
+        for (uint32_t i = 0; i + 1 < n; ++i) ctrl.push_back(i);
+        std::vector<Gate> gates(n, Gate::Id());
+        gates[n - 1] = Gate::Custom(multicnot, ctrl, "X");
+        quantr::detail::EncodedOps enc;
+        quantr::detail::encode(gates, n, enc);
+        CHECK(enc.ops.size() == 1 && enc.ops[0].iparam == 1 && enc.ops[0].n_controls == n - 1 && enc.ops[0].target == n - 1);
+        const size_t dim = (size_t)1 << n;
+        CHECK(enc.matrices[0].size() == 2 * 2 * dim);  // two columns: |1..10> and |1..11>
+        size_t answered = 0;
+        for (uint8_t v : enc.masks[0]) answered += v == 0;
+        CHECK(answered == 2 && enc.masks[0][dim - 2] == 0 && enc.masks[0][dim - 1] == 0);
+        CHECK(enc.matrices[0][2 * (dim - 1)] == 1.0 && enc.matrices[0][2 * dim + 2 * (dim - 2)] == 1.0);  // images: flipped target
+    }
     {  // super_positions.rs:437-497 (hash constructors), :270-295, :315-342
         ++g_run;
         const double r = std::sqrt(0.5);
@@ -112,6 +134,22 @@ static void host_tests() {
 
 static void device_tests() {
     const Complex64 Z(0, 0), I(0, 1);
+    {  // multicnot::<12> (examples/generalised_control_not_gate.rs:24-35 at 12 wires): compact columns through qsv_apply
+        const size_t n = 12;
+        auto multicnot = [n](ProductState p) -> std::optional<SuperPosition> {
+            for (size_t i = 0; i + 1 < n; ++i) if (p.qubits[i] != Qubit::One) return std::nullopt;
+            p.invert_digit(n - 1);
+            return SuperPosition::from(p);
+        };
+        std::vector<uint32_t> ctrl;
+        std::vector<size_t> wires;
+        for (uint32_t i = 0; i + 1 < n; ++i) { ctrl.push_back(i); wires.push_back(i); }
+        Circuit c(n);
+        c.add_repeating_gate(Gate::X(), wires).add_gate(Gate::Custom(multicnot, ctrl, "X"), n - 1);
+        std::vector<Complex64> want((size_t)1 << n, Z);
+        want.back() = 1.0;
+        compare_circuit(c, want, 1e-12, "multicnot_12_compact_columns");
+    }
     { Circuit c(2); c.add_gates({Gate::H(), Gate::H()}).add_gates({Gate::S(), Gate::Sdag()});
       compare_circuit(c, {0.5, -0.5 * I, 0.5 * I, 0.5}, 1e-6, "swap_and_conjugate_gates"); }                                           // :604
     { Circuit c(2); c.add_gates({Gate::H(), Gate::H()}).add_gates({Gate::T(), Gate::Tdag()});
