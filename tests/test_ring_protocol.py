@@ -1,4 +1,4 @@
-"""Model check of the pipelined pass kernel's buffer ring (quantr_b200/csrc/pass_kernel_async.cu).
+"""Model check of the pipelined pass kernel's buffer ring (quantr_b200/csrc/pass_kernel_tma.cu; first written for its cp.async predecessor).
 
 kG compute groups consume tiles k = g, g + kG, ... from a ring of kNB shared-memory buffers (tile k lives in buffer
 k % kNB).  The consumer of tile k refills its buffer with tile k + kNB; a consumer learns that its tile has landed from
