@@ -91,3 +91,16 @@ def test_null_handles_are_rejected():
     assert lib.qsv_init_basis(None, 0) == 1
     assert lib.qsv_destroy(None) == 0
     assert lib.qsv_plan_destroy(None) == 0
+
+
+def test_plain_c_consumer(tmp_path):
+    """include/qsv.h is a C header: a C99 program (what cgo or bindgen would see) compiles against it with -pedantic,
+    links libqsv.so, finds the struct layout the bindings assume and drives the plan API and its error paths."""
+    import subprocess
+    exe = str(tmp_path / "abi_consumer")
+    libdir = os.path.join(ROOT, "quantr_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "c", "abi_consumer.c"), "-L" + libdir, "-lqsv", "-Wl,-rpath," + libdir,
+                    "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "0 failed" in out.stdout, out.stdout + out.stderr
