@@ -155,7 +155,8 @@ public:
     const std::vector<Complex64>& get_amplitudes() const { return amplitudes; }
     std::optional<Complex64> get_amplitude(size_t pos) const { return pos < amplitudes.size() ? std::optional<Complex64>(amplitudes[pos]) : std::nullopt; }
     Complex64 get_amplitude_from_state(const ProductState& p) const {  // :207
-        if (p.num_qubits() != product_dim) throw QuantrError("Unable to retreive product state, |" + p.to_string() + "> with a different dimension.");
+        if (p.num_qubits() != product_dim) throw QuantrError("Unable to retreive product state, |\"" + p.to_string() + "\"> with dimension " + std::to_string(p.num_qubits()) +
+                              ". The superposition is a linear combination of states with different dimension. These dimensions should be equal.");
         return amplitudes[p.comp_basis()];
     }
     SuperPosition& set_amplitudes(const std::vector<Complex64>& a) {  // :229

@@ -212,7 +212,7 @@ class SuperPosition:
     def get_amplitude_from_state(self, prod_state: ProductState) -> complex:  # super_positions.rs:207
         if prod_state.num_qubits() != self.product_dim:
             raise QuantrError(
-                f"Unable to retreive product state, |{prod_state}> with dimension {prod_state.num_qubits()}. "
+                f"Unable to retreive product state, |\"{prod_state.to_string()}\"> with dimension {prod_state.num_qubits()}. "  # ({:?} of a String: quoted)
                 f"The superposition is a linear combination of states with different dimension. These dimensions should be equal."
             )
         return complex(self.amplitudes[prod_state.comp_basis()])
